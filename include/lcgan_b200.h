@@ -1,0 +1,144 @@
+/* lcgan_b200 C ABI  --  the drop-in boundary for the LC-GAN training hot path on B200 (sm_100a).
+ *
+ * The reference (rakutentech/lcgan) has no FFI of its own: its hot path is PyTorch library calls
+ * made from custom_layers.py / cnn.py / loss.py.  Each entry point below replaces one of those
+ * library call sites (cited per function as reference file:line).  The host side
+ * (lcgan_b200/ops.py) wraps them in torch.autograd.Functions; INTEGRATION.md shows the ctypes
+ * binding.  Conventions:
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless stated otherwise;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never synchronises
+ *     the device, never allocates or frees device memory (workspaces are caller-provided);
+ *   - returns 0 on success, non-zero on error; lcgan_last_error() returns a message for the
+ *     calling thread;
+ *   - dtype codes: 0 = float32, 1 = bfloat16.
+ */
+#ifndef LCGAN_B200_H
+#define LCGAN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LCGAN_F32 0
+#define LCGAN_BF16 1
+#define LCGAN_MAX_TAPS 9
+
+/* A "tap convolution": the one contraction every conv / transposed conv / linear layer and their
+ * data- and weight-gradients reduce to.
+ *
+ *   for a lattice point (b, m, n), m < MH, n < MW:
+ *     out pixel (oy, ox) = (m*os + py, n*os + px)
+ *     acc[o] = sum_t sum_c  X[b, m*is + dy[t], n*is + dx[t], c] * W2[o][wtap[t]*Cin + c]
+ *     Y[b, oy, ox, o] = lrelu(acc[o]*rowscale[b,o] + bias[o]*bias_scale, slope) * gain + R[b,oy,ox,o]
+ *   out-of-range input pixels read as zero.
+ *
+ * X and Y are addressed with explicit element strides, so NCHW fp32 images and channels-last bf16
+ * activations go through the same descriptor.
+ */
+typedef struct lcgan_tapconv {
+  int32_t N, IH, IW, Cin;          /* input tensor  */
+  int32_t OH, OW, Cout;            /* output tensor */
+  int64_t xs_n, xs_h, xs_w, xs_c;  /* input element strides  */
+  int64_t ys_n, ys_h, ys_w, ys_c;  /* output (and residual) element strides */
+  int32_t x_dtype, y_dtype, w_dtype;
+  int32_t MH, MW;                  /* lattice extent */
+  int32_t os, py, px;              /* lattice -> output pixel */
+  int32_t is;                      /* lattice -> input pixel stride */
+  int32_t ntaps;
+  int32_t dy[LCGAN_MAX_TAPS], dx[LCGAN_MAX_TAPS], wtap[LCGAN_MAX_TAPS];
+  int64_t w_ld;                    /* row stride (elements) of W2[Cout][w_ld] */
+  float bias_scale, slope, gain;   /* slope = 1 -> no activation */
+} lcgan_tapconv;
+
+const char* lcgan_last_error(void);
+int lcgan_version(void);
+/* 1 if the tcgen05 path can take this descriptor (channels-last bf16, Cin%64==0, ...) */
+int lcgan_tapconv_tc_eligible(const lcgan_tapconv* d);
+
+/* Forward-type tap conv on CUDA cores (any strides/dtypes; fp32 accumulate).
+ * Replaces F.conv2d / F.conv_transpose2d / F.linear call sites (custom_layers.py:25,41,43,78,83)
+ * and their autograd data-gradients.  rowscale [N,Cout] f32, bias [Cout] f32, residual like Y;
+ * each may be NULL. */
+int lcgan_tapconv_simt(const lcgan_tapconv* d, const void* x, const void* w2, void* y,
+                       const float* rowscale, const float* bias, const void* residual, void* stream);
+
+/* Same contraction on the 5th-gen tensor cores: tcgen05.mma, TMEM accumulators, TMA-fed operands
+ * (bf16 channels-last X, bf16 W2, Cin % 64 == 0).  Y may be bf16 or f32 channels-last. */
+int lcgan_tapconv_tc(const lcgan_tapconv* d, const void* x, const void* w2, void* y,
+                     const float* rowscale, const float* bias, const void* residual, void* stream);
+
+/* Weight gradient of the same contraction (autograd of custom_layers.py:41,43,78,83,25):
+ *   dW2[o][wtap[t]*Cin + c] += scale * sum_{b,m,n} G[b, m*os+py, n*os+px, o] * X[b, m*is+dy[t], n*is+dx[t], c]
+ * G is addressed with the descriptor's Y strides/dtype.  dW2 is f32 [Cout][w_ld], accumulated into
+ * (caller zeroes it). */
+int lcgan_tapconv_wgrad_simt(const lcgan_tapconv* d, const void* x, const void* g, float* dw2,
+                             float scale, void* stream);
+int lcgan_tapconv_wgrad_tc(const lcgan_tapconv* d, const void* x, const void* g, float* dw2,
+                           float scale, void* stream);
+
+/* ---- memory-bound kernels; tensors are dense channels-last [N,H,W,C] of dtype `dt` ---------- */
+
+/* out = post(box3(pre(a)))  (F.avg_pool2d(3,1,1), custom_layers.py:137,197, fused with the
+ * neighbouring leaky-relu*gain of :155,205 or with its backward mask).
+ * pre(a) = a * (mask > 0 ? pre_gain : pre_gain*pre_slope) when mask != NULL, else a.
+ * post(v) = (v > 0 ? v : v*post_slope) * post_gain. */
+int lcgan_box3(const void* a, const void* mask, void* out, int dt, int N, int H, int W, int C,
+               float pre_slope, float pre_gain, float post_slope, float post_gain, void* stream);
+
+/* y[b,i,j,c] = scale * sum_{2x2} x[b,2i+a,2j+b,c]   (F.avg_pool2d(2,2), custom_layers.py:202; scale=.25) */
+int lcgan_pool2(const void* x, void* y, int dt, int N, int H, int W, int C, float scale, void* stream);
+/* y[b,2i+a,2j+b,c] = scale * x[b,i,j,c]   (F.interpolate nearest x2, custom_layers.py:146; adjoint of pool2) */
+int lcgan_up2(const void* x, void* y, int dt, int N, int H, int W, int C, float scale, void* stream);
+/* out = box3(nearest_up2(s)) + t   (custom_layers.py:146-147,159); s [N,H,W,C], t/out [N,2H,2W,C] */
+int lcgan_up2box_add(const void* s, const void* t, void* out, int dt, int N, int H, int W, int C, void* stream);
+
+/* Backward of the fused epilogue  y = lrelu(acc*d + bias)*gain:
+ *   dz = dy * gain * (y > 0 ? 1 : slope);  gout = dz * d[b,c] (d may be NULL)
+ *   r0[b,c] += sum_p dz;   r1[b,c] += sum_p dz * z,  z = y/gain (y>0) or y/(gain*slope)
+ * r0/r1 (f32, caller-zeroed) may be NULL.  dy/y/gout are [N,P,C] channels-last. */
+int lcgan_act_bwd(const void* dy, const void* y, void* gout, const float* d, float* r0, float* r1,
+                  int dt, int N, int P, int C, float slope, float gain, void* stream);
+
+/* xs[b,p,c] = x[b,p,c] * s[b,c]   (style modulation, custom_layers.py:62-64, shared-weight form) */
+int lcgan_modulate(const void* x, const float* s, void* xs, int dt, int N, int P, int C, void* stream);
+/* dx = t * s ; ds[b,c] += sum_p x*t */
+int lcgan_modulate_bwd(const void* x, const void* t, const float* s, void* dx, float* ds,
+                       int dt, int N, int P, int C, void* stream);
+
+/* Flow warp (custom_layers.py:127-134,151,161-165): grid = linspace coords + tanh(flow)*scale,
+ * bicubic (A=-0.75), zeros padding, align_corners=False.  x/out [N,H,W,C] dt; flow [N,H,W,2] f32
+ * (pre-tanh). */
+int lcgan_warp_fwd(const void* x, const float* flow, void* out, int dt, int N, int H, int W, int C,
+                   float flow_scale, void* stream);
+/* dx_acc [N,H,W,C] f32 (caller-zeroed, atomically accumulated); dflow [N,H,W,2] f32 (written). */
+int lcgan_warp_bwd(const void* x, const float* flow, const void* dout, float* dx_acc, float* dflow,
+                   int dt, int N, int H, int W, int C, float flow_scale, void* stream);
+
+/* dtype/layout conversion out = (T_out) in, both dense with the same element order */
+int lcgan_cast(const void* in, void* out, int dt_in, int dt_out, int64_t n, void* stream);
+
+/* ---- loss reductions ---------------------------------------------------------------------- */
+/* y = x / max(||x||_2, 1e-12) per row (F.normalize, cnn.py:40-41); x,y [B,D] f32; inv_norm [B] out */
+int lcgan_l2norm_fwd(const float* x, float* y, float* inv_norm, int B, int D, void* stream);
+int lcgan_l2norm_bwd(const float* y, const float* inv_norm, const float* dy, float* dx, int B, int D, void* stream);
+/* per-sample InfoNCE with one negative (loss.py:9-15): l[b] = softplus((a.n - a.p)/tau);
+ * sig[b] = sigmoid((a.n - a.p)/tau) kept for backward. */
+int lcgan_contrastive_fwd(const float* a, const float* p, const float* n, float* l, float* sig,
+                          int B, int D, float tau, void* stream);
+int lcgan_contrastive_bwd(const float* a, const float* p, const float* n, const float* sig,
+                          const float* dl, float* da, float* dp, float* dn, int B, int D, float tau, void* stream);
+/* out[b] = sum_i x[b,i]^2   (R1, loss.py:21-23); x [B,L] f32 */
+int lcgan_sumsq(const float* x, float* out, int B, int64_t L, void* stream);
+/* y[b,i] = x[b,i] * s[b]  (backward of sumsq) */
+int lcgan_rowscale(const float* x, const float* s, float* y, int B, int64_t L, void* stream);
+
+/* multi-tensor EMA (ema.py:26-32): dst = src + decay*(dst - src) over n contiguous f32 spans */
+int lcgan_ema_lerp(float* const* dst, const float* const* src, const int64_t* numel, int n,
+                   float decay, void* stream); /* dst/src/numel are DEVICE arrays of length n */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,124 @@
+"""ctypes binding of liblcgan_b200.so (the C ABI declared in include/lcgan_b200.h).
+
+The library is loaded lazily at module level and never stored on an nn.Module, so modules stay
+picklable (worker.py:40 deep-copies a DDP-wrapped generator).  There is no CPU fallback: if the
+shared library is missing, every op raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liblcgan_b200.so")
+_SRCS = ["api.cu", "conv_simt.cu", "conv_tc.cu", "resample.cu", "warp.cu", "loss.cu"]
+_lock = threading.Lock()
+_lib = None
+
+F32, BF16 = 0, 1
+MAX_TAPS = 9
+
+
+class TapConvDesc(C.Structure):
+    """Mirror of `struct lcgan_tapconv` (include/lcgan_b200.h)."""
+    _fields_ = [
+        ("N", C.c_int32), ("IH", C.c_int32), ("IW", C.c_int32), ("Cin", C.c_int32),
+        ("OH", C.c_int32), ("OW", C.c_int32), ("Cout", C.c_int32),
+        ("xs_n", C.c_int64), ("xs_h", C.c_int64), ("xs_w", C.c_int64), ("xs_c", C.c_int64),
+        ("ys_n", C.c_int64), ("ys_h", C.c_int64), ("ys_w", C.c_int64), ("ys_c", C.c_int64),
+        ("x_dtype", C.c_int32), ("y_dtype", C.c_int32), ("w_dtype", C.c_int32),
+        ("MH", C.c_int32), ("MW", C.c_int32),
+        ("os", C.c_int32), ("py", C.c_int32), ("px", C.c_int32),
+        ("is_", C.c_int32),
+        ("ntaps", C.c_int32),
+        ("dy", C.c_int32 * MAX_TAPS), ("dx", C.c_int32 * MAX_TAPS), ("wtap", C.c_int32 * MAX_TAPS),
+        ("w_ld", C.c_int64),
+        ("bias_scale", C.c_float), ("slope", C.c_float), ("gain", C.c_float),
+    ]
+
+
+def build(verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into lcgan_b200/liblcgan_b200.so (nvcc cross-compiles
+    without a GPU)."""
+    src_dir = os.path.join(_HERE, "csrc")
+    srcs = [os.path.join(src_dir, s) for s in _SRCS]
+    deps = srcs + [os.path.join(src_dir, f) for f in os.listdir(src_dir) if f.endswith(".cuh")]
+    deps.append(os.path.join(os.path.dirname(_HERE), "include", "lcgan_b200.h"))
+    if os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps):
+        return _SO
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+           "-Xcompiler", "-fPIC", "-shared", "-o", _SO] + srcs
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return _SO
+
+
+_VOIDP = C.c_void_p
+_FP = C.c_void_p   # float* passed as raw address
+_SIGS = {
+    "lcgan_version": ([], C.c_int),
+    "lcgan_tapconv_tc_eligible": ([C.POINTER(TapConvDesc)], C.c_int),
+    "lcgan_tapconv_simt": ([C.POINTER(TapConvDesc), _VOIDP, _VOIDP, _VOIDP, _FP, _FP, _VOIDP, _VOIDP], C.c_int),
+    "lcgan_tapconv_tc": ([C.POINTER(TapConvDesc), _VOIDP, _VOIDP, _VOIDP, _FP, _FP, _VOIDP, _VOIDP], C.c_int),
+    "lcgan_tapconv_wgrad_simt": ([C.POINTER(TapConvDesc), _VOIDP, _VOIDP, _FP, C.c_float, _VOIDP], C.c_int),
+    "lcgan_tapconv_wgrad_tc": ([C.POINTER(TapConvDesc), _VOIDP, _VOIDP, _FP, C.c_float, _VOIDP], C.c_int),
+    "lcgan_box3": ([_VOIDP, _VOIDP, _VOIDP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                    C.c_float, C.c_float, C.c_float, C.c_float, _VOIDP], C.c_int),
+    "lcgan_pool2": ([_VOIDP, _VOIDP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _VOIDP], C.c_int),
+    "lcgan_up2": ([_VOIDP, _VOIDP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _VOIDP], C.c_int),
+    "lcgan_up2box_add": ([_VOIDP, _VOIDP, _VOIDP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _VOIDP], C.c_int),
+    "lcgan_act_bwd": ([_VOIDP, _VOIDP, _VOIDP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int,
+                       C.c_float, C.c_float, _VOIDP], C.c_int),
+    "lcgan_modulate": ([_VOIDP, _FP, _VOIDP, C.c_int, C.c_int, C.c_int, C.c_int, _VOIDP], C.c_int),
+    "lcgan_modulate_bwd": ([_VOIDP, _VOIDP, _FP, _VOIDP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, _VOIDP], C.c_int),
+    "lcgan_warp_fwd": ([_VOIDP, _FP, _VOIDP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _VOIDP], C.c_int),
+    "lcgan_warp_bwd": ([_VOIDP, _FP, _VOIDP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                        C.c_float, _VOIDP], C.c_int),
+    "lcgan_cast": ([_VOIDP, _VOIDP, C.c_int, C.c_int, C.c_int64, _VOIDP], C.c_int),
+    "lcgan_l2norm_fwd": ([_FP, _FP, _FP, C.c_int, C.c_int, _VOIDP], C.c_int),
+    "lcgan_l2norm_bwd": ([_FP, _FP, _FP, _FP, C.c_int, C.c_int, _VOIDP], C.c_int),
+    "lcgan_contrastive_fwd": ([_FP, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_float, _VOIDP], C.c_int),
+    "lcgan_contrastive_bwd": ([_FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_float, _VOIDP], C.c_int),
+    "lcgan_sumsq": ([_FP, _FP, C.c_int, C.c_int64, _VOIDP], C.c_int),
+    "lcgan_rowscale": ([_FP, _FP, _FP, C.c_int, C.c_int64, _VOIDP], C.c_int),
+    "lcgan_ema_lerp": ([_VOIDP, _VOIDP, _VOIDP, C.c_int, C.c_float, _VOIDP], C.c_int),
+}
+EXPORTS = tuple(_SIGS) + ("lcgan_last_error",)
+
+
+def lib():
+    """The loaded library (raises if it has not been built)."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(_SO):
+                    raise RuntimeError(
+                        f"{_SO} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(lcgan_b200 has no CPU fallback)")
+                l = C.CDLL(_SO)
+                for name, (args, res) in _SIGS.items():
+                    fn = getattr(l, name)
+                    fn.argtypes, fn.restype = args, res
+                l.lcgan_last_error.argtypes, l.lcgan_last_error.restype = [], C.c_char_p
+                _lib = l
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (code {rc}): {lib().lcgan_last_error().decode()}")
+
+
+# launch counter: bench.py reports how many of OUR kernels ran inside the timed region
+launches = 0
+
+
+def call(name: str, *args):
+    global launches
+    launches += 1
+    check(getattr(lib(), name)(*args), name)

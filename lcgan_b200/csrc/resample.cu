@@ -1,0 +1,404 @@
+// Memory-bound kernels on dense channels-last tensors: box filter (+fused activation / mask),
+// 2x2 pool, nearest x2, skip-path upsample, epilogue backward, style modulation, casts.
+// One thread handles one 16-byte channel vector of one pixel (V=1 fallback for odd C), so a warp
+// reads/writes contiguous 512-byte runs along the channel-innermost axis.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+template <typename T, int V>
+__device__ __forceinline__ void ldv(const T* p, float* f) {
+  if constexpr (V == 1) {
+    f[0] = ldf(p);
+  } else {
+    Vec16<T> v; v.load(p); v.unpack(f);
+  }
+}
+template <typename T, int V>
+__device__ __forceinline__ void stv(T* p, const float* f) {
+  if constexpr (V == 1) {
+    stf(p, f[0]);
+  } else {
+    Vec16<T> v; v.pack(f); v.store(p);
+  }
+}
+
+inline int grid_for(int64_t n) {
+  int64_t b = (n + kThreads - 1) / kThreads;
+  const int64_t cap = 148LL * 64;   // grid-stride beyond 64 CTAs per SM
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+// ------------------------------------------------------------------------------------------
+template <typename T, int V>
+__global__ void __launch_bounds__(kThreads)
+box3_kernel(const T* __restrict__ a, const T* __restrict__ mask, T* __restrict__ out, int N, int H,
+            int W, int C, float pre_slope, float pre_gain, float post_slope, float post_gain) {
+  const int cv = C / V;
+  const int64_t total = (int64_t)N * H * W * cv;
+  for (int64_t idx = blockIdx.x * (int64_t)kThreads + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * kThreads) {
+    const int c = (int)(idx % cv) * V;
+    int64_t p = idx / cv;
+    const int x = (int)(p % W); p /= W;
+    const int y = (int)(p % H);
+    const int b = (int)(p / H);
+    float acc[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int yy = y + dy;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int xx = x + dx;
+        if (xx < 0 || xx >= W) continue;
+        const int64_t off = (((int64_t)b * H + yy) * W + xx) * C + c;
+        float f[V];
+        ldv<T, V>(a + off, f);
+        if (mask) {
+          float m[V];
+          ldv<T, V>(mask + off, m);
+#pragma unroll
+          for (int i = 0; i < V; ++i) f[i] *= (m[i] > 0.f ? pre_gain : pre_gain * pre_slope);
+        }
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] += f[i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float v = acc[i] * (1.f / 9.f);
+      acc[i] = (v > 0.f ? v : v * post_slope) * post_gain;
+    }
+    stv<T, V>(out + idx * V, acc);
+  }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(kThreads)
+pool2_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, float scale) {
+  const int cv = C / V, OH = H / 2, OW = W / 2;
+  const int64_t total = (int64_t)N * OH * OW * cv;
+  for (int64_t idx = blockIdx.x * (int64_t)kThreads + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * kThreads) {
+    const int c = (int)(idx % cv) * V;
+    int64_t p = idx / cv;
+    const int ox = (int)(p % OW); p /= OW;
+    const int oy = (int)(p % OH);
+    const int b = (int)(p / OH);
+    float acc[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        float f[V];
+        ldv<T, V>(x + (((int64_t)b * H + 2 * oy + dy) * W + 2 * ox + dx) * C + c, f);
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] += f[i];
+      }
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] *= scale;
+    stv<T, V>(y + idx * V, acc);
+  }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(kThreads)
+up2_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, float scale) {
+  const int cv = C / V, OH = H * 2, OW = W * 2;
+  const int64_t total = (int64_t)N * OH * OW * cv;
+  for (int64_t idx = blockIdx.x * (int64_t)kThreads + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * kThreads) {
+    const int c = (int)(idx % cv) * V;
+    int64_t p = idx / cv;
+    const int ox = (int)(p % OW); p /= OW;
+    const int oy = (int)(p % OH);
+    const int b = (int)(p / OH);
+    float f[V];
+    ldv<T, V>(x + (((int64_t)b * H + oy / 2) * W + ox / 2) * C + c, f);
+#pragma unroll
+    for (int i = 0; i < V; ++i) f[i] *= scale;
+    stv<T, V>(y + idx * V, f);
+  }
+}
+
+// out = box3(nearest_up2(s)) + t ; s [N,H,W,C] -> out [N,2H,2W,C]
+template <typename T, int V>
+__global__ void __launch_bounds__(kThreads)
+up2box_add_kernel(const T* __restrict__ s, const T* __restrict__ t, T* __restrict__ out, int N, int H,
+                  int W, int C) {
+  const int cv = C / V, OH = H * 2, OW = W * 2;
+  const int64_t total = (int64_t)N * OH * OW * cv;
+  for (int64_t idx = blockIdx.x * (int64_t)kThreads + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * kThreads) {
+    const int c = (int)(idx % cv) * V;
+    int64_t p = idx / cv;
+    const int ox = (int)(p % OW); p /= OW;
+    const int oy = (int)(p % OH);
+    const int b = (int)(p / OH);
+    // the 3x3 window on the x2 grid covers at most 2 low-res rows/cols with weights (2,1) or (1,2)
+    const int y0 = (oy - 1) >> 1, y1 = (oy + 1) >> 1;   // oy-1 may be -1 -> y0 = -1 (arith shift)
+    const int x0 = (ox - 1) >> 1, x1 = (ox + 1) >> 1;
+    const float wy0 = (oy & 1) ? 2.f : 1.f, wy1 = (oy & 1) ? 1.f : 2.f;
+    const float wx0 = (ox & 1) ? 2.f : 1.f, wx1 = (ox & 1) ? 1.f : 2.f;
+    float acc[V];
+    ldv<T, V>(t + idx * V, acc);
+    const int ys[2] = {y0, y1};
+    const int xs[2] = {x0, x1};
+    const float wys[2] = {wy0, wy1};
+    const float wxs[2] = {wx0, wx1};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (ys[j] < 0 || ys[j] >= H) continue;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        if (xs[i] < 0 || xs[i] >= W) continue;
+        float f[V];
+        ldv<T, V>(s + (((int64_t)b * H + ys[j]) * W + xs[i]) * C + c, f);
+        const float wgt = wys[j] * wxs[i] * (1.f / 9.f);
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] += f[k] * wgt;
+      }
+    }
+    stv<T, V>(out + idx * V, acc);
+  }
+}
+
+// Epilogue backward with per-(b,c) reductions.  Block = (pixel chunk, b); threads along channels
+// first so loads coalesce; each thread owns one channel vector, keeps V partial sums over its
+// pixels and finishes with one atomic per (b,c).
+template <typename T, int V>
+__global__ void __launch_bounds__(kThreads)
+act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ gout,
+               const float* __restrict__ d, float* __restrict__ r0, float* __restrict__ r1, int P, int C,
+               float slope, float gain, int pix_per_block) {
+  const int cv = C / V;
+  const int b = blockIdx.y;
+  const int p_begin = blockIdx.x * pix_per_block;
+  const int p_end = min(P, p_begin + pix_per_block);
+  const float inv_pos = 1.f / gain, inv_neg = 1.f / (gain * slope);
+  for (int cg = 0; cg < cv; cg += kThreads) {
+    const int ncv = min(kThreads, cv - cg);
+    const int lanes = kThreads / ncv;          // pixels processed per block iteration
+    if ((int)threadIdx.x >= lanes * ncv) continue;
+    const int c = (cg + (int)threadIdx.x % ncv) * V;
+    float s0[V], s1[V], dd[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) { s0[i] = 0.f; s1[i] = 0.f; dd[i] = d ? d[(int64_t)b * C + c + i] : 1.f; }
+    for (int p = p_begin + threadIdx.x / ncv; p < p_end; p += lanes) {
+      const int64_t off = ((int64_t)b * P + p) * C + c;
+      float g[V], yy[V];
+      ldv<T, V>(dy + off, g);
+      ldv<T, V>(y + off, yy);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const bool pos = yy[i] > 0.f;
+        const float dz = g[i] * (pos ? gain : gain * slope);
+        s0[i] += dz;
+        s1[i] += dz * yy[i] * (pos ? inv_pos : inv_neg);
+        g[i] = dz * dd[i];
+      }
+      stv<T, V>(gout + off, g);
+    }
+    if (r0) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) atomicAdd(r0 + (int64_t)b * C + c + i, s0[i]);
+    }
+    if (r1) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) atomicAdd(r1 + (int64_t)b * C + c + i, s1[i]);
+    }
+  }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(kThreads)
+modulate_kernel(const T* __restrict__ x, const float* __restrict__ s, T* __restrict__ xs, int N, int P, int C) {
+  const int cv = C / V;
+  const int64_t total = (int64_t)N * P * cv;
+  for (int64_t idx = blockIdx.x * (int64_t)kThreads + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * kThreads) {
+    const int c = (int)(idx % cv) * V;
+    const int b = (int)(idx / ((int64_t)P * cv));
+    float f[V];
+    ldv<T, V>(x + idx * V, f);
+#pragma unroll
+    for (int i = 0; i < V; ++i) f[i] *= s[(int64_t)b * C + c + i];
+    stv<T, V>(xs + idx * V, f);
+  }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(kThreads)
+modulate_bwd_kernel(const T* __restrict__ x, const T* __restrict__ t, const float* __restrict__ s,
+                    T* __restrict__ dx, float* __restrict__ ds, int P, int C, int pix_per_block) {
+  const int cv = C / V;
+  const int b = blockIdx.y;
+  const int p_begin = blockIdx.x * pix_per_block;
+  const int p_end = min(P, p_begin + pix_per_block);
+  for (int cg = 0; cg < cv; cg += kThreads) {
+    const int ncv = min(kThreads, cv - cg);
+    const int lanes = kThreads / ncv;
+    if ((int)threadIdx.x >= lanes * ncv) continue;
+    const int c = (cg + (int)threadIdx.x % ncv) * V;
+    float acc[V], ss[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) { acc[i] = 0.f; ss[i] = s[(int64_t)b * C + c + i]; }
+    for (int p = p_begin + threadIdx.x / ncv; p < p_end; p += lanes) {
+      const int64_t off = ((int64_t)b * P + p) * C + c;
+      float xv[V], tv[V];
+      ldv<T, V>(x + off, xv);
+      ldv<T, V>(t + off, tv);
+#pragma unroll
+      for (int i = 0; i < V; ++i) { acc[i] += xv[i] * tv[i]; tv[i] *= ss[i]; }
+      stv<T, V>(dx + off, tv);
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) atomicAdd(ds + (int64_t)b * C + c + i, acc[i]);
+  }
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(kThreads) cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
+    stf(out + i, ldf(in + i));
+}
+
+template <typename T> constexpr int vec_of() { return Vec16<T>::N; }
+
+// dispatch on dtype and on whether C admits 16-byte vectors
+#define DISPATCH_TV(dt, C, CALL)                                          \
+  do {                                                                    \
+    if ((dt) == LCGAN_F32) {                                              \
+      if ((C) % 4 == 0) { CALL(float, 4); } else { CALL(float, 1); }      \
+    } else if ((dt) == LCGAN_BF16) {                                      \
+      if ((C) % 8 == 0) { CALL(bf16, 8); } else { CALL(bf16, 1); }        \
+    } else {                                                              \
+      lcgan_set_error("bad dtype code %d", (int)(dt));                    \
+      return 1;                                                           \
+    }                                                                     \
+  } while (0)
+
+}  // namespace
+
+extern "C" int lcgan_box3(const void* a, const void* mask, void* out, int dt, int N, int H, int W, int C,
+                          float pre_slope, float pre_gain, float post_slope, float post_gain, void* stream) {
+  LCGAN_CHECK(a && out && N > 0 && H > 0 && W > 0 && C > 0, "box3: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+#define CALL(T, V)                                                                              \
+  box3_kernel<T, V><<<grid_for((int64_t)N * H * W * (C / V)), kThreads, 0, s>>>(                \
+      (const T*)a, (const T*)mask, (T*)out, N, H, W, C, pre_slope, pre_gain, post_slope, post_gain)
+  DISPATCH_TV(dt, C, CALL);
+#undef CALL
+  LCGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int lcgan_pool2(const void* x, void* y, int dt, int N, int H, int W, int C, float scale, void* stream) {
+  LCGAN_CHECK(x && y && N > 0 && H > 0 && W > 0 && C > 0 && H % 2 == 0 && W % 2 == 0, "pool2: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+#define CALL(T, V)                                                                              \
+  pool2_kernel<T, V><<<grid_for((int64_t)N * (H / 2) * (W / 2) * (C / V)), kThreads, 0, s>>>(   \
+      (const T*)x, (T*)y, N, H, W, C, scale)
+  DISPATCH_TV(dt, C, CALL);
+#undef CALL
+  LCGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int lcgan_up2(const void* x, void* y, int dt, int N, int H, int W, int C, float scale, void* stream) {
+  LCGAN_CHECK(x && y && N > 0 && H > 0 && W > 0 && C > 0, "up2: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+#define CALL(T, V)                                                                              \
+  up2_kernel<T, V><<<grid_for((int64_t)N * H * W * 4 * (C / V)), kThreads, 0, s>>>(             \
+      (const T*)x, (T*)y, N, H, W, C, scale)
+  DISPATCH_TV(dt, C, CALL);
+#undef CALL
+  LCGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int lcgan_up2box_add(const void* sk, const void* t, void* out, int dt, int N, int H, int W, int C,
+                                void* stream) {
+  LCGAN_CHECK(sk && t && out && N > 0 && H > 0 && W > 0 && C > 0, "up2box_add: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+#define CALL(T, V)                                                                              \
+  up2box_add_kernel<T, V><<<grid_for((int64_t)N * H * W * 4 * (C / V)), kThreads, 0, s>>>(      \
+      (const T*)sk, (const T*)t, (T*)out, N, H, W, C)
+  DISPATCH_TV(dt, C, CALL);
+#undef CALL
+  LCGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+static inline int pix_per_block_for(int N, int P) {
+  // aim for ~8 CTAs per SM overall, at least 64 pixels per block
+  int64_t want_blocks = 148LL * 8;
+  int64_t per_b = (want_blocks + N - 1) / N;
+  int ppb = (int)((P + per_b - 1) / per_b);
+  if (ppb < 64) ppb = 64;
+  return ppb;
+}
+
+extern "C" int lcgan_act_bwd(const void* dy, const void* y, void* gout, const float* d, float* r0, float* r1,
+                             int dt, int N, int P, int C, float slope, float gain, void* stream) {
+  LCGAN_CHECK(dy && y && gout && N > 0 && P > 0 && C > 0, "act_bwd: bad arguments");
+  LCGAN_CHECK(slope > 0.f && gain > 0.f, "act_bwd: slope and gain must be positive");
+  LCGAN_CHECK(N <= 65535, "act_bwd: batch too large");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int ppb = pix_per_block_for(N, P);
+  dim3 grid(ceil_div(P, ppb), N);
+#define CALL(T, V)                                                                              \
+  act_bwd_kernel<T, V><<<grid, kThreads, 0, s>>>((const T*)dy, (const T*)y, (T*)gout, d, r0, r1, P, C, \
+                                                 slope, gain, ppb)
+  DISPATCH_TV(dt, C, CALL);
+#undef CALL
+  LCGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int lcgan_modulate(const void* x, const float* sc, void* xs, int dt, int N, int P, int C, void* stream) {
+  LCGAN_CHECK(x && sc && xs && N > 0 && P > 0 && C > 0, "modulate: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+#define CALL(T, V)                                                                              \
+  modulate_kernel<T, V><<<grid_for((int64_t)N * P * (C / V)), kThreads, 0, s>>>((const T*)x, sc, (T*)xs, N, P, C)
+  DISPATCH_TV(dt, C, CALL);
+#undef CALL
+  LCGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int lcgan_modulate_bwd(const void* x, const void* t, const float* sc, void* dx, float* ds, int dt,
+                                  int N, int P, int C, void* stream) {
+  LCGAN_CHECK(x && t && sc && dx && ds && N > 0 && P > 0 && C > 0, "modulate_bwd: bad arguments");
+  LCGAN_CHECK(N <= 65535, "modulate_bwd: batch too large");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int ppb = pix_per_block_for(N, P);
+  dim3 grid(ceil_div(P, ppb), N);
+#define CALL(T, V)                                                                              \
+  modulate_bwd_kernel<T, V><<<grid, kThreads, 0, s>>>((const T*)x, (const T*)t, sc, (T*)dx, ds, P, C, ppb)
+  DISPATCH_TV(dt, C, CALL);
+#undef CALL
+  LCGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int lcgan_cast(const void* in, void* out, int dt_in, int dt_out, int64_t n, void* stream) {
+  LCGAN_CHECK(in && out && n >= 0, "cast: bad arguments");
+  if (n == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int g = grid_for(n);
+  if (dt_in == LCGAN_F32 && dt_out == LCGAN_BF16) cast_kernel<float, bf16><<<g, kThreads, 0, s>>>((const float*)in, (bf16*)out, n);
+  else if (dt_in == LCGAN_BF16 && dt_out == LCGAN_F32) cast_kernel<bf16, float><<<g, kThreads, 0, s>>>((const bf16*)in, (float*)out, n);
+  else if (dt_in == LCGAN_F32 && dt_out == LCGAN_F32) cast_kernel<float, float><<<g, kThreads, 0, s>>>((const float*)in, (float*)out, n);
+  else if (dt_in == LCGAN_BF16 && dt_out == LCGAN_BF16) cast_kernel<bf16, bf16><<<g, kThreads, 0, s>>>((const bf16*)in, (bf16*)out, n);
+  else { lcgan_set_error("cast: bad dtype codes %d -> %d", dt_in, dt_out); return 1; }
+  LCGAN_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,218 @@
+// Flow warp of SynthesisBlock (reference custom_layers.py:127-134,151,161-165):
+//   grid = linspace(-1,1) coordinates + tanh(flow) * max_flow_scale
+//   out  = grid_sample(x, grid, mode='bicubic', padding_mode='zeros', align_corners=False)
+// tanh, coordinate generation and the 16-tap bicubic gather are one kernel; the backward produces
+// the feature gradient (vector atomics into an fp32 accumulator) and the flow gradient (warp-shuffle
+// reduction over channels) in one pass.  A group of G lanes (G = min(32, C/V)) owns one pixel and
+// strides over its 16-byte channel vectors, so every gather tap is a contiguous run.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr float kA = -0.75f;
+
+__device__ __forceinline__ float cub_near(float u) { return ((kA + 2.f) * u - (kA + 3.f)) * u * u + 1.f; }
+__device__ __forceinline__ float cub_far(float u) { return ((kA * u - 5.f * kA) * u + 8.f * kA) * u - 4.f * kA; }
+__device__ __forceinline__ float dcub_near(float u) { return (3.f * (kA + 2.f) * u - 2.f * (kA + 3.f)) * u; }
+__device__ __forceinline__ float dcub_far(float u) { return (3.f * kA * u - 10.f * kA) * u + 8.f * kA; }
+
+__device__ __forceinline__ void cubic_w(float t, float* w) {
+  w[0] = cub_far(t + 1.f); w[1] = cub_near(t); w[2] = cub_near(1.f - t); w[3] = cub_far(2.f - t);
+}
+__device__ __forceinline__ void cubic_dw(float t, float* w) {
+  w[0] = dcub_far(t + 1.f); w[1] = dcub_near(t); w[2] = -dcub_near(1.f - t); w[3] = -dcub_far(2.f - t);
+}
+
+struct PixCoord {
+  int x0, y0;       // floor of the source index
+  float tx, ty;     // fractional parts
+  float th0, th1;   // tanh(flow)
+};
+
+__device__ __forceinline__ PixCoord source_index(const float* __restrict__ flow, int64_t pix, int h, int w,
+                                                 int H, int W, float scale) {
+  PixCoord pc;
+  const float2 f = *reinterpret_cast<const float2*>(flow + pix * 2);
+  pc.th0 = tanhf(f.x);
+  pc.th1 = tanhf(f.y);
+  const float gx = (2.f * (float)w / (float)(W - 1) - 1.f) + pc.th0 * scale;
+  const float gy = (2.f * (float)h / (float)(H - 1) - 1.f) + pc.th1 * scale;
+  const float ix = ((gx + 1.f) * (float)W - 1.f) * 0.5f;
+  const float iy = ((gy + 1.f) * (float)H - 1.f) * 0.5f;
+  const float fx = floorf(ix), fy = floorf(iy);
+  pc.x0 = (int)fx; pc.y0 = (int)fy;
+  pc.tx = ix - fx; pc.ty = iy - fy;
+  return pc;
+}
+
+template <typename T, int V> __device__ __forceinline__ void ldv(const T* p, float* f) {
+  if constexpr (V == 1) f[0] = ldf(p); else { Vec16<T> v; v.load(p); v.unpack(f); }
+}
+template <typename T, int V> __device__ __forceinline__ void stv(T* p, const float* f) {
+  if constexpr (V == 1) stf(p, f[0]); else { Vec16<T> v; v.pack(f); v.store(p); }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(kThreads)
+warp_fwd_kernel(const T* __restrict__ x, const float* __restrict__ flow, T* __restrict__ out, int N, int H,
+                int W, int C, float scale, int G) {
+  const int cv = C / V;
+  const int64_t npix = (int64_t)N * H * W;
+  const int gl = threadIdx.x % G;
+  const int64_t groups_per_grid = (int64_t)gridDim.x * (kThreads / G);
+  for (int64_t pix = blockIdx.x * (int64_t)(kThreads / G) + threadIdx.x / G; pix < npix; pix += groups_per_grid) {
+    const int w = (int)(pix % W);
+    const int h = (int)((pix / W) % H);
+    const int b = (int)(pix / ((int64_t)W * H));
+    const PixCoord pc = source_index(flow, pix, h, w, H, W, scale);
+    float wx[4], wy[4];
+    cubic_w(pc.tx, wx);
+    cubic_w(pc.ty, wy);
+    const T* xb = x + (int64_t)b * H * W * C;
+    for (int v = gl; v < cv; v += G) {
+      float acc[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[i] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int yy = pc.y0 - 1 + j;
+        if (yy < 0 || yy >= H) continue;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int xx = pc.x0 - 1 + i;
+          if (xx < 0 || xx >= W) continue;
+          float f[V];
+          ldv<T, V>(xb + ((int64_t)yy * W + xx) * C + v * V, f);
+          const float wgt = wy[j] * wx[i];
+#pragma unroll
+          for (int k = 0; k < V; ++k) acc[k] = fmaf(f[k], wgt, acc[k]);
+        }
+      }
+      stv<T, V>(out + pix * C + v * V, acc);
+    }
+  }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(kThreads)
+warp_bwd_kernel(const T* __restrict__ x, const float* __restrict__ flow, const T* __restrict__ dout,
+                float* __restrict__ dx, float* __restrict__ dflow, int N, int H, int W, int C, float scale,
+                int G) {
+  const int cv = C / V;
+  const int64_t npix = (int64_t)N * H * W;
+  const int gl = threadIdx.x % G;
+  const int64_t groups_per_grid = (int64_t)gridDim.x * (kThreads / G);
+  // all lanes of a warp run the same trip count (npix rounded up) so the shuffles stay converged
+  const int64_t npix_pad = (npix + (kThreads / G) - 1) / (kThreads / G) * (kThreads / G);
+  for (int64_t pix = blockIdx.x * (int64_t)(kThreads / G) + threadIdx.x / G; pix < npix_pad; pix += groups_per_grid) {
+    const bool live = pix < npix;
+    float gix = 0.f, giy = 0.f;
+    PixCoord pc{};
+    if (live) {
+      const int w = (int)(pix % W);
+      const int h = (int)((pix / W) % H);
+      const int b = (int)(pix / ((int64_t)W * H));
+      pc = source_index(flow, pix, h, w, H, W, scale);
+      float wx[4], wy[4], dwx[4], dwy[4];
+      cubic_w(pc.tx, wx); cubic_w(pc.ty, wy);
+      cubic_dw(pc.tx, dwx); cubic_dw(pc.ty, dwy);
+      const int64_t boff = (int64_t)b * H * W * C;
+      for (int v = gl; v < cv; v += G) {
+        float g[V];
+        ldv<T, V>(dout + pix * C + v * V, g);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int yy = pc.y0 - 1 + j;
+          if (yy < 0 || yy >= H) continue;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int xx = pc.x0 - 1 + i;
+            if (xx < 0 || xx >= W) continue;
+            const int64_t off = boff + ((int64_t)yy * W + xx) * C + v * V;
+            float f[V];
+            ldv<T, V>(x + off, f);
+            float dot = 0.f;
+#pragma unroll
+            for (int k = 0; k < V; ++k) dot = fmaf(f[k], g[k], dot);
+            gix = fmaf(dot, wy[j] * dwx[i], gix);
+            giy = fmaf(dot, dwy[j] * wx[i], giy);
+            const float wgt = wy[j] * wx[i];
+            if constexpr (V % 4 == 0) {
+#pragma unroll
+              for (int k = 0; k < V; k += 4)
+                atomicAdd(reinterpret_cast<float4*>(dx + off + k),
+                          make_float4(g[k] * wgt, g[k + 1] * wgt, g[k + 2] * wgt, g[k + 3] * wgt));
+            } else {
+#pragma unroll
+              for (int k = 0; k < V; ++k) atomicAdd(dx + off + k, g[k] * wgt);
+            }
+          }
+        }
+      }
+    }
+    // reduce over the G lanes of the group
+    for (int o = G >> 1; o > 0; o >>= 1) {
+      gix += __shfl_xor_sync(0xffffffffu, gix, o);
+      giy += __shfl_xor_sync(0xffffffffu, giy, o);
+    }
+    if (live && gl == 0) {
+      // d ix / d gx = W/2 ; d gx / d flow = scale * (1 - tanh^2)
+      const float d0 = gix * (0.5f * (float)W) * scale * (1.f - pc.th0 * pc.th0);
+      const float d1 = giy * (0.5f * (float)H) * scale * (1.f - pc.th1 * pc.th1);
+      *reinterpret_cast<float2*>(dflow + pix * 2) = make_float2(d0, d1);
+    }
+  }
+}
+
+inline int group_size(int cv) {
+  if (cv & (cv - 1)) return 1;   // not a power of two: one lane per pixel
+  return cv < 32 ? cv : 32;
+}
+
+inline int grid_for_groups(int64_t npix, int G) {
+  const int per_block = kThreads / G;
+  int64_t b = (npix + per_block - 1) / per_block;
+  const int64_t cap = 148LL * 32;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+}  // namespace
+
+extern "C" int lcgan_warp_fwd(const void* x, const float* flow, void* out, int dt, int N, int H, int W, int C,
+                              float flow_scale, void* stream) {
+  LCGAN_CHECK(x && flow && out && N > 0 && H > 1 && W > 1 && C > 0, "warp_fwd: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t npix = (int64_t)N * H * W;
+#define CALL(T, V)                                                                         \
+  do {                                                                                     \
+    const int G = group_size(C / V);                                                       \
+    warp_fwd_kernel<T, V><<<grid_for_groups(npix, G), kThreads, 0, s>>>(                   \
+        (const T*)x, flow, (T*)out, N, H, W, C, flow_scale, G);                            \
+  } while (0)
+  if (dt == LCGAN_F32) { if (C % 4 == 0) CALL(float, 4); else CALL(float, 1); }
+  else if (dt == LCGAN_BF16) { if (C % 8 == 0) CALL(bf16, 8); else CALL(bf16, 1); }
+  else { lcgan_set_error("warp_fwd: bad dtype %d", dt); return 1; }
+#undef CALL
+  LCGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int lcgan_warp_bwd(const void* x, const float* flow, const void* dout, float* dx_acc, float* dflow,
+                              int dt, int N, int H, int W, int C, float flow_scale, void* stream) {
+  LCGAN_CHECK(x && flow && dout && dx_acc && dflow && N > 0 && H > 1 && W > 1 && C > 0, "warp_bwd: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t npix = (int64_t)N * H * W;
+#define CALL(T, V)                                                                         \
+  do {                                                                                     \
+    const int G = group_size(C / V);                                                       \
+    warp_bwd_kernel<T, V><<<grid_for_groups(npix, G), kThreads, 0, s>>>(                   \
+        (const T*)x, flow, (const T*)dout, dx_acc, dflow, N, H, W, C, flow_scale, G);      \
+  } while (0)
+  if (dt == LCGAN_F32) { if (C % 4 == 0) CALL(float, 4); else CALL(float, 1); }
+  else if (dt == LCGAN_BF16) { if (C % 8 == 0) CALL(bf16, 8); else CALL(bf16, 1); }
+  else { lcgan_set_error("warp_bwd: bad dtype %d", dt); return 1; }
+#undef CALL
+  LCGAN_LAUNCH_CHECK();
+  return 0;
+}

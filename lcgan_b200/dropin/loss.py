@@ -1,0 +1,3 @@
+"""Drop-in shim: put this directory ahead of the reference on sys.path and the reference's
+main.py / worker.py import the B200-native `loss` unchanged."""
+from lcgan_b200.loss import *  # noqa: F401,F403

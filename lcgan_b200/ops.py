@@ -1,0 +1,639 @@
+"""torch.autograd.Functions over the lcgan_b200 C ABI.
+
+Everything activation-sized runs in our CUDA kernels; torch is used for memory (torch.empty),
+streams (the caller's current stream is passed to every launch, so DDP's bucket hooks order
+correctly) and for a few weight-/[b,C]-sized scalar ops.
+
+Second order (R1, reference loss.py:18-34): the discriminator-side Functions implement their
+backward by *calling other Functions* (ConvFwd <-> ConvWgrad, ActBwd, Box3, Pool2 <-> Up2), so
+autograd.grad(create_graph=True) builds a graph whose nodes are again our kernels - the
+conv2d_gradfix pattern.  Generator-only Functions (Modulate, Warp, Up2BoxAdd, Box3Act) are
+once-differentiable.
+"""
+from __future__ import annotations
+
+import contextlib
+import ctypes as C
+import math
+import threading
+import weakref
+
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import _lib, plans
+from ._lib import BF16, F32, TapConvDesc
+
+_state = threading.local()
+_ACT_DTYPE = torch.bfloat16
+_USE_TC = True
+
+
+def set_precision(mode: str):
+    """'bf16': bf16 activations, tcgen05 tensor-core convs (fp32 accumulate).
+    'fp32': fp32 activations and CUDA-core kernels (the <=1e-4 parity mode)."""
+    global _ACT_DTYPE
+    assert mode in ("bf16", "fp32")
+    _ACT_DTYPE = torch.bfloat16 if mode == "bf16" else torch.float32
+
+
+def get_precision() -> str:
+    return "bf16" if _ACT_DTYPE == torch.bfloat16 else "fp32"
+
+
+def act_dtype():
+    return _ACT_DTYPE
+
+
+def set_tensor_cores(flag: bool):
+    global _USE_TC
+    _USE_TC = bool(flag)
+
+
+@contextlib.contextmanager
+def no_weight_gradients():
+    """Skip weight/bias gradients inside (used for the R1 first-order pass, which only needs
+    d logit / d image; same role as conv2d_gradfix.no_weight_gradients)."""
+    old = getattr(_state, "no_wgrad", False)
+    _state.no_wgrad = True
+    try:
+        yield
+    finally:
+        _state.no_wgrad = old
+
+
+def _wgrad_enabled():
+    return not getattr(_state, "no_wgrad", False)
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"lcgan_b200: unsupported dtype {t.dtype}")
+
+
+def _stream(t: torch.Tensor):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("lcgan_b200 ops need CUDA tensors (there is no CPU fallback)")
+
+
+def _cl(x: torch.Tensor, dtype=None) -> torch.Tensor:
+    """Dense channels-last view/copy of a logical NCHW tensor in `dtype`."""
+    dtype = dtype or x.dtype
+    if x.dtype != dtype:
+        x = x.to(dtype)
+    return x.contiguous(memory_format=torch.channels_last)
+
+
+def _is_cl(x):
+    n, c, h, w = x.shape
+    return x.stride() == (h * w * c, 1, w * c, c) or x.is_contiguous(memory_format=torch.channels_last)
+
+
+def empty_cl(n, c, h, w, dtype, device):
+    return torch.empty((n, c, h, w), dtype=dtype, device=device, memory_format=torch.channels_last)
+
+
+def _strides_nhwc(t):
+    """element strides (n, h, w, c) of a logical NCHW tensor"""
+    s = t.stride()
+    return s[0], s[2], s[3], s[1]
+
+
+# ------------------------------------------------------------------------------------------
+# weight packing (cached per parameter version)
+# ------------------------------------------------------------------------------------------
+_pack_cache = {}
+_pack_lock = threading.Lock()
+
+
+def pack_weight(w: torch.Tensor, scale: float, transposed: bool, dtype: torch.dtype) -> torch.Tensor:
+    """W2[o][tap*Cin + c] = scale * w[o, c, kh, kw]  (transposed: rows = c, contraction over o).
+    Packs of nn.Parameters are cached until the parameter's version counter moves (optimizer
+    step, load_state_dict); the cache entry dies with the parameter."""
+    cacheable = isinstance(w, torch.nn.Parameter)
+    if cacheable:
+        key = (id(w), transposed, dtype)
+        tag = (w._version, w.data_ptr(), float(scale))
+        with _pack_lock:
+            hit = _pack_cache.get(key)
+            if hit is not None and hit[0] == tag:
+                return hit[1]
+    wd = w.detach()
+    if wd.dim() == 2:
+        wd = wd[:, :, None, None]
+    perm = (1, 2, 3, 0) if transposed else (0, 2, 3, 1)
+    p = (wd * scale).permute(*perm).reshape(wd.shape[perm[0]], -1).to(dtype).contiguous()
+    if cacheable:
+        with _pack_lock:
+            if key not in _pack_cache:
+                weakref.finalize(w, _pack_cache.pop, key, None)
+            _pack_cache[key] = (tag, p)
+    return p
+
+
+def unpack_wgrad(dw2: torch.Tensor, wshape, transposed: bool) -> torch.Tensor:
+    if len(wshape) == 2:
+        o, i = wshape
+        return dw2.t() if transposed else dw2
+    o, i, kh, kw = wshape
+    if transposed:
+        return dw2.view(i, kh, kw, o).permute(3, 0, 1, 2)
+    return dw2.view(o, kh, kw, i).permute(0, 3, 1, 2)
+
+
+# ------------------------------------------------------------------------------------------
+# raw launches
+# ------------------------------------------------------------------------------------------
+def _fill_desc(d: TapConvDesc, l: plans.Launch, x, y, cin, cout, w2, slope, gain, bias_scale):
+    n = x.shape[0]
+    d.N, d.IH, d.IW, d.Cin = n, x.shape[2], x.shape[3], cin
+    d.OH, d.OW, d.Cout = y.shape[2], y.shape[3], cout
+    d.xs_n, d.xs_h, d.xs_w, d.xs_c = _strides_nhwc(x)
+    d.ys_n, d.ys_h, d.ys_w, d.ys_c = _strides_nhwc(y)
+    d.x_dtype, d.y_dtype = _dt(x), _dt(y)
+    d.w_dtype = _dt(w2) if w2 is not None else F32
+    d.MH, d.MW, d.os, d.py, d.px, d.is_ = l.MH, l.MW, l.os, l.py, l.px, l.is_
+    d.ntaps = len(l.taps)
+    for t, (dy, dx, wt) in enumerate(l.taps):
+        d.dy[t], d.dx[t], d.wtap[t] = dy, dx, wt
+    d.w_ld = w2.shape[1] if w2 is not None else len(l.taps) * cin
+    d.bias_scale, d.slope, d.gain = bias_scale, slope, gain
+
+
+def tapconv(x, w2, y, plan: plans.Plan, rowscale=None, bias=None, residual=None, slope=1.0, gain=1.0,
+            bias_scale=1.0):
+    """y = epilogue(tapconv(x, w2)) for every launch of the plan; x, y logical NCHW."""
+    _need_cuda(x, w2, y)
+    cout, cin = w2.shape[0], x.shape[1]
+    assert w2.shape[1] == plan.k * plan.k * cin, (w2.shape, plan.k, cin)
+    assert x.shape[2:] == (plan.IH, plan.IW) and y.shape[2:] == (plan.OH, plan.OW) and y.shape[1] == cout
+    if residual is not None:
+        assert residual.shape == y.shape and residual.stride() == y.stride() and residual.dtype == y.dtype
+    lib = _lib.lib()
+    st = _stream(x)
+    d = TapConvDesc()
+    for l in plan.launches:
+        _fill_desc(d, l, x, y, cin, cout, w2, slope, gain, bias_scale)
+        fn = "lcgan_tapconv_tc" if (_USE_TC and lib.lcgan_tapconv_tc_eligible(C.byref(d))) else "lcgan_tapconv_simt"
+        _lib.call(fn, C.byref(d), _ptr(x), _ptr(w2), _ptr(y), _ptr(rowscale), _ptr(bias), _ptr(residual), st)
+    return y
+
+
+def tapconv_wgrad(x, g, plan: plans.Plan, cin, cout, scale=1.0):
+    """dW2[o][tap*cin + c] (f32) for x at the plan's input positions and g at its output positions."""
+    _need_cuda(x, g)
+    assert x.shape[1] == cin and g.shape[1] == cout
+    assert x.shape[2:] == (plan.IH, plan.IW) and g.shape[2:] == (plan.OH, plan.OW)
+    dw2 = torch.zeros((cout, plan.k * plan.k * cin), dtype=torch.float32, device=x.device)
+    lib = _lib.lib()
+    st = _stream(x)
+    d = TapConvDesc()
+    for l in plan.launches:
+        _fill_desc(d, l, x, g, cin, cout, None, 1.0, 1.0, 1.0)
+        d.w_ld = plan.k * plan.k * cin
+        fn = "lcgan_tapconv_wgrad_tc" if (_USE_TC and lib.lcgan_tapconv_tc_eligible(C.byref(d))
+                                          and _wgrad_tc_ok(d)) else "lcgan_tapconv_wgrad_simt"
+        _lib.call(fn, C.byref(d), _ptr(x), _ptr(g), _ptr(dw2), C.c_float(scale), st)
+    return dw2
+
+
+def _wgrad_tc_ok(d):
+    return False   # enabled once the tcgen05 wgrad kernel is validated
+
+
+def _alloc_out(n, c, h, w, dtype, device, nchw):
+    if nchw:
+        return torch.empty((n, c, h, w), dtype=dtype, device=device)
+    return empty_cl(n, c, h, w, dtype, device)
+
+
+# ------------------------------------------------------------------------------------------
+# convolution family (closed under differentiation)
+# ------------------------------------------------------------------------------------------
+class ConvFwd(torch.autograd.Function):
+    """Pure linear tap conv.  transposed=False contracts w over dim 1 (input channels);
+    transposed=True contracts over dim 0 (this is the data gradient of the former)."""
+
+    @staticmethod
+    def forward(ctx, x, w, wscale, plan, transposed, out_dtype, out_nchw):
+        ctx.plan, ctx.transposed, ctx.wscale = plan, transposed, wscale
+        ctx.x_dtype, ctx.x_nchw = x.dtype, (x.is_contiguous() and not _is_cl(x))
+        ctx.save_for_backward(x, w)
+        w2 = pack_weight(w, wscale, transposed, torch.float32 if x.dtype == torch.float32 else torch.bfloat16)
+        y = _alloc_out(x.shape[0], w2.shape[0], plan.OH, plan.OW, out_dtype, x.device, out_nchw)
+        return tapconv(x, w2, y, plan)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = ConvFwd.apply(dy, w, ctx.wscale, plans.adjoint(ctx.plan), not ctx.transposed,
+                               ctx.x_dtype, ctx.x_nchw)
+        if ctx.needs_input_grad[1] and _wgrad_enabled():
+            dw = ConvWgrad.apply(x, dy, ctx.plan, ctx.transposed, tuple(w.shape)) * ctx.wscale
+        return dx, dw, None, None, None, None, None
+
+
+class ConvWgrad(torch.autograd.Function):
+    """dw[o,c,t] = sum x[p+t, c] g[p, o]   (transposed: sum x[p+t, o] g[p, c])."""
+
+    @staticmethod
+    def forward(ctx, x, g, plan, transposed, wshape):
+        ctx.plan, ctx.transposed, ctx.wshape = plan, transposed, wshape
+        ctx.x_fmt = (x.dtype, x.is_contiguous() and not _is_cl(x))
+        ctx.g_fmt = (g.dtype, g.is_contiguous() and not _is_cl(g))
+        ctx.save_for_backward(x, g)
+        o, i = wshape[0], wshape[1]
+        cin, cout = (o, i) if transposed else (i, o)
+        dw2 = tapconv_wgrad(x, g, plan, cin, cout)
+        return unpack_wgrad(dw2, wshape, transposed).contiguous()
+
+    @staticmethod
+    def backward(ctx, ggw):
+        x, g = ctx.saved_tensors
+        dx = dg = None
+        if ctx.needs_input_grad[0]:
+            dx = ConvFwd.apply(g, ggw, 1.0, plans.adjoint(ctx.plan), not ctx.transposed, *ctx.x_fmt)
+        if ctx.needs_input_grad[1]:
+            dg = ConvFwd.apply(x, ggw, 1.0, ctx.plan, ctx.transposed, *ctx.g_fmt)
+        return dx, dg, None, None, None
+
+
+class ActBwd(torch.autograd.Function):
+    """gout = dy * gain * (y>0 ? 1 : slope) * d[b,c];  r0 = sum_p dz, r1 = sum_p dz*z (f32 [N,C]).
+    Linear (and self-adjoint) in dy, so its own backward is the same kernel."""
+
+    @staticmethod
+    def forward(ctx, dy, y, d, slope, gain, want_r0, want_r1):
+        _need_cuda(dy, y)
+        n, c, h, w = y.shape
+        dy = _cl(dy, y.dtype)
+        assert _is_cl(y)
+        gout = torch.empty_like(y)
+        r0 = torch.zeros((n, c), dtype=torch.float32, device=y.device) if want_r0 else None
+        r1 = torch.zeros((n, c), dtype=torch.float32, device=y.device) if want_r1 else None
+        _lib.call("lcgan_act_bwd", _ptr(dy), _ptr(y), _ptr(gout), _ptr(d), _ptr(r0), _ptr(r1), _dt(y),
+                  n, h * w, c, C.c_float(slope), C.c_float(gain), _stream(y))
+        ctx.save_for_backward(y, d)
+        ctx.slope, ctx.gain = slope, gain
+        outs = (gout, r0 if want_r0 else gout.new_zeros(()), r1 if want_r1 else gout.new_zeros(()))
+        ctx.mark_non_differentiable(outs[1], outs[2])
+        return outs
+
+    @staticmethod
+    def backward(ctx, gg, _g0, _g1):
+        y, d = ctx.saved_tensors
+        out = ActBwd.apply(gg, y, d, ctx.slope, ctx.gain, False, False)[0]
+        return out, None, None, None, None, None, None
+
+
+class ConvAct(torch.autograd.Function):
+    """y = lrelu(tapconv(x, w*wscale) * rowscale[b,o] + bias*bias_scale, slope) * gain (+ residual).
+
+    One fused kernel forward (custom_layers.py:41-43 / :83-85 + the F.leaky_relu that follows).
+    Backward composes ActBwd, ConvFwd(adjoint) and ConvWgrad, so it is differentiable again.
+    """
+
+    @staticmethod
+    def forward(ctx, x, w, bias, rowscale, residual, wscale, plan, slope, gain, bias_scale, out_dtype,
+                out_nchw):
+        assert residual is None or slope == 1.0, "residual fusion only without activation"
+        compute = torch.float32 if x.dtype == torch.float32 else torch.bfloat16
+        w2 = pack_weight(w, wscale, False, compute)
+        y = _alloc_out(x.shape[0], w2.shape[0], plan.OH, plan.OW, out_dtype, x.device, out_nchw)
+        assert rowscale is None or (rowscale.is_contiguous() and rowscale.dtype == torch.float32)
+        assert bias is None or (bias.is_contiguous() and bias.dtype == torch.float32)
+        tapconv(x, w2, y, plan, rowscale, bias, residual, slope, gain, bias_scale)
+        ctx.save_for_backward(x, w, bias, rowscale, y)
+        ctx.cfg = (wscale, plan, slope, gain, bias_scale, residual is not None)
+        ctx.x_fmt = (x.dtype, x.is_contiguous() and not _is_cl(x))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, bias, rowscale, y = ctx.saved_tensors
+        wscale, plan, slope, gain, bias_scale, has_res = ctx.cfg
+        need_x, need_w, need_b, need_rs, need_res = ctx.needs_input_grad[:5]
+        wg = _wgrad_enabled()
+        need_w, need_b = need_w and wg, need_b and wg
+        dres = dy if (has_res and need_res) else None
+        trivial = slope == 1.0 and gain == 1.0 and rowscale is None
+        if trivial and not need_b:
+            g, r0, r1 = dy, None, None
+        else:
+            ycl = y if _is_cl(y) else _cl(y)
+            if has_res:
+                # slope == 1 here, so the mask is all-ones and y is only used when rowscale needs z;
+                # residual + rowscale are never combined by the layers.
+                assert rowscale is None
+            g, r0, r1 = ActBwd.apply(dy, ycl, rowscale, slope, gain, bool(need_b or need_rs), bool(need_rs))
+        dx = dw = db = drs = None
+        if need_x:
+            dx = ConvFwd.apply(g, w, wscale, plans.adjoint(plan), True, *ctx.x_fmt)
+        if need_w:
+            dw = ConvWgrad.apply(x, g, plan, False, tuple(w.shape)) * wscale
+        if need_b:
+            db = r0.sum(0) * bias_scale
+        if need_rs:
+            beff = (bias * bias_scale)[None] if bias is not None else 0.0
+            drs = (r1 - beff * r0) / rowscale
+        return dx, dw, db, drs, dres, None, None, None, None, None, None, None
+
+
+def conv_act(x, w, bias=None, rowscale=None, residual=None, *, wscale=1.0, plan, slope=1.0, gain=1.0,
+             bias_scale=1.0, out_dtype=None, out_nchw=False):
+    return ConvAct.apply(x, w, bias, rowscale, residual, wscale, plan, slope, gain, bias_scale,
+                         out_dtype or _ACT_DTYPE, out_nchw)
+
+
+def linear_act(x2d, w, bias, *, wscale, bias_scale, slope=1.0, gain=1.0, out_dtype=torch.float32):
+    """EqualizedLinear (+ optional leaky-relu) as a 1x1 tap conv; x2d [b, in] -> [b, out]."""
+    y = ConvAct.apply(x2d[:, :, None, None], w, bias, None, None, wscale, plans.linear(), slope, gain,
+                      bias_scale, out_dtype, True)
+    return y[:, :, 0, 0]
+
+
+# ------------------------------------------------------------------------------------------
+# resampling (discriminator side: differentiable twice)
+# ------------------------------------------------------------------------------------------
+class Box3(torch.autograd.Function):
+    """F.avg_pool2d(x, 3, 1, 1) (count_include_pad) - linear and self-adjoint."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _need_cuda(x)
+        x = _cl(x)
+        n, c, h, w = x.shape
+        out = torch.empty_like(x)
+        _lib.call("lcgan_box3", _ptr(x), None, _ptr(out), _dt(x), n, h, w, c,
+                  C.c_float(1.0), C.c_float(1.0), C.c_float(1.0), C.c_float(1.0), _stream(x))
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        return Box3.apply(dy)
+
+
+class Pool2(torch.autograd.Function):
+    """y = scale * sum over 2x2 (F.avg_pool2d(2,2) with scale .25); adjoint is Up2."""
+
+    @staticmethod
+    def forward(ctx, x, scale):
+        _need_cuda(x)
+        x = _cl(x)
+        n, c, h, w = x.shape
+        ctx.scale = scale
+        out = empty_cl(n, c, h // 2, w // 2, x.dtype, x.device)
+        _lib.call("lcgan_pool2", _ptr(x), _ptr(out), _dt(x), n, h, w, c, C.c_float(scale), _stream(x))
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        return Up2.apply(dy, ctx.scale), None
+
+
+class Up2(torch.autograd.Function):
+    """y[2i+a, 2j+b] = scale * x[i, j]; adjoint is Pool2."""
+
+    @staticmethod
+    def forward(ctx, x, scale):
+        _need_cuda(x)
+        x = _cl(x)
+        n, c, h, w = x.shape
+        ctx.scale = scale
+        out = empty_cl(n, c, h * 2, w * 2, x.dtype, x.device)
+        _lib.call("lcgan_up2", _ptr(x), _ptr(out), _dt(x), n, h, w, c, C.c_float(scale), _stream(x))
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        return Pool2.apply(dy, ctx.scale), None
+
+
+# ------------------------------------------------------------------------------------------
+# generator-side fused ops (first order only)
+# ------------------------------------------------------------------------------------------
+class Box3Act(torch.autograd.Function):
+    """y = lrelu(box3(x), slope) * gain   (custom_layers.py:154-155)."""
+
+    @staticmethod
+    def forward(ctx, x, slope, gain):
+        _need_cuda(x)
+        x = _cl(x)
+        n, c, h, w = x.shape
+        y = torch.empty_like(x)
+        _lib.call("lcgan_box3", _ptr(x), None, _ptr(y), _dt(x), n, h, w, c,
+                  C.c_float(1.0), C.c_float(1.0), C.c_float(slope), C.c_float(gain), _stream(x))
+        ctx.save_for_backward(y)
+        ctx.cfg = (slope, gain)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        slope, gain = ctx.cfg
+        dy = _cl(dy, y.dtype)
+        n, c, h, w = y.shape
+        dx = torch.empty_like(y)
+        _lib.call("lcgan_box3", _ptr(dy), _ptr(y), _ptr(dx), _dt(y), n, h, w, c,
+                  C.c_float(slope), C.c_float(gain), C.c_float(1.0), C.c_float(1.0), _stream(y))
+        return dx, None, None
+
+
+class Up2BoxAdd(torch.autograd.Function):
+    """out = box3(nearest_up2(s)) + t   (custom_layers.py:146-147,159)."""
+
+    @staticmethod
+    def forward(ctx, s, t):
+        _need_cuda(s, t)
+        s, t = _cl(s), _cl(t)
+        n, c, h, w = s.shape
+        out = torch.empty_like(t)
+        _lib.call("lcgan_up2box_add", _ptr(s), _ptr(t), _ptr(out), _dt(s), n, h, w, c, _stream(s))
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        dy = _cl(dy)
+        n, c, h, w = dy.shape
+        ds = None
+        if ctx.needs_input_grad[0]:
+            tmp = torch.empty_like(dy)
+            _lib.call("lcgan_box3", _ptr(dy), None, _ptr(tmp), _dt(dy), n, h, w, c,
+                      C.c_float(1.0), C.c_float(1.0), C.c_float(1.0), C.c_float(1.0), _stream(dy))
+            ds = empty_cl(n, c, h // 2, w // 2, dy.dtype, dy.device)
+            _lib.call("lcgan_pool2", _ptr(tmp), _ptr(ds), _dt(dy), n, h, w, c, C.c_float(1.0), _stream(dy))
+        return ds, (dy if ctx.needs_input_grad[1] else None)
+
+
+class Modulate(torch.autograd.Function):
+    """xs = x * s[b,c]   (style modulation in shared-weight form, custom_layers.py:62-64)."""
+
+    @staticmethod
+    def forward(ctx, x, s):
+        _need_cuda(x, s)
+        x = _cl(x)
+        s = s.contiguous().float()
+        n, c, h, w = x.shape
+        xs = torch.empty_like(x)
+        _lib.call("lcgan_modulate", _ptr(x), _ptr(s), _ptr(xs), _dt(x), n, h * w, c, _stream(x))
+        ctx.save_for_backward(x, s)
+        return xs
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, t):
+        x, s = ctx.saved_tensors
+        t = _cl(t, x.dtype)
+        n, c, h, w = x.shape
+        dx = torch.empty_like(x)
+        ds = torch.zeros_like(s)
+        _lib.call("lcgan_modulate_bwd", _ptr(x), _ptr(t), _ptr(s), _ptr(dx), _ptr(ds), _dt(x), n, h * w, c,
+                  _stream(x))
+        return dx, ds
+
+
+class Warp(torch.autograd.Function):
+    """Flow warp: bicubic grid_sample at linspace coords + tanh(flow)*scale
+    (custom_layers.py:127-134,151,161-165).  flow is the box-filtered, pre-tanh field [b,2,H,W] f32."""
+
+    @staticmethod
+    def forward(ctx, x, flow, scale):
+        _need_cuda(x, flow)
+        x = _cl(x)
+        flow = _cl(flow, torch.float32)
+        n, c, h, w = x.shape
+        out = torch.empty_like(x)
+        _lib.call("lcgan_warp_fwd", _ptr(x), _ptr(flow), _ptr(out), _dt(x), n, h, w, c, C.c_float(scale),
+                  _stream(x))
+        ctx.save_for_backward(x, flow)
+        ctx.scale = scale
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        x, flow = ctx.saved_tensors
+        dout = _cl(dout, x.dtype)
+        n, c, h, w = x.shape
+        dx_acc = torch.zeros((n, c, h, w), dtype=torch.float32, device=x.device,
+                             memory_format=torch.channels_last)
+        dflow = torch.empty_like(flow)
+        _lib.call("lcgan_warp_bwd", _ptr(x), _ptr(flow), _ptr(dout), _ptr(dx_acc), _ptr(dflow), _dt(x),
+                  n, h, w, c, C.c_float(ctx.scale), _stream(x))
+        if x.dtype != torch.float32:
+            dx = torch.empty_like(x)
+            _lib.call("lcgan_cast", _ptr(dx_acc), _ptr(dx), F32, _dt(x), C.c_int64(dx_acc.numel()), _stream(x))
+        else:
+            dx = dx_acc
+        return dx, dflow, None
+
+
+# ------------------------------------------------------------------------------------------
+# losses
+# ------------------------------------------------------------------------------------------
+class L2Normalize(torch.autograd.Function):
+    """F.normalize(x, dim=1) (cnn.py:40-41)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _need_cuda(x)
+        x = x.contiguous().float()
+        b, d = x.shape
+        y = torch.empty_like(x)
+        inv = torch.empty((b,), dtype=torch.float32, device=x.device)
+        _lib.call("lcgan_l2norm_fwd", _ptr(x), _ptr(y), _ptr(inv), b, d, _stream(x))
+        ctx.save_for_backward(y, inv)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        y, inv = ctx.saved_tensors
+        dy = dy.contiguous().float()
+        dx = torch.empty_like(y)
+        _lib.call("lcgan_l2norm_bwd", _ptr(y), _ptr(inv), _ptr(dy), _ptr(dx), y.shape[0], y.shape[1], _stream(y))
+        return dx
+
+
+class Contrastive(torch.autograd.Function):
+    """Per-sample softplus((a.n - a.p)/tau)  (loss.py:9-14)."""
+
+    @staticmethod
+    def forward(ctx, a, p, n, tau):
+        _need_cuda(a, p, n)
+        a, p, n = (t.contiguous().float() for t in (a, p, n))
+        b, d = a.shape
+        l = torch.empty((b,), dtype=torch.float32, device=a.device)
+        sig = torch.empty_like(l)
+        _lib.call("lcgan_contrastive_fwd", _ptr(a), _ptr(p), _ptr(n), _ptr(l), _ptr(sig), b, d, C.c_float(tau),
+                  _stream(a))
+        ctx.save_for_backward(a, p, n, sig)
+        ctx.tau = tau
+        return l
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dl):
+        a, p, n, sig = ctx.saved_tensors
+        dl = dl.contiguous().float()
+        da, dp, dn = torch.empty_like(a), torch.empty_like(a), torch.empty_like(a)
+        _lib.call("lcgan_contrastive_bwd", _ptr(a), _ptr(p), _ptr(n), _ptr(sig), _ptr(dl), _ptr(da), _ptr(dp),
+                  _ptr(dn), a.shape[0], a.shape[1], C.c_float(ctx.tau), _stream(a))
+        return da, dp, dn, None
+
+
+class SumSq(torch.autograd.Function):
+    """out[b] = sum_i x[b,i]^2  (R1 penalty reduction, loss.py:21-23)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _need_cuda(x)
+        x = x.contiguous().float()
+        b = x.shape[0]
+        out = torch.zeros((b,), dtype=torch.float32, device=x.device)
+        _lib.call("lcgan_sumsq", _ptr(x), _ptr(out), b, C.c_int64(x.numel() // b), _stream(x))
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        (x,) = ctx.saved_tensors
+        s = (dout.float() * 2.0).contiguous()
+        dx = torch.empty_like(x)
+        _lib.call("lcgan_rowscale", _ptr(x), _ptr(s), _ptr(dx), x.shape[0], C.c_int64(x.numel() // x.shape[0]),
+                  _stream(x))
+        return dx
+
+
+def ema_lerp_(dst_tensors, src_tensors, decay: float):
+    """dst = src.lerp(dst, decay) for every tensor pair, in ONE launch (ema.py:26-32)."""
+    pairs = [(d, s) for d, s in zip(dst_tensors, src_tensors) if d.numel() > 0]
+    if not pairs:
+        return
+    dev = pairs[0][0].device
+    _need_cuda(pairs[0][0])
+    for d, s in pairs:
+        assert d.dtype == torch.float32 and s.dtype == torch.float32 and d.is_contiguous() and s.is_contiguous()
+    table = torch.tensor([[d.data_ptr() for d, _ in pairs], [s.data_ptr() for _, s in pairs],
+                          [d.numel() for d, _ in pairs]], dtype=torch.int64).to(dev, non_blocking=True)
+    _lib.call("lcgan_ema_lerp", _ptr(table[0]), _ptr(table[1]), _ptr(table[2]), len(pairs), C.c_float(decay),
+              _stream(pairs[0][0]))
+    # keep the table alive until the kernel has consumed it
+    table.record_stream(torch.cuda.current_stream(dev))

@@ -1,0 +1,152 @@
+"""Model-level parity on the B200: lcgan_b200 modules vs the oracle (oracle/lcgan_oracle.py) on
+identical seeded parameters and inputs, and vs the committed golden vectors that came from the
+unmodified reference.  fp32 mode: rel-L2 <= 1e-4 (north_star); bf16 mode: <= 1e-2 at the outputs
+of the small models used here."""
+import os
+
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _setup():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from lcgan_b200 import ops
+    yield
+    ops.set_precision("bf16")
+
+
+def _build(res, seed, mode):
+    from lcgan_b200 import cnn, ops
+    from oracle import lcgan_oracle as O
+    ops.set_precision(mode)
+    cfg = O.Config(img_resolution=res)
+    gsd, dsd = O.make_generator_state(cfg, seed), O.make_discriminator_state(cfg, seed + 1)
+    G, D = cnn.Generator(cfg.namespace()), cnn.Discriminator(cfg.namespace())
+    G.load_state_dict(gsd); D.load_state_dict(dsd)
+    return O, cfg, gsd, dsd, G.cuda(), D.cuda()
+
+
+@pytest.mark.parametrize("name,mode", [("model_r16_b4.pt", "fp32"), ("model_r32_b2.pt", "fp32"),
+                                       ("model_r16_b4.pt", "bf16"), ("model_r32_b2.pt", "bf16")])
+def test_forward_against_reference_golden(golden_dir, name, mode):
+    g = torch.load(os.path.join(golden_dir, name), weights_only=False)
+    O, cfg, gsd, dsd, G, D = _build(g["res"], g["seed"], mode)
+    tol = 1e-4 if mode == "fp32" else 3e-2
+    gen = torch.Generator().manual_seed(1000 + g["seed"])
+    z = O.synthetic_latents(g["b"], cfg, gen, "cuda")
+    data = O.synthetic_data(g["b"], cfg, gen, "cuda")
+    with torch.no_grad():
+        img = G(z["rand1"], z["rand2"])
+        assert img.dtype == torch.float32 and img.is_contiguous()
+        assert rel_l2(img.cpu(), g["g_image"]) < tol
+        assert rel_l2(G.avg_latent1.cpu(), g["avg_latent1"]) < 1e-4
+        assert rel_l2(G(z["rand1"], z["rand2"], 0.7).cpu(), g["g_image_psi07"]) < tol
+        logit, ge, ae = D(data["image"], True)
+        assert rel_l2(logit.cpu(), g["d_logit"]) < tol
+        assert rel_l2(ge.cpu(), g["d_geo"]) < tol and rel_l2(ae.cpu(), g["d_app"]) < tol
+
+
+def _grad_summary(named):
+    out = {}
+    for k, p in named:
+        if p.grad is None:
+            out[k] = None
+            continue
+        gr = p.grad.detach().double().cpu()
+        ramp = torch.linspace(0.5, 1.5, gr.numel(), dtype=torch.float64).reshape(gr.shape)
+        out[k] = (float(gr.norm()), float((gr * ramp).sum()))
+    return out
+
+
+@pytest.mark.parametrize("name", ["model_r16_b4.pt", "model_r32_b2.pt"])
+def test_losses_and_gradients_fp32_against_reference_golden(golden_dir, name):
+    """All five step variants (G even/odd, D even/odd/odd+R1) in fp32 mode: loss values and
+    per-parameter gradient norms vs the unmodified reference."""
+    from lcgan_b200 import train_step as T
+    g = torch.load(os.path.join(golden_dir, name), weights_only=False)
+    O, cfg, gsd, dsd, G, D = _build(g["res"], g["seed"], "fp32")
+    hp = O.Hyper()
+    gen = torch.Generator().manual_seed(1000 + g["seed"])
+    z = O.synthetic_latents(g["b"], cfg, gen, "cuda")
+    data = O.synthetic_data(g["b"], cfg, gen, "cuda")
+    for it in (0, 1):
+        G.load_state_dict(gsd); G.zero_grad(); D.zero_grad()
+        T.requires_grad(G, True); T.requires_grad(D, False)
+        loss = T.generator_loss(G, D, hp, it, z)
+        loss.backward()
+        assert abs(float(loss) - g[f"g_loss_it{it}"]) < 1e-4 * max(1.0, abs(g[f"g_loss_it{it}"]))
+        mine = _grad_summary(G.named_parameters())
+        for k, ref in g[f"g_grads_it{it}"].items():
+            if ref is None:
+                continue
+            assert mine[k] is not None, k
+            assert abs(mine[k][0] - ref[0]) < 2e-3 * max(ref[0], 1e-9), (k, mine[k], ref)
+    for it in (0, 1, 3):
+        G.load_state_dict(gsd); G.zero_grad(); D.zero_grad()
+        T.requires_grad(G, False); T.requires_grad(D, True)
+        loss = T.discriminator_loss(G, D, hp, it, z, data)
+        loss.backward()
+        assert abs(float(loss) - g[f"d_loss_it{it}"]) < 1e-4 * max(1.0, abs(g[f"d_loss_it{it}"]))
+        mine = _grad_summary(D.named_parameters())
+        for k, ref in g[f"d_grads_it{it}"].items():
+            if ref is None:
+                continue
+            assert mine[k] is not None, k
+            assert abs(mine[k][0] - ref[0]) < 2e-3 * max(ref[0], 1e-9), (k, mine[k], ref)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_per_layer_activations_and_grads_vs_oracle(mode):
+    """Per-layer parity with identical inputs (SURVEY hard parts): feed the oracle's block input
+    to each block and compare block output and gradients."""
+    from lcgan_b200 import ops
+    O, cfg, gsd, dsd, G, D = _build(64, 5, mode)
+    tol = 1e-4 if mode == "fp32" else 1e-2
+    dt = torch.float32 if mode == "fp32" else torch.bfloat16
+    gcuda = {k: v.cuda() for k, v in gsd.items()}
+    dcuda = {k: v.cuda() for k, v in dsd.items()}
+    torch.manual_seed(1)
+    b = 4
+    glat, alat = torch.randn(b, 64, device="cuda"), torch.randn(b, 512, device="cuda")
+    for i, (cin, cout, res) in enumerate(cfg.g_channels()):
+        x = torch.randn(b, cin, res // 2, res // 2, device="cuda").to(dt).float()
+        xo = x.clone().requires_grad_()
+        for v in gcuda.values():
+            v.requires_grad_(True); v.grad = None
+        yo = O.synthesis_block(gcuda, f"model.{i}", xo, glat, alat, cfg.max_flow_scale)
+        gy = torch.randn_like(yo).to(dt).float()
+        yo.backward(gy)
+        xm = x.to(dt).contiguous(memory_format=torch.channels_last).requires_grad_()
+        G.zero_grad()
+        ym = G.model[i](xm, glat[:, None], alat[:, None].expand(-1, 2, -1))
+        ym.backward(gy.to(dt).contiguous(memory_format=torch.channels_last))
+        assert rel_l2(ym.float(), yo.detach()) < tol, f"G block {i} fwd"
+        assert rel_l2(xm.grad.float(), xo.grad) < tol * 3, f"G block {i} dx"
+        for k, p in G.model[i].named_parameters():
+            ref = gcuda[f"model.{i}.{k}"].grad
+            assert rel_l2(p.grad, ref) < tol * 5, f"G block {i} {k}"
+    for i, (cin, cout) in enumerate(cfg.d_channels()):
+        res = cfg.img_resolution >> i
+        x = torch.randn(b, cin, res, res, device="cuda").to(dt).float()
+        xo = x.clone().requires_grad_()
+        for v in dcuda.values():
+            v.requires_grad_(True); v.grad = None
+        yo = O.discriminator_block(dcuda, f"shared_model.{i + 2}", xo)
+        gy = torch.randn_like(yo).to(dt).float()
+        yo.backward(gy)
+        xm = x.to(dt).contiguous(memory_format=torch.channels_last).requires_grad_()
+        D.zero_grad()
+        ym = D.shared_model[i + 2](xm)
+        ym.backward(gy.to(dt).contiguous(memory_format=torch.channels_last))
+        assert rel_l2(ym.float(), yo.detach()) < tol, f"D block {i} fwd"
+        assert rel_l2(xm.grad.float(), xo.grad) < tol * 3, f"D block {i} dx"
+        for k, p in D.shared_model[i + 2].named_parameters():
+            assert rel_l2(p.grad, dcuda[f"shared_model.{i + 2}.{k}"].grad) < tol * 5, f"D block {i} {k}"
