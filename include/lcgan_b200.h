@@ -31,7 +31,7 @@ extern "C" {
  *   for a lattice point (b, m, n), m < MH, n < MW:
  *     out pixel (oy, ox) = (m*os + py, n*os + px)
  *     acc[o] = sum_t sum_c  X[b, m*is + dy[t], n*is + dx[t], c] * W2[o][wtap[t]*Cin + c]
- *     Y[b, oy, ox, o] = lrelu(acc[o]*rowscale[b,o] + bias[o]*bias_scale, slope) * gain + R[b,oy,ox,o]
+ *     Y[b, oy, ox, o] = lrelu(acc[o]*acc_scale*rowscale[b,o] + bias[o]*bias_scale, slope) * gain + R[b,oy,ox,o]
  *   out-of-range input pixels read as zero.
  *
  * X and Y are addressed with explicit element strides, so NCHW fp32 images and channels-last bf16
@@ -49,6 +49,7 @@ typedef struct lcgan_tapconv {
   int32_t ntaps;
   int32_t dy[LCGAN_MAX_TAPS], dx[LCGAN_MAX_TAPS], wtap[LCGAN_MAX_TAPS];
   int64_t w_ld;                    /* row stride (elements) of W2[Cout][w_ld] */
+  float acc_scale;                 /* equalized-lr constant c (weights are packed unscaled) */
   float bias_scale, slope, gain;   /* slope = 1 -> no activation */
 } lcgan_tapconv;
 

@@ -35,7 +35,7 @@ class TapConvDesc(C.Structure):
         ("ntaps", C.c_int32),
         ("dy", C.c_int32 * MAX_TAPS), ("dx", C.c_int32 * MAX_TAPS), ("wtap", C.c_int32 * MAX_TAPS),
         ("w_ld", C.c_int64),
-        ("bias_scale", C.c_float), ("slope", C.c_float), ("gain", C.c_float),
+        ("acc_scale", C.c_float), ("bias_scale", C.c_float), ("slope", C.c_float), ("gain", C.c_float),
     ]
 
 

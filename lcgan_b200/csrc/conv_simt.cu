@@ -94,7 +94,7 @@ tapconv_simt_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const TW* _
     for (int j = 0; j < TN; ++j) {
       const int o = o0 + tx + j * TXN;
       if (o >= d.Cout) continue;
-      float v = acc[i][j];
+      float v = acc[i][j] * d.acc_scale;
       if (rowscale) v *= rowscale[(int64_t)b * d.Cout + o];
       if (bias) v += bias[o] * d.bias_scale;
       v = (v > 0.f ? v : v * d.slope) * d.gain;

@@ -1,5 +1,579 @@
-// placeholder until the tcgen05 kernel lands
+// Tap-convolution on the 5th-generation tensor cores (sm_100a):
+//   tcgen05.mma (cta_group::1, kind::f16, bf16 x bf16 -> fp32) issued by one elected thread,
+//   accumulators in TMEM, operands staged in shared memory by TMA (cp.async.bulk.tensor) through an
+//   mbarrier ring, epilogue (demod row scale, bias, leaky-relu, gain, residual) applied on the
+//   tcgen05.ld'ed accumulator and stored straight to the channels-last output.
+//
+// Implicit GEMM without im2col: the activation operand of a tap is ONE 4-D TMA box
+//   {64 channels, wt, ht, nt} of the channels-last tensor at the tap's shifted origin - out-of-range
+//   coordinates are zero-filled by TMA, which is exactly the convolution's zero padding, and
+//   elementStrides = 2 walks the stride-2 lattices.  The 128 rows of the box land in shared memory
+//   as a K-major SWIZZLE_128B tile, directly consumable by the UMMA descriptor.
+//
+// Forward-type kernel:  D[128 lattice points x BN out-channels] += A[128 x 64] * W2[BN x 64]^T
+//                       over taps x (Cin/64) k-blocks.                  (A, B K-major)
+// Weight-gradient kernel: D[128 out-ch x BN in-ch] += G[128 px x 128 ch]^T * X[128 px x BN ch]
+//                       over the lattice points of a K-split.           (A, B MN-major, same TMA tiles)
 #include "common.cuh"
-extern "C" int lcgan_tapconv_tc_eligible(const lcgan_tapconv*) { return 0; }
-extern "C" int lcgan_tapconv_tc(const lcgan_tapconv*, const void*, const void*, void*, const float*, const float*, const void*, void*) { lcgan_set_error("tc path not built"); return 9; }
-extern "C" int lcgan_tapconv_wgrad_tc(const lcgan_tapconv*, const void*, const void*, float*, float, void*) { lcgan_set_error("tc path not built"); return 9; }
+#include <cuda.h>
+#include <mutex>
+
+namespace {
+
+constexpr int kStages = 3;
+constexpr int kTileM = 128;                    // lattice points (fwd) / pixels per k-block (wgrad)
+constexpr int kBlockK = 64;                    // channels per k-block = one 128-byte swizzle row
+constexpr int kMaxBN = 128;
+constexpr int kABytes = kTileM * kBlockK * 2;  // 16 KiB
+constexpr int kBBytes = kMaxBN * kBlockK * 2;  // 16 KiB
+constexpr int kThreads = 192;                  // warp0: TMA, warp1: MMA, warps 2-5: epilogue
+
+struct TcParams {
+  int N, Cin, Cout;
+  int wt, ht, nt, tiles_w, tiles_h;
+  int is, os, py, px;
+  int ntaps, kpt;                               // kpt = Cin / 64
+  int dy[LCGAN_MAX_TAPS], dx[LCGAN_MAX_TAPS], wtap[LCGAN_MAX_TAPS];
+  int BN;
+  long long ys_n, ys_h, ys_w;
+  int y_f32;
+  float acc_scale, bias_scale, slope, gain;
+};
+
+struct WgParams {
+  int N, Cin, Cout;
+  int wt, ht, nt, tiles_w, tiles_h, tiles_total;
+  int is, os, py, px;
+  int ntaps;
+  int dy[LCGAN_MAX_TAPS], dx[LCGAN_MAX_TAPS], wtap[LCGAN_MAX_TAPS];
+  int BN, ctiles;
+  int tiles_per_split;
+  long long w_ld;
+  float scale;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(kCols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier once all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100 version 1, SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;     // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;     // LayoutType::SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): bf16 x bf16 -> f32, M=128.
+__device__ __forceinline__ uint32_t make_idesc(int n, bool a_mn_major, bool b_mn_major) {
+  uint32_t d = 0;
+  d |= 1u << 4;                          // c_format = F32
+  d |= 1u << 7;                          // a_format = BF16
+  d |= 1u << 10;                         // b_format = BF16
+  d |= (a_mn_major ? 1u : 0u) << 15;
+  d |= (b_mn_major ? 1u : 0u) << 16;
+  d |= (uint32_t)(n >> 3) << 17;
+  d |= (uint32_t)(kTileM >> 4) << 24;
+  return d;
+}
+
+struct Smem {
+  uint8_t* a[kStages];
+  uint8_t* b[kStages];
+  uint64_t* full;
+  uint64_t* empty;
+  uint64_t* done;
+  uint32_t* tmem_slot;
+};
+
+__device__ __forceinline__ Smem carve(uint8_t* raw, int a_bytes, int b_bytes) {
+  Smem s;
+  uint8_t* base = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+  for (int i = 0; i < kStages; ++i) {
+    s.a[i] = base + (size_t)i * (a_bytes + b_bytes);
+    s.b[i] = s.a[i] + a_bytes;
+  }
+  uint8_t* tail = base + (size_t)kStages * (a_bytes + b_bytes);
+  s.full = (uint64_t*)tail;
+  s.empty = s.full + kStages;
+  s.done = s.empty + kStages;
+  s.tmem_slot = (uint32_t*)(s.done + 1);
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward-type kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmw, const TcParams p,
+                  void* __restrict__ y, const float* __restrict__ rowscale, const float* __restrict__ bias,
+                  const void* __restrict__ residual) {
+  extern __shared__ uint8_t smem_raw[];
+  Smem s = carve(smem_raw, kABytes, kBBytes);
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+
+  // tile coordinates
+  int t = blockIdx.x;
+  const int tw = t % p.tiles_w; t /= p.tiles_w;
+  const int th = t % p.tiles_h;
+  const int tb = t / p.tiles_h;
+  const int n0 = tw * p.wt, m0 = th * p.ht, b0 = tb * p.nt;
+  const int o0 = blockIdx.y * p.BN;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmx);
+    tma_prefetch_desc(&tmw);
+    for (int i = 0; i < kStages; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    mbar_init(s.done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<kMaxBN>(s.tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s.tmem_slot;
+  const int nkb = p.ntaps * p.kpt;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t tx_bytes = kABytes + p.BN * kBlockK * 2;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int st = kb % kStages, ph = (kb / kStages) & 1;
+        mbar_wait(&s.empty[st], ph ^ 1);
+        const int tap = kb / p.kpt, cb = kb - tap * p.kpt;
+        mbar_expect_tx(&s.full[st], tx_bytes);
+        tma_load_4d(s.a[st], &tmx, &s.full[st], cb * kBlockK, n0 * p.is + p.dx[tap], m0 * p.is + p.dy[tap], b0);
+        tma_load_2d(s.b[st], &tmw, &s.full[st], p.wtap[tap] * p.Cin + cb * kBlockK, o0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(p.BN, false, false);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int st = kb % kStages, ph = (kb / kStages) & 1;
+        mbar_wait(&s.full[st], ph);
+        tc_fence_after();
+        const uint64_t ad = make_desc(smem_u32(s.a[st]), 16, 1024);
+        const uint64_t bd = make_desc(smem_u32(s.b[st]), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k)   // +32 bytes along K inside the 128-byte swizzle row
+          umma_f16(tmem_base, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+        umma_commit(&s.empty[st]);
+      }
+      umma_commit(s.done);
+    }
+  } else {
+    // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31  (= tile rows)
+    const int q = warp % 4;
+    const int r = q * 32 + lane;
+    const int ni = r % p.wt, mi = (r / p.wt) % p.ht, bi = r / (p.wt * p.ht);
+    const int b = b0 + bi;
+    const bool live = b < p.N;
+    const long long pix = (long long)b * p.ys_n + (long long)((m0 + mi) * p.os + p.py) * p.ys_h +
+                          (long long)((n0 + ni) * p.os + p.px) * p.ys_w;
+    mbar_wait(s.done, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int c = 0; c < p.BN; c += 16) {
+      uint32_t v[16];
+      tmem_ld16(trow + c, v);
+      tmem_ld_wait();
+      const int o = o0 + c;
+      if (live && o < p.Cout) {
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * p.acc_scale;
+        if (rowscale) {
+          const float4* rs = reinterpret_cast<const float4*>(rowscale + (long long)b * p.Cout + o);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 sc = rs[i];
+            f[4 * i] *= sc.x; f[4 * i + 1] *= sc.y; f[4 * i + 2] *= sc.z; f[4 * i + 3] *= sc.w;
+          }
+        }
+        if (bias) {
+          const float4* bp = reinterpret_cast<const float4*>(bias + o);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 bb = bp[i];
+            f[4 * i] += bb.x * p.bias_scale; f[4 * i + 1] += bb.y * p.bias_scale;
+            f[4 * i + 2] += bb.z * p.bias_scale; f[4 * i + 3] += bb.w * p.bias_scale;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = (f[i] > 0.f ? f[i] : f[i] * p.slope) * p.gain;
+        if (p.y_f32) {
+          float* yp = reinterpret_cast<float*>(y) + pix + o;
+          if (residual) {
+            const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(residual) + pix + o);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 rr = rp[i];
+              f[4 * i] += rr.x; f[4 * i + 1] += rr.y; f[4 * i + 2] += rr.z; f[4 * i + 3] += rr.w;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            reinterpret_cast<float4*>(yp)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+        } else {
+          bf16* yp = reinterpret_cast<bf16*>(y) + pix + o;
+          if (residual) {
+            const bf16* rp = reinterpret_cast<const bf16*>(residual) + pix + o;
+            Vec16<bf16> r0, r1;
+            r0.load(rp); r1.load(rp + 8);
+            float g[16];
+            r0.unpack(g); r1.unpack(g + 8);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] += g[i];
+          }
+          Vec16<bf16> o0v, o1v;
+          o0v.pack(f); o1v.pack(f + 8);
+          o0v.store(yp); o1v.store(yp + 8);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<kMaxBN>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight-gradient kernel: one CTA = (128 out-channels x BN in-channels) of one tap over a K-split
+// ---------------------------------------------------------------------------------------------
+constexpr int kWgABytes = kTileM * 128 * 2;   // G tile: 128 px x 128 ch = two 64-channel boxes
+constexpr int kWgBBytes = kTileM * kMaxBN * 2;
+
+__global__ void __launch_bounds__(kThreads)
+tapconv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUtensorMap tmx,
+                        const WgParams p, float* __restrict__ dw) {
+  extern __shared__ uint8_t smem_raw[];
+  Smem s = carve(smem_raw, kWgABytes, kWgBBytes);
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int o0 = (blockIdx.x / p.ctiles) * 128, c0 = (blockIdx.x % p.ctiles) * p.BN;
+  const int tap = blockIdx.y;
+  const int t_begin = blockIdx.z * p.tiles_per_split;
+  const int t_end = min(p.tiles_total, t_begin + p.tiles_per_split);
+  const int nkb = t_end - t_begin;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmg);
+    tma_prefetch_desc(&tmx);
+    for (int i = 0; i < kStages; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    mbar_init(s.done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<kMaxBN>(s.tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s.tmem_slot;
+  const int nbx = p.BN / 64;                      // 64-channel boxes of the X operand
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t tx_bytes = kWgABytes + nbx * kABytes;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int st = kb % kStages, ph = (kb / kStages) & 1;
+        mbar_wait(&s.empty[st], ph ^ 1);
+        int t = t_begin + kb;
+        const int tw = t % p.tiles_w; t /= p.tiles_w;
+        const int th = t % p.tiles_h;
+        const int tb = t / p.tiles_h;
+        const int n0 = tw * p.wt, m0 = th * p.ht, b0 = tb * p.nt;
+        mbar_expect_tx(&s.full[st], tx_bytes);
+        for (int j = 0; j < 2; ++j)
+          tma_load_4d(s.a[st] + j * kABytes, &tmg, &s.full[st], o0 + 64 * j, n0 * p.os + p.px, m0 * p.os + p.py, b0);
+        for (int j = 0; j < nbx; ++j)
+          tma_load_4d(s.b[st] + j * kABytes, &tmx, &s.full[st], c0 + 64 * j, n0 * p.is + p.dx[tap],
+                      m0 * p.is + p.dy[tap], b0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(p.BN, true, true);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int st = kb % kStages, ph = (kb / kStages) & 1;
+        mbar_wait(&s.full[st], ph);
+        tc_fence_after();
+        // MN-major SWIZZLE_128B: 64-channel x 8-pixel atoms of 1024 B; LBO = next 64 channels (one box),
+        // SBO = next 8 pixels; one MMA consumes 16 pixels = 2048 B along K.
+        const uint64_t ad = make_desc(smem_u32(s.a[st]), kABytes, 1024);
+        const uint64_t bd = make_desc(smem_u32(s.b[st]), kABytes, 1024);
+#pragma unroll
+        for (int k = 0; k < kTileM / 16; ++k)
+          umma_f16(tmem_base, ad + (uint64_t)(k * 128), bd + (uint64_t)(k * 128), idesc, (kb | k) != 0);
+        umma_commit(&s.empty[st]);
+      }
+      umma_commit(s.done);
+    }
+  } else {
+    const int q = warp % 4;
+    const int o = o0 + q * 32 + lane;
+    mbar_wait(s.done, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    float* row = dw + (long long)o * p.w_ld + (long long)p.wtap[tap] * p.Cin + c0;
+    for (int c = 0; c < p.BN; c += 16) {
+      uint32_t v[16];
+      tmem_ld16(trow + c, v);
+      tmem_ld_wait();
+      if (o < p.Cout && nkb > 0) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          if (c0 + c + i < p.Cin)
+            atomicAdd(reinterpret_cast<float4*>(row + c + i),
+                      make_float4(__uint_as_float(v[i]) * p.scale, __uint_as_float(v[i + 1]) * p.scale,
+                                  __uint_as_float(v[i + 2]) * p.scale, __uint_as_float(v[i + 3]) * p.scale));
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<kMaxBN>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+// 4-D map over a dense channels-last bf16 tensor [N, H, W, C]: box {64, wt, ht, nt} walked with
+// element stride `es` along W and H.
+int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int wt, int ht, int nt, int es) {
+  EncodeTiledFn enc = get_encode();
+  LCGAN_CHECK(enc != nullptr, "cuTensorMapEncodeTiled unavailable (driver too old?)");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(wt * es), (cuuint32_t)(ht * es), (cuuint32_t)nt};
+  cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LCGAN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation) failed: %d (N=%d H=%d W=%d C=%d box=%d,%d,%d es=%d)",
+              (int)r, N, H, W, C, wt, ht, nt, es);
+  return 0;
+}
+
+int make_w_map(CUtensorMap* m, const void* base, int rows, long long ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  LCGAN_CHECK(enc != nullptr, "cuTensorMapEncodeTiled unavailable (driver too old?)");
+  cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LCGAN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight) failed: %d (rows=%d ld=%lld)", (int)r, rows, ld);
+  return 0;
+}
+
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// lattice tile {wt, ht, nt} with wt*ht*nt == 128
+bool lattice_tile(int MW, int MH, int* wt, int* ht, int* nt) {
+  if (!is_pow2(MW) || !is_pow2(MH)) return false;
+  *wt = MW < 16 ? MW : 16;
+  const int rem = kTileM / *wt;
+  *ht = MH < rem ? MH : rem;
+  *nt = rem / *ht;
+  return true;
+}
+
+bool dense_cl(int64_t sn, int64_t sh, int64_t sw, int64_t sc, int H, int W, int C) {
+  return sc == 1 && sw == C && sh == (int64_t)W * C && sn == (int64_t)H * W * C;
+}
+
+int fwd_smem_bytes() { return kStages * (kABytes + kBBytes) + 1024 + 256; }
+int wg_smem_bytes() { return kStages * (kWgABytes + kWgBBytes) + 1024 + 256; }
+
+}  // namespace
+
+extern "C" int lcgan_tapconv_tc_eligible(const lcgan_tapconv* d) {
+  if (!d) return 0;
+  if (d->x_dtype != LCGAN_BF16) return 0;
+  if (d->Cin % kBlockK != 0 || d->Cout % 16 != 0) return 0;
+  if (!dense_cl(d->xs_n, d->xs_h, d->xs_w, d->xs_c, d->IH, d->IW, d->Cin)) return 0;
+  // output: channel-innermost, 16-byte aligned pixel rows (dense channels-last or any such strides)
+  if (d->ys_c != 1 || d->ys_w % 8 != 0 || d->ys_h % 8 != 0 || d->ys_n % 8 != 0) return 0;
+  int wt, ht, nt;
+  if (!lattice_tile(d->MW, d->MH, &wt, &ht, &nt)) return 0;
+  if (d->is < 1 || d->is > 2 || d->os < 1 || d->os > 2) return 0;
+  if (d->ntaps < 1 || d->ntaps > LCGAN_MAX_TAPS) return 0;
+  return 1;
+}
+
+extern "C" int lcgan_tapconv_tc(const lcgan_tapconv* d, const void* x, const void* w2, void* y,
+                                const float* rowscale, const float* bias, const void* residual, void* stream) {
+  LCGAN_CHECK(lcgan_tapconv_tc_eligible(d), "tapconv_tc: descriptor not eligible for the tensor-core path");
+  LCGAN_CHECK(d->w_dtype == LCGAN_BF16, "tapconv_tc: weights must be bf16");
+  LCGAN_CHECK(x && w2 && y, "tapconv_tc: null tensor pointer");
+  LCGAN_CHECK(((uintptr_t)x % 16 == 0) && ((uintptr_t)w2 % 16 == 0) && ((uintptr_t)y % 16 == 0) &&
+              (d->w_ld % 8 == 0), "tapconv_tc: operands must be 16-byte aligned");
+  TcParams p{};
+  p.N = d->N; p.Cin = d->Cin; p.Cout = d->Cout;
+  lattice_tile(d->MW, d->MH, &p.wt, &p.ht, &p.nt);
+  p.tiles_w = d->MW / p.wt; p.tiles_h = d->MH / p.ht;
+  const int tiles_b = (d->N + p.nt - 1) / p.nt;
+  p.is = d->is; p.os = d->os; p.py = d->py; p.px = d->px;
+  p.ntaps = d->ntaps; p.kpt = d->Cin / kBlockK;
+  for (int t = 0; t < d->ntaps; ++t) { p.dy[t] = d->dy[t]; p.dx[t] = d->dx[t]; p.wtap[t] = d->wtap[t]; }
+  p.BN = d->Cout >= kMaxBN ? kMaxBN : d->Cout;       // Cout % 16 == 0
+  p.ys_n = d->ys_n; p.ys_h = d->ys_h; p.ys_w = d->ys_w;
+  p.y_f32 = d->y_dtype == LCGAN_F32;
+  p.acc_scale = d->acc_scale; p.bias_scale = d->bias_scale; p.slope = d->slope; p.gain = d->gain;
+
+  CUtensorMap tmx, tmw;
+  if (int e = make_act_map(&tmx, x, d->N, d->IH, d->IW, d->Cin, p.wt, p.ht, p.nt, d->is)) return e;
+  if (int e = make_w_map(&tmw, w2, d->Cout, d->w_ld, p.BN)) return e;
+
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(tapconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem_bytes());
+  });
+  LCGAN_CHECK(attr_err == cudaSuccess, "tapconv_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(attr_err));
+  dim3 grid(p.tiles_w * p.tiles_h * tiles_b, (d->Cout + p.BN - 1) / p.BN);
+  tapconv_tc_kernel<<<grid, kThreads, fwd_smem_bytes(), (cudaStream_t)stream>>>(tmx, tmw, p, y, rowscale, bias, residual);
+  LCGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int lcgan_tapconv_wgrad_tc(const lcgan_tapconv* d, const void* x, const void* g, float* dw2, float scale,
+                                      void* stream) {
+  // here the descriptor's X side is the layer input and its Y side is the output gradient G
+  LCGAN_CHECK(lcgan_tapconv_tc_eligible(d), "tapconv_wgrad_tc: descriptor not eligible");
+  LCGAN_CHECK(d->y_dtype == LCGAN_BF16 && d->Cout % 64 == 0 &&
+              dense_cl(d->ys_n, d->ys_h, d->ys_w, d->ys_c, d->OH, d->OW, d->Cout),
+              "tapconv_wgrad_tc: G must be dense channels-last bf16 with Cout %% 64 == 0");
+  LCGAN_CHECK(x && g && dw2 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)dw2 % 16 == 0) &&
+              d->w_ld % 4 == 0, "tapconv_wgrad_tc: bad pointers/alignment");
+  WgParams p{};
+  p.N = d->N; p.Cin = d->Cin; p.Cout = d->Cout;
+  lattice_tile(d->MW, d->MH, &p.wt, &p.ht, &p.nt);
+  p.tiles_w = d->MW / p.wt; p.tiles_h = d->MH / p.ht;
+  const int tiles_b = (d->N + p.nt - 1) / p.nt;
+  p.tiles_total = p.tiles_w * p.tiles_h * tiles_b;
+  p.is = d->is; p.os = d->os; p.py = d->py; p.px = d->px;
+  p.ntaps = d->ntaps;
+  for (int t = 0; t < d->ntaps; ++t) { p.dy[t] = d->dy[t]; p.dx[t] = d->dx[t]; p.wtap[t] = d->wtap[t]; }
+  p.BN = d->Cin >= kMaxBN ? kMaxBN : 64;            // Cin % 64 == 0
+  p.ctiles = (d->Cin + p.BN - 1) / p.BN;
+  const int otiles = (d->Cout + 127) / 128;
+  const int base = otiles * p.ctiles * d->ntaps;
+  int splits = (2 * 148 + base - 1) / base;
+  if (splits > p.tiles_total) splits = p.tiles_total;
+  if (splits < 1) splits = 1;
+  p.tiles_per_split = (p.tiles_total + splits - 1) / splits;
+  splits = (p.tiles_total + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.w_ld = d->w_ld; p.scale = scale;
+
+  CUtensorMap tmg, tmx;
+  if (int e = make_act_map(&tmg, g, d->N, d->OH, d->OW, d->Cout, p.wt, p.ht, p.nt, d->os)) return e;
+  if (int e = make_act_map(&tmx, x, d->N, d->IH, d->IW, d->Cin, p.wt, p.ht, p.nt, d->is)) return e;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(tapconv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem_bytes());
+  });
+  LCGAN_CHECK(attr_err == cudaSuccess, "tapconv_wgrad_tc: cannot raise dynamic shared memory: %s",
+              cudaGetErrorString(attr_err));
+  dim3 grid(otiles * p.ctiles, d->ntaps, splits);
+  tapconv_wgrad_tc_kernel<<<grid, kThreads, wg_smem_bytes(), (cudaStream_t)stream>>>(tmg, tmx, p, dw2);
+  LCGAN_LAUNCH_CHECK();
+  return 0;
+}

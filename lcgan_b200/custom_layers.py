@@ -28,7 +28,7 @@ def _as_act(x):
 
 class EqualizedWeight(nn.Module):
     """Reference custom_layers.py:7-14.  Parameter stored as randn/lr_mul under `.weight`; the
-    runtime scale c = lr_mul/sqrt(fan_in) is folded into the bf16/fp32 weight pack (ops.pack_weight)."""
+    runtime scale c = lr_mul/sqrt(fan_in) is applied to the fp32 accumulator in the conv epilogue."""
 
     def __init__(self, shape, lr_mul=1.0):
         super().__init__()
@@ -96,7 +96,9 @@ class ModulatedConv2d(nn.Module):
         w = self.weight.weight
         c = float(self.weight.c)
         # demodulation coefficients, fp32: d[b,o] = rsqrt(s^2 @ Wsq^T + eps)
-        wsq = (w * c).square().sum(dim=(2, 3))
+        # (from the weights as the conv sees them: rounded to the compute dtype, scaled in fp32)
+        wq = w.to(ops.act_dtype()).float() if ops.act_dtype() != torch.float32 else w
+        wsq = (wq * c).square().sum(dim=(2, 3))
         s = s.float()
         d = torch.rsqrt(ops.linear_act(s * s, wsq, None, wscale=1.0, bias_scale=1.0) + self.eps)
         xs = ops.Modulate.apply(_as_act(x), s)

@@ -15,6 +15,7 @@ from __future__ import annotations
 import contextlib
 import ctypes as C
 import math
+import os
 import threading
 import weakref
 
@@ -26,7 +27,7 @@ from ._lib import BF16, F32, TapConvDesc
 
 _state = threading.local()
 _ACT_DTYPE = torch.bfloat16
-_USE_TC = True
+_USE_TC = os.environ.get("LCGAN_DISABLE_TC", "0") != "1"
 
 
 def set_precision(mode: str):
@@ -118,14 +119,16 @@ _pack_cache = {}
 _pack_lock = threading.Lock()
 
 
-def pack_weight(w: torch.Tensor, scale: float, transposed: bool, dtype: torch.dtype) -> torch.Tensor:
-    """W2[o][tap*Cin + c] = scale * w[o, c, kh, kw]  (transposed: rows = c, contraction over o).
+def pack_weight(w: torch.Tensor, transposed: bool, dtype: torch.dtype) -> torch.Tensor:
+    """W2[o][tap*Cin + c] = w[o, c, kh, kw]  (transposed: rows = c, contraction over o), cast to the
+    compute dtype.  The equalized-lr constant is NOT folded in: the parameter values themselves are
+    rounded to bf16 and the constant is applied to the fp32 accumulator (lcgan_tapconv.acc_scale).
     Packs of nn.Parameters are cached until the parameter's version counter moves (optimizer
     step, load_state_dict); the cache entry dies with the parameter."""
     cacheable = isinstance(w, torch.nn.Parameter)
     if cacheable:
         key = (id(w), transposed, dtype)
-        tag = (w._version, w.data_ptr(), float(scale))
+        tag = (w._version, w.data_ptr())
         with _pack_lock:
             hit = _pack_cache.get(key)
             if hit is not None and hit[0] == tag:
@@ -134,7 +137,7 @@ def pack_weight(w: torch.Tensor, scale: float, transposed: bool, dtype: torch.dt
     if wd.dim() == 2:
         wd = wd[:, :, None, None]
     perm = (1, 2, 3, 0) if transposed else (0, 2, 3, 1)
-    p = (wd * scale).permute(*perm).reshape(wd.shape[perm[0]], -1).to(dtype).contiguous()
+    p = wd.permute(*perm).reshape(wd.shape[perm[0]], -1).to(dtype).contiguous()
     if cacheable:
         with _pack_lock:
             if key not in _pack_cache:
@@ -156,7 +159,7 @@ def unpack_wgrad(dw2: torch.Tensor, wshape, transposed: bool) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------
 # raw launches
 # ------------------------------------------------------------------------------------------
-def _fill_desc(d: TapConvDesc, l: plans.Launch, x, y, cin, cout, w2, slope, gain, bias_scale):
+def _fill_desc(d: TapConvDesc, l: plans.Launch, x, y, cin, cout, w2, slope, gain, bias_scale, acc_scale=1.0):
     n = x.shape[0]
     d.N, d.IH, d.IW, d.Cin = n, x.shape[2], x.shape[3], cin
     d.OH, d.OW, d.Cout = y.shape[2], y.shape[3], cout
@@ -169,23 +172,24 @@ def _fill_desc(d: TapConvDesc, l: plans.Launch, x, y, cin, cout, w2, slope, gain
     for t, (dy, dx, wt) in enumerate(l.taps):
         d.dy[t], d.dx[t], d.wtap[t] = dy, dx, wt
     d.w_ld = w2.shape[1] if w2 is not None else len(l.taps) * cin
-    d.bias_scale, d.slope, d.gain = bias_scale, slope, gain
+    d.acc_scale, d.bias_scale, d.slope, d.gain = acc_scale, bias_scale, slope, gain
 
 
 def tapconv(x, w2, y, plan: plans.Plan, rowscale=None, bias=None, residual=None, slope=1.0, gain=1.0,
-            bias_scale=1.0):
+            bias_scale=1.0, acc_scale=1.0):
     """y = epilogue(tapconv(x, w2)) for every launch of the plan; x, y logical NCHW."""
     _need_cuda(x, w2, y)
     cout, cin = w2.shape[0], x.shape[1]
     assert w2.shape[1] == plan.k * plan.k * cin, (w2.shape, plan.k, cin)
     assert x.shape[2:] == (plan.IH, plan.IW) and y.shape[2:] == (plan.OH, plan.OW) and y.shape[1] == cout
     if residual is not None:
-        assert residual.shape == y.shape and residual.stride() == y.stride() and residual.dtype == y.dtype
+        assert residual.shape == y.shape and residual.dtype == y.dtype
+        assert all(a == b for a, b, n in zip(residual.stride(), y.stride(), y.shape) if n > 1)
     lib = _lib.lib()
     st = _stream(x)
     d = TapConvDesc()
     for l in plan.launches:
-        _fill_desc(d, l, x, y, cin, cout, w2, slope, gain, bias_scale)
+        _fill_desc(d, l, x, y, cin, cout, w2, slope, gain, bias_scale, acc_scale)
         fn = "lcgan_tapconv_tc" if (_USE_TC and lib.lcgan_tapconv_tc_eligible(C.byref(d))) else "lcgan_tapconv_simt"
         _lib.call(fn, C.byref(d), _ptr(x), _ptr(w2), _ptr(y), _ptr(rowscale), _ptr(bias), _ptr(residual), st)
     return y
@@ -209,8 +213,18 @@ def tapconv_wgrad(x, g, plan: plans.Plan, cin, cout, scale=1.0):
     return dw2
 
 
+_USE_WGRAD_TC = _USE_TC
+
+
+def set_wgrad_tensor_cores(flag: bool):
+    global _USE_WGRAD_TC
+    _USE_WGRAD_TC = bool(flag)
+
+
 def _wgrad_tc_ok(d):
-    return False   # enabled once the tcgen05 wgrad kernel is validated
+    # the wgrad kernel additionally needs G dense channels-last bf16 with Cout % 64 == 0
+    return (_USE_WGRAD_TC and d.y_dtype == BF16 and d.Cout % 64 == 0 and d.ys_c == 1 and d.ys_w == d.Cout
+            and d.ys_h == d.OW * d.Cout and d.ys_n == d.OH * d.OW * d.Cout)
 
 
 def _alloc_out(n, c, h, w, dtype, device, nchw):
@@ -231,9 +245,9 @@ class ConvFwd(torch.autograd.Function):
         ctx.plan, ctx.transposed, ctx.wscale = plan, transposed, wscale
         ctx.x_dtype, ctx.x_nchw = x.dtype, (x.is_contiguous() and not _is_cl(x))
         ctx.save_for_backward(x, w)
-        w2 = pack_weight(w, wscale, transposed, torch.float32 if x.dtype == torch.float32 else torch.bfloat16)
+        w2 = pack_weight(w, transposed, torch.float32 if x.dtype == torch.float32 else torch.bfloat16)
         y = _alloc_out(x.shape[0], w2.shape[0], plan.OH, plan.OW, out_dtype, x.device, out_nchw)
-        return tapconv(x, w2, y, plan)
+        return tapconv(x, w2, y, plan, acc_scale=wscale)
 
     @staticmethod
     def backward(ctx, dy):
@@ -312,11 +326,11 @@ class ConvAct(torch.autograd.Function):
                 out_nchw):
         assert residual is None or slope == 1.0, "residual fusion only without activation"
         compute = torch.float32 if x.dtype == torch.float32 else torch.bfloat16
-        w2 = pack_weight(w, wscale, False, compute)
+        w2 = pack_weight(w, False, compute)
         y = _alloc_out(x.shape[0], w2.shape[0], plan.OH, plan.OW, out_dtype, x.device, out_nchw)
         assert rowscale is None or (rowscale.is_contiguous() and rowscale.dtype == torch.float32)
         assert bias is None or (bias.is_contiguous() and bias.dtype == torch.float32)
-        tapconv(x, w2, y, plan, rowscale, bias, residual, slope, gain, bias_scale)
+        tapconv(x, w2, y, plan, rowscale, bias, residual, slope, gain, bias_scale, wscale)
         ctx.save_for_backward(x, w, bias, rowscale, y)
         ctx.cfg = (wscale, plan, slope, gain, bias_scale, residual is not None)
         ctx.x_fmt = (x.dtype, x.is_contiguous() and not _is_cl(x))
@@ -531,8 +545,7 @@ class Warp(torch.autograd.Function):
         x, flow = ctx.saved_tensors
         dout = _cl(dout, x.dtype)
         n, c, h, w = x.shape
-        dx_acc = torch.zeros((n, c, h, w), dtype=torch.float32, device=x.device,
-                             memory_format=torch.channels_last)
+        dx_acc = empty_cl(n, c, h, w, torch.float32, x.device).zero_()
         dflow = torch.empty_like(flow)
         _lib.call("lcgan_warp_bwd", _ptr(x), _ptr(flow), _ptr(dout), _ptr(dx_acc), _ptr(dflow), _dt(x),
                   n, h, w, c, C.c_float(ctx.scale), _stream(x))

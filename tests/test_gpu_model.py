@@ -110,9 +110,21 @@ def test_per_layer_activations_and_grads_vs_oracle(mode):
     from lcgan_b200 import ops
     O, cfg, gsd, dsd, G, D = _build(64, 5, mode)
     tol = 1e-4 if mode == "fp32" else 1e-2
+    # Gradients pass through leaky-relu masks.  Two correct fp32 implementations disagree on the sign
+    # of a pre-activation that is within rounding noise of zero; ONE such flip among ~5e5 elements
+    # moves a layer's gradient by ~1e-3 rel-L2 (measured: against an fp64 oracle our kernels and
+    # torch's own fp32 GPU kernels each show 1e-6 on most blocks and ~1.5e-3 on a block where one of
+    # them flipped - DESIGN.md "numerics").  Hence the gradient bound is 5e-3, the forward bound 1e-4.
+    gtol = 5e-3 if mode == "fp32" else 3e-2
     dt = torch.float32 if mode == "fp32" else torch.bfloat16
-    gcuda = {k: v.cuda() for k, v in gsd.items()}
-    dcuda = {k: v.cuda() for k, v in dsd.items()}
+    # the oracle sees the parameter values the kernels see: conv weights rounded to the compute
+    # dtype (bf16 mode), everything else fp32 - so lrelu masks agree and the comparison measures
+    # the kernels, not the mask flips that weight rounding alone causes (numerics)
+    def q(k, v):
+        conv_w = k.endswith("weight.weight") and v.dim() == 4
+        return v.to(dt).float().cuda() if conv_w else v.cuda()
+    gcuda = {k: q(k, v) for k, v in gsd.items()}
+    dcuda = {k: q(k, v) for k, v in dsd.items()}
     torch.manual_seed(1)
     b = 4
     glat, alat = torch.randn(b, 64, device="cuda"), torch.randn(b, 512, device="cuda")
@@ -129,10 +141,10 @@ def test_per_layer_activations_and_grads_vs_oracle(mode):
         ym = G.model[i](xm, glat[:, None], alat[:, None].expand(-1, 2, -1))
         ym.backward(gy.to(dt).contiguous(memory_format=torch.channels_last))
         assert rel_l2(ym.float(), yo.detach()) < tol, f"G block {i} fwd"
-        assert rel_l2(xm.grad.float(), xo.grad) < tol * 3, f"G block {i} dx"
+        assert rel_l2(xm.grad.float(), xo.grad) < gtol, f"G block {i} dx"
         for k, p in G.model[i].named_parameters():
             ref = gcuda[f"model.{i}.{k}"].grad
-            assert rel_l2(p.grad, ref) < tol * 5, f"G block {i} {k}"
+            assert rel_l2(p.grad, ref) < gtol, f"G block {i} {k}"
     for i, (cin, cout) in enumerate(cfg.d_channels()):
         res = cfg.img_resolution >> i
         x = torch.randn(b, cin, res, res, device="cuda").to(dt).float()
@@ -147,6 +159,6 @@ def test_per_layer_activations_and_grads_vs_oracle(mode):
         ym = D.shared_model[i + 2](xm)
         ym.backward(gy.to(dt).contiguous(memory_format=torch.channels_last))
         assert rel_l2(ym.float(), yo.detach()) < tol, f"D block {i} fwd"
-        assert rel_l2(xm.grad.float(), xo.grad) < tol * 3, f"D block {i} dx"
+        assert rel_l2(xm.grad.float(), xo.grad) < gtol, f"D block {i} dx"
         for k, p in D.shared_model[i + 2].named_parameters():
-            assert rel_l2(p.grad, dcuda[f"shared_model.{i + 2}.{k}"].grad) < tol * 5, f"D block {i} {k}"
+            assert rel_l2(p.grad, dcuda[f"shared_model.{i + 2}.{k}"].grad) < gtol, f"D block {i} {k}"

@@ -1,0 +1,91 @@
+"""tcgen05 kernels against the CUDA-core kernels on identical bf16 operands (both accumulate in
+fp32, so they must agree to accumulation-order noise), over the lattice shapes the networks use:
+stride-1/2, the four transposed-conv phases, 1x1, linear, small maps with batch folded into the
+tile, partial batch tiles, every epilogue feature."""
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _setup():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    torch.manual_seed(0)
+    from lcgan_b200 import ops
+    ops.set_precision("bf16")
+    yield
+    ops.set_tensor_cores(True)
+    ops.set_wgrad_tensor_cores(True)
+
+
+def _cl(x):
+    return x.contiguous(memory_format=torch.channels_last)
+
+
+def _plan(kind, k, H, W):
+    from lcgan_b200 import plans
+    if kind == "up2":
+        return plans.conv_transpose_up2(3, H, W)
+    if kind == "s2":
+        return plans.conv(k, 2, H, W)
+    if kind == "s2_adj":
+        return plans.adjoint(plans.conv(k, 2, 2 * H, 2 * W))
+    if kind == "up2_adj":
+        return plans.adjoint(plans.conv_transpose_up2(3, H // 2, W // 2))
+    return plans.conv(k, 1, H, W)
+
+
+CASES = [  # kind, k, N, Cin, Cout, H, W
+    ("s1", 3, 2, 64, 64, 16, 16), ("s1", 3, 3, 128, 256, 8, 8), ("s1", 3, 5, 64, 32, 4, 4),
+    ("s1", 1, 2, 64, 128, 32, 32), ("s2", 3, 2, 64, 128, 16, 16), ("up2", 3, 2, 128, 64, 8, 8),
+    ("s2_adj", 3, 2, 128, 64, 8, 8), ("up2_adj", 3, 2, 64, 128, 16, 16), ("s1", 1, 32, 8192, 512, 1, 1),
+    ("s1", 3, 1, 192, 48, 64, 32),
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("out_f32", [False, True])
+def test_tc_forward_matches_simt(case, out_f32):
+    from lcgan_b200 import ops, _lib
+    kind, k, N, Cin, Cout, H, W = case
+    plan = _plan(kind, k, H, W)
+    x = _cl((torch.randn(N, Cin, plan.IH, plan.IW, device="cuda")).bfloat16())
+    w2 = (torch.randn(Cout, k * k * Cin, device="cuda") / (k * k * Cin) ** 0.5).bfloat16()
+    rs = torch.rand(N, Cout, device="cuda") + 0.5
+    bias = torch.randn(Cout, device="cuda")
+    dt = torch.float32 if out_f32 else torch.bfloat16
+    res = _cl(torch.randn(N, Cout, plan.OH, plan.OW, device="cuda").to(dt))
+    outs = []
+    for tc in (False, True):
+        ops.set_tensor_cores(tc)
+        before = _lib.launches
+        y = ops.empty_cl(N, Cout, plan.OH, plan.OW, dt, "cuda").fill_(float("nan"))
+        ops.tapconv(x, w2, y, plan, rs, bias, None, slope=0.2, gain=1.4, bias_scale=0.5)
+        y2 = ops.empty_cl(N, Cout, plan.OH, plan.OW, dt, "cuda").fill_(float("nan"))
+        ops.tapconv(x, w2, y2, plan, None, None, res, slope=1.0, gain=0.7)
+        outs.append((y.float(), y2.float()))
+    torch.cuda.synchronize()
+    (a, a2), (b, b2) = outs
+    assert torch.isfinite(b).all() and torch.isfinite(b2).all()
+    tol = 1e-5 if out_f32 else 4e-3
+    assert rel_l2(b, a) < tol, f"{case}: {rel_l2(b, a)}"
+    assert rel_l2(b2, a2) < tol, f"{case} residual: {rel_l2(b2, a2)}"
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c[4] % 64 == 0])
+def test_tc_wgrad_matches_simt(case):
+    from lcgan_b200 import ops
+    kind, k, N, Cin, Cout, H, W = case
+    plan = _plan(kind, k, H, W)
+    x = _cl(torch.randn(N, Cin, plan.IH, plan.IW, device="cuda").bfloat16())
+    g = _cl(torch.randn(N, Cout, plan.OH, plan.OW, device="cuda").bfloat16())
+    ops.set_wgrad_tensor_cores(False)
+    ref = ops.tapconv_wgrad(x, g, plan, Cin, Cout)
+    ops.set_wgrad_tensor_cores(True)
+    out = ops.tapconv_wgrad(x, g, plan, Cin, Cout)
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref) < 1e-5, f"{case}: {rel_l2(out, ref)}"
