@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""LC-GAN G+D training throughput on B200 (BASELINE.json metric), one JSON line on rank 0.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--res R] [--batch B] [--impl ours|reference]
+
+A *step* is one reference iteration (loader.py:44-54): generator step + EMA update + discriminator
+step on a global batch of B images, with the reference's loss schedule (aux losses on even
+iterations, R1 on iteration % 8 == 1, sparsity on even G steps).  The timed region starts at an
+iteration index that is a multiple of 8, so K = 8*n covers whole schedule cycles.
+
+  value    img/s, inputs resident in HBM, timed on the device with CUDA events (max over ranks)
+  e2e      img/s through the same public modules with the step's real images / views / latents
+           copied from pinned host memory and both losses read back (.item()) every step
+  roofline the dominant kernel (by summed device time in an event-instrumented pass): algorithmic
+           FLOPs or bytes / event-measured duration, against MEASURED_PEAKS.json
+  cpu_baseline / --impl reference: the oracle port of the reference's CPU path (oracle/), timed on
+           the host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "G+D train img/s"
+FLOP_PER_IMG_ITER = {256: 2.03e12, 512: 2.65e12, 1024: 3.27e12}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--res", type=int, default=int(os.environ.get("LCGAN_BENCH_RES", "256")))
+    ap.add_argument("--batch", type=int, default=32, help="global batch (reference recipes: 32)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--freeze-d", action="store_true", help="post-freezeD schedule (worker.py:127-131)")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm": d["hbm_gbs"], "tensor_burst": d["bf16_tflops"],
+                "tensor_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor_sustained": 1400.0, "src": "fallback"}
+
+
+def workload_name(res, batch):
+    hp = {256: "ffhq_256", 512: "afhq_v2_512 (freezeD_layer 4)", 1024: "ffhq_1024 (freezeD_layer 5)"}.get(res, "custom")
+    return f"LC-GAN {res}x{res} training batch {batch} ({hp} hyperparams), synthetic data"
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md "clocks DURING the timed region")
+# ---------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's CPU path
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_sample(res, budget_s=150.0):
+    """Time reference iterations 1 (G odd + D odd with R1) and 0 (G even + D even: aux + l_s) on the
+    host cores, fp32, all threads, at batch 1 and the bench resolution, through the oracle port.
+    Returns (img_per_s, cores, sample description)."""
+    import torch
+    from oracle import lcgan_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.Config(img_resolution=res)
+    hp = O.Hyper(lr=1e-3 if res == 1024 else 2e-3)
+    tr = O.OracleTrainer(cfg, hp, O.make_generator_state(cfg, 0), O.make_discriminator_state(cfg, 1))
+    gen = torch.Generator().manual_seed(1000)
+    b = 1
+    done, t_total = [], 0.0
+    for it in (1, 0):
+        zg, zd = O.synthetic_latents(b, cfg, gen), O.synthetic_latents(b, cfg, gen)
+        data = O.synthetic_data(b, cfg, gen)
+        t0 = time.perf_counter()
+        tr.iteration(it, zg, zd, data)
+        dt = time.perf_counter() - t0
+        done.append((it, dt)); t_total += dt
+        if t_total > budget_s / 3:
+            break
+    imgs = b * len(done)
+    desc = (f"oracle port (oracle/lcgan_oracle.py, torch CPU fp32, {torch.get_num_threads()} threads): full "
+            f"iterations {[i for i, _ in done]} at batch {b}, {res}x{res} "
+            f"({', '.join(f'it{i}={t:.1f}s' for i, t in done)}); img/s = images / time of these iterations")
+    return imgs / t_total, cores, desc
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    v, cores, desc = cpu_reference_sample(args.res)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "img/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * args.batch / v,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.res, args.batch), "note": "CPU arm runs on host cores only"},
+            "cpu_baseline": {"value": v, "unit": "img/s", "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+    from lcgan_b200 import _lib, cnn, ops, train_step as T
+    from oracle.lcgan_oracle import Config, Hyper   # configuration containers only (no compute)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        entry.build()
+    if world > 1:
+        dist.barrier()
+    ops.set_precision(args.precision)
+    assert args.batch % world == 0
+    b = args.batch // world                                   # worker.py:35
+    res = args.res
+    cfg = Config(img_resolution=res)
+    hp = Hyper(lr=1e-3 if res == 1024 else 2e-3)             # README.md:29/45/49
+    torch.manual_seed(0)
+    G, D = cnn.Generator(cfg.namespace()).to(dev), cnn.Discriminator(cfg.namespace()).to(dev)
+    if world > 1:
+        from torch.nn.parallel import DistributedDataParallel as DDP     # worker.py:88-96
+        G = DDP(G, device_ids=[local_rank], broadcast_buffers=False, find_unused_parameters=True)
+        D = DDP(D, device_ids=[local_rank], broadcast_buffers=False, find_unused_parameters=True)
+    fl = {256: 3, 512: 4, 1024: 5}.get(res, 3)
+    tr = T.Trainer(G, D, hp, freeze_d_start=0 if args.freeze_d else 10 ** 9, freeze_d_layer=fl)
+
+    gcpu = torch.Generator().manual_seed(1000 + rank)
+    n_pool = 2
+    host = [{k: (torch.rand(b, 3, res, res, generator=gcpu) * 2 - 1).pin_memory()
+             for k in ("image", "geometry_change", "appearance_change")} for _ in range(n_pool)]
+    host_z = [{k: torch.randn(b, 64, generator=gcpu).pin_memory()
+               for k in ("rand1", "rand2", "resample1", "resample2", "drand1", "drand2")} for _ in range(n_pool)]
+    resident = [{k: v.to(dev) for k, v in h.items()} for h in host]
+
+    def latents():
+        z = {k: torch.randn(b, 64, device=dev) for k in ("rand1", "rand2", "resample1", "resample2")}
+        zd = {k: torch.randn(b, 64, device=dev) for k in ("rand1", "rand2")}
+        return z, zd
+
+    def step_resident(it):
+        z, zd = latents()                                     # device RNG, like worker.py:145-146,182-185
+        gl = tr.g_step(it, z)
+        tr.ema.update(it)
+        dl = tr.d_step(it, zd, resident[it % n_pool])
+        return gl, dl
+
+    def step_e2e(it):
+        h, hz = host[it % n_pool], host_z[it % n_pool]
+        data = {k: v.to(dev, non_blocking=True) for k, v in h.items()}
+        zs = {k: v.to(dev, non_blocking=True) for k, v in hz.items()}
+        z = {k: zs[k] for k in ("rand1", "rand2", "resample1", "resample2")}
+        zd = {"rand1": zs["drand1"], "rand2": zs["drand2"]}
+        return tr.iteration(it, z, zd, data)                  # .item() on both losses (worker.py:177,214)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, first_it, k):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = _lib.launches
+        e0.record()
+        for i in range(k):
+            fn(first_it + i)
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms), _lib.launches - launches0
+
+    K, W = args.steps, max(args.warmup, 3)
+    it0 = 0
+    for i in range(W):
+        step_resident(it0 + i)
+    it0 = ((it0 + W + 7) // 8) * 8                           # timed region starts on a cycle boundary
+    clocks = Clocks(local_rank) if rank == 0 else None
+    ms, launches = timed(step_resident, it0, K)
+    clk = clocks.stop() if clocks else None
+    value = args.batch * K / (ms / 1000.0)
+    it0 += ((K + 7) // 8) * 8
+
+    e2e = None
+    if not args.no_e2e:
+        step_e2e(it0); it0 += 8                               # warm the pinned-copy path
+        ms_e, _ = timed(step_e2e, it0, K)
+        it0 += ((K + 7) // 8) * 8
+        h2d = sum(v.numel() * v.element_size() for v in host[0].values()) + \
+            sum(v.numel() * v.element_size() for v in host_z[0].values())
+        e2e = {"value": args.batch * K / (ms_e / 1000.0), "unit": "img/s", "h2d_bytes_per_step": h2d * world,
+               "d2h_bytes_per_step": 8 * world}
+
+    roof, kernels = None, None
+    if not args.no_roofline and rank == 0:
+        roof, kernels = roofline_pass(step_resident, it0, _lib, peaks())
+    if world > 1:
+        dist.barrier()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        del tr, G, D
+        torch.cuda.empty_cache()
+        v, cores, desc = cpu_reference_sample(min(res, 256) if res > 256 else res)
+        if res > 256:
+            desc += f"  [measured at 256x256: the {res}x{res} CPU step does not fit the time bound]"
+        cpu = {"value": v, "unit": "img/s", "cores": cores, "kind": "port", "sample": desc}
+
+    if rank == 0:
+        flop = FLOP_PER_IMG_ITER.get(res)
+        pk = peaks()
+        line = {
+            "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": workload_name(res, args.batch), "global_batch": args.batch, "local_batch": b,
+                       "resolution": res, "parallelism": f"dp{world}", "schedule": "timed region = iterations "
+                       f"{it0 - 2 * ((K + 7) // 8) * 8 - (8 if not args.no_e2e else 0)}..+{K} (cycle-aligned)",
+                       "freezeD": bool(args.freeze_d), "l2": "activations per layer exceed the 126 MB L2; no flush needed",
+                       "model_tflop_per_img_iter": flop / 1e12 if flop else None,
+                       "model_tflops_achieved": value * flop / 1e12 if flop else None,
+                       "frac_of_bf16_peak_sustained": (value * flop / 1e12) / (world * pk["tensor_sustained"]) if flop else None,
+                       "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
+                       "peaks": pk["src"]},
+            "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+            "kernels": kernels,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def roofline_pass(step_fn, it0, _lib, pk):
+    """One extra (untimed-for-the-headline) cycle with a CUDA event pair around every launch of our
+    library: per-kernel device time, algorithmic FLOPs (tap convs) and bytes.  The dominant kernel
+    by summed time is the one reported."""
+    import torch
+    _lib.profile_begin()
+    for i in range(8):
+        step_fn(it0 + i)
+    torch.cuda.synchronize()
+    stats = _lib.profile_end()
+    rows = []
+    for name, s in stats.items():
+        rows.append({"kernel": name, "launches": s["n"], "ms": s["ms"], "tflops": (s["flops"] / (s["ms"] / 1e3) / 1e12)
+                     if s["flops"] and s["ms"] > 0 else None,
+                     "gbs": (s["bytes"] / (s["ms"] / 1e3) / 1e9) if s["bytes"] and s["ms"] > 0 else None})
+    rows.sort(key=lambda r: -r["ms"])
+    total = sum(r["ms"] for r in rows) or 1.0
+    for r in rows:
+        r["share"] = r["ms"] / total
+    top = rows[0]
+    s = stats[top["kernel"]]
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(top["kernel"])
+    if top["tflops"] is not None and "tapconv" in top["kernel"]:
+        roof = {"kernel": top["kernel"], "bound": "tensor", "achieved": top["tflops"], "peak": pk["tensor_sustained"],
+                "unit": "TFLOP/s", "frac": top["tflops"] / pk["tensor_sustained"], "traffic": traffic,
+                "peak_source": pk["src"] + " (sustained: kernel timed inside a long step)",
+                "avg_launch_ms": s["ms"] / s["n"], "share_of_step": top["share"],
+                "flop_per_launch": s["flops"] / s["n"]}
+    else:
+        roof = {"kernel": top["kernel"], "bound": "hbm", "achieved": top["gbs"], "peak": pk["hbm"], "unit": "GB/s",
+                "frac": (top["gbs"] or 0) / pk["hbm"], "traffic": traffic, "peak_source": pk["src"],
+                "avg_launch_ms": s["ms"] / s["n"], "share_of_step": top["share"],
+                "bytes_per_launch": s["bytes"] / s["n"]}
+    return roof, rows[:12]
+
+
+if __name__ == "__main__":
+    main()

@@ -118,7 +118,42 @@ def check(rc: int, what: str):
 launches = 0
 
 
-def call(name: str, *args):
+_prof = None
+
+
+def profile_begin():
+    """Start recording a CUDA-event pair around every launch (bench.py roofline pass)."""
+    global _prof
+    _prof = []
+
+
+def profile_end():
+    """Stop recording; returns {tag: {n, ms, flops, bytes}} (synchronises the device)."""
+    global _prof
+    import torch
+    torch.cuda.synchronize()
+    out = {}
+    for tag, e0, e1, flops, nbytes in _prof:
+        s = out.setdefault(tag, {"n": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+        s["n"] += 1
+        s["ms"] += e0.elapsed_time(e1)
+        s["flops"] += flops
+        s["bytes"] += nbytes
+    _prof = None
+    return out
+
+
+def call(name: str, *args, flops=0, nbytes=0, tag=None):
+    """Launch one C-ABI entry point on the caller's current stream.  flops / nbytes are the
+    ALGORITHMIC work of the launch, used only by the profiling pass."""
     global launches
     launches += 1
+    if _prof is None:
+        check(getattr(lib(), name)(*args), name)
+        return
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     check(getattr(lib(), name)(*args), name)
+    e1.record()
+    _prof.append((tag or name.replace("lcgan_", ""), e0, e1, flops, nbytes))

@@ -191,7 +191,11 @@ def tapconv(x, w2, y, plan: plans.Plan, rowscale=None, bias=None, residual=None,
     for l in plan.launches:
         _fill_desc(d, l, x, y, cin, cout, w2, slope, gain, bias_scale, acc_scale)
         fn = "lcgan_tapconv_tc" if (_USE_TC and lib.lcgan_tapconv_tc_eligible(C.byref(d))) else "lcgan_tapconv_simt"
-        _lib.call(fn, C.byref(d), _ptr(x), _ptr(w2), _ptr(y), _ptr(rowscale), _ptr(bias), _ptr(residual), st)
+        rows = x.shape[0] * l.MH * l.MW
+        _lib.call(fn, C.byref(d), _ptr(x), _ptr(w2), _ptr(y), _ptr(rowscale), _ptr(bias), _ptr(residual), st,
+                  flops=2.0 * rows * len(l.taps) * cin * cout,
+                  nbytes=(x.numel() * x.element_size() + y.numel() * y.element_size()) / len(plan.launches)
+                  + w2.numel() * w2.element_size() * len(l.taps) / (plan.k * plan.k))
     return y
 
 
@@ -209,7 +213,10 @@ def tapconv_wgrad(x, g, plan: plans.Plan, cin, cout, scale=1.0):
         d.w_ld = plan.k * plan.k * cin
         fn = "lcgan_tapconv_wgrad_tc" if (_USE_TC and lib.lcgan_tapconv_tc_eligible(C.byref(d))
                                           and _wgrad_tc_ok(d)) else "lcgan_tapconv_wgrad_simt"
-        _lib.call(fn, C.byref(d), _ptr(x), _ptr(g), _ptr(dw2), C.c_float(scale), st)
+        rows = x.shape[0] * l.MH * l.MW
+        _lib.call(fn, C.byref(d), _ptr(x), _ptr(g), _ptr(dw2), C.c_float(scale), st,
+                  flops=2.0 * rows * len(l.taps) * cin * cout,
+                  nbytes=(x.numel() * x.element_size() + g.numel() * g.element_size()) / len(plan.launches))
     return dw2
 
 
@@ -300,7 +307,8 @@ class ActBwd(torch.autograd.Function):
         r0 = torch.zeros((n, c), dtype=torch.float32, device=y.device) if want_r0 else None
         r1 = torch.zeros((n, c), dtype=torch.float32, device=y.device) if want_r1 else None
         _lib.call("lcgan_act_bwd", _ptr(dy), _ptr(y), _ptr(gout), _ptr(d), _ptr(r0), _ptr(r1), _dt(y),
-                  n, h * w, c, C.c_float(slope), C.c_float(gain), _stream(y))
+                  n, h * w, c, C.c_float(slope), C.c_float(gain), _stream(y),
+                  nbytes=3 * y.numel() * y.element_size())
         ctx.save_for_backward(y, d)
         ctx.slope, ctx.gain = slope, gain
         outs = (gout, r0 if want_r0 else gout.new_zeros(()), r1 if want_r1 else gout.new_zeros(()))
@@ -393,7 +401,8 @@ class Box3(torch.autograd.Function):
         n, c, h, w = x.shape
         out = torch.empty_like(x)
         _lib.call("lcgan_box3", _ptr(x), None, _ptr(out), _dt(x), n, h, w, c,
-                  C.c_float(1.0), C.c_float(1.0), C.c_float(1.0), C.c_float(1.0), _stream(x))
+                  C.c_float(1.0), C.c_float(1.0), C.c_float(1.0), C.c_float(1.0), _stream(x),
+                  nbytes=2 * x.numel() * x.element_size())
         return out
 
     @staticmethod
@@ -411,7 +420,8 @@ class Pool2(torch.autograd.Function):
         n, c, h, w = x.shape
         ctx.scale = scale
         out = empty_cl(n, c, h // 2, w // 2, x.dtype, x.device)
-        _lib.call("lcgan_pool2", _ptr(x), _ptr(out), _dt(x), n, h, w, c, C.c_float(scale), _stream(x))
+        _lib.call("lcgan_pool2", _ptr(x), _ptr(out), _dt(x), n, h, w, c, C.c_float(scale), _stream(x),
+                  nbytes=1.25 * x.numel() * x.element_size())
         return out
 
     @staticmethod
@@ -429,7 +439,8 @@ class Up2(torch.autograd.Function):
         n, c, h, w = x.shape
         ctx.scale = scale
         out = empty_cl(n, c, h * 2, w * 2, x.dtype, x.device)
-        _lib.call("lcgan_up2", _ptr(x), _ptr(out), _dt(x), n, h, w, c, C.c_float(scale), _stream(x))
+        _lib.call("lcgan_up2", _ptr(x), _ptr(out), _dt(x), n, h, w, c, C.c_float(scale), _stream(x),
+                  nbytes=5 * x.numel() * x.element_size())
         return out
 
     @staticmethod
@@ -450,7 +461,8 @@ class Box3Act(torch.autograd.Function):
         n, c, h, w = x.shape
         y = torch.empty_like(x)
         _lib.call("lcgan_box3", _ptr(x), None, _ptr(y), _dt(x), n, h, w, c,
-                  C.c_float(1.0), C.c_float(1.0), C.c_float(slope), C.c_float(gain), _stream(x))
+                  C.c_float(1.0), C.c_float(1.0), C.c_float(slope), C.c_float(gain), _stream(x),
+                  nbytes=2 * x.numel() * x.element_size(), tag="box3_act")
         ctx.save_for_backward(y)
         ctx.cfg = (slope, gain)
         return y
@@ -464,7 +476,8 @@ class Box3Act(torch.autograd.Function):
         n, c, h, w = y.shape
         dx = torch.empty_like(y)
         _lib.call("lcgan_box3", _ptr(dy), _ptr(y), _ptr(dx), _dt(y), n, h, w, c,
-                  C.c_float(slope), C.c_float(gain), C.c_float(1.0), C.c_float(1.0), _stream(y))
+                  C.c_float(slope), C.c_float(gain), C.c_float(1.0), C.c_float(1.0), _stream(y),
+                  nbytes=3 * y.numel() * y.element_size(), tag="box3_act_bwd")
         return dx, None, None
 
 
@@ -477,7 +490,8 @@ class Up2BoxAdd(torch.autograd.Function):
         s, t = _cl(s), _cl(t)
         n, c, h, w = s.shape
         out = torch.empty_like(t)
-        _lib.call("lcgan_up2box_add", _ptr(s), _ptr(t), _ptr(out), _dt(s), n, h, w, c, _stream(s))
+        _lib.call("lcgan_up2box_add", _ptr(s), _ptr(t), _ptr(out), _dt(s), n, h, w, c, _stream(s),
+                  nbytes=(s.numel() + 2 * t.numel()) * s.element_size())
         return out
 
     @staticmethod
@@ -489,9 +503,11 @@ class Up2BoxAdd(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             tmp = torch.empty_like(dy)
             _lib.call("lcgan_box3", _ptr(dy), None, _ptr(tmp), _dt(dy), n, h, w, c,
-                      C.c_float(1.0), C.c_float(1.0), C.c_float(1.0), C.c_float(1.0), _stream(dy))
+                      C.c_float(1.0), C.c_float(1.0), C.c_float(1.0), C.c_float(1.0), _stream(dy),
+                      nbytes=2 * dy.numel() * dy.element_size())
             ds = empty_cl(n, c, h // 2, w // 2, dy.dtype, dy.device)
-            _lib.call("lcgan_pool2", _ptr(tmp), _ptr(ds), _dt(dy), n, h, w, c, C.c_float(1.0), _stream(dy))
+            _lib.call("lcgan_pool2", _ptr(tmp), _ptr(ds), _dt(dy), n, h, w, c, C.c_float(1.0), _stream(dy),
+                      nbytes=1.25 * dy.numel() * dy.element_size())
         return ds, (dy if ctx.needs_input_grad[1] else None)
 
 
@@ -505,7 +521,8 @@ class Modulate(torch.autograd.Function):
         s = s.contiguous().float()
         n, c, h, w = x.shape
         xs = torch.empty_like(x)
-        _lib.call("lcgan_modulate", _ptr(x), _ptr(s), _ptr(xs), _dt(x), n, h * w, c, _stream(x))
+        _lib.call("lcgan_modulate", _ptr(x), _ptr(s), _ptr(xs), _dt(x), n, h * w, c, _stream(x),
+                  nbytes=2 * x.numel() * x.element_size())
         ctx.save_for_backward(x, s)
         return xs
 
@@ -518,7 +535,7 @@ class Modulate(torch.autograd.Function):
         dx = torch.empty_like(x)
         ds = torch.zeros_like(s)
         _lib.call("lcgan_modulate_bwd", _ptr(x), _ptr(t), _ptr(s), _ptr(dx), _ptr(ds), _dt(x), n, h * w, c,
-                  _stream(x))
+                  _stream(x), nbytes=3 * x.numel() * x.element_size())
         return dx, ds
 
 
@@ -534,7 +551,7 @@ class Warp(torch.autograd.Function):
         n, c, h, w = x.shape
         out = torch.empty_like(x)
         _lib.call("lcgan_warp_fwd", _ptr(x), _ptr(flow), _ptr(out), _dt(x), n, h, w, c, C.c_float(scale),
-                  _stream(x))
+                  _stream(x), nbytes=2 * x.numel() * x.element_size() + flow.numel() * 4)
         ctx.save_for_backward(x, flow)
         ctx.scale = scale
         return out
@@ -548,10 +565,12 @@ class Warp(torch.autograd.Function):
         dx_acc = empty_cl(n, c, h, w, torch.float32, x.device).zero_()
         dflow = torch.empty_like(flow)
         _lib.call("lcgan_warp_bwd", _ptr(x), _ptr(flow), _ptr(dout), _ptr(dx_acc), _ptr(dflow), _dt(x),
-                  n, h, w, c, C.c_float(ctx.scale), _stream(x))
+                  n, h, w, c, C.c_float(ctx.scale), _stream(x),
+                  nbytes=2 * x.numel() * x.element_size() + x.numel() * 4 + 2 * flow.numel() * 4)
         if x.dtype != torch.float32:
             dx = torch.empty_like(x)
-            _lib.call("lcgan_cast", _ptr(dx_acc), _ptr(dx), F32, _dt(x), C.c_int64(dx_acc.numel()), _stream(x))
+            _lib.call("lcgan_cast", _ptr(dx_acc), _ptr(dx), F32, _dt(x), C.c_int64(dx_acc.numel()), _stream(x),
+                      nbytes=dx_acc.numel() * (4 + x.element_size()))
         else:
             dx = dx_acc
         return dx, dflow, None
