@@ -180,7 +180,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     if rank == 0:
-        entry.build()
+        _lib.build()          # quiet: stdout carries exactly one JSON line
     if world > 1:
         dist.barrier()
     ops.set_precision(args.precision)

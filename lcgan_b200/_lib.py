@@ -13,7 +13,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "liblcgan_b200.so")
-_SRCS = ["api.cu", "conv_simt.cu", "conv_tc.cu", "resample.cu", "warp.cu", "loss.cu"]
+_SRCS = ["api.cu", "conv_simt.cu", "conv_tc.cu", "thin.cu", "resample.cu", "warp.cu", "loss.cu"]
 _lock = threading.Lock()
 _lib = None
 

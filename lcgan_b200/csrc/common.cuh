@@ -81,4 +81,9 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// thin.cu: special-shape kernels tried before the generic tiled ones (-1 = not applicable)
+int lcgan_thin_forward(const lcgan_tapconv& d, const void* x, const void* w, void* y, const float* rowscale,
+                       const float* bias, const void* residual, cudaStream_t s);
+int lcgan_thin_wgrad(const lcgan_tapconv& d, const void* x, const void* g, float* dw, float scale, cudaStream_t s);
+
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

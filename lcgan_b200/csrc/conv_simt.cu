@@ -240,6 +240,10 @@ extern "C" int lcgan_tapconv_simt(const lcgan_tapconv* d, const void* x, const v
   if (int e = check_desc(d)) return e;
   LCGAN_CHECK(x && w2 && y, "tapconv_simt: null tensor pointer");
   cudaStream_t s = (cudaStream_t)stream;
+  {
+    const int e = lcgan_thin_forward(*d, x, w2, y, rowscale, bias, residual, s);
+    if (e >= 0) return e;
+  }
   if (d->x_dtype == LCGAN_F32) return dispatch_w<float>(*d, x, w2, y, rowscale, bias, residual, s);
   return dispatch_w<bf16>(*d, x, w2, y, rowscale, bias, residual, s);
 }
@@ -249,6 +253,10 @@ extern "C" int lcgan_tapconv_wgrad_simt(const lcgan_tapconv* d, const void* x, c
   if (int e = check_desc(d)) return e;
   LCGAN_CHECK(x && g && dw2, "tapconv_wgrad_simt: null tensor pointer");
   cudaStream_t s = (cudaStream_t)stream;
+  {
+    const int e = lcgan_thin_wgrad(*d, x, g, dw2, scale, s);
+    if (e >= 0) return e;
+  }
   const int64_t rows = (int64_t)d->N * d->MH * d->MW;
   const int otiles = ceil_div(d->Cout, 64), ctiles = ceil_div(d->Cin, 64);
   const int base_blocks = otiles * ctiles * d->ntaps;

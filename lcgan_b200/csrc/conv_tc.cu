@@ -474,8 +474,9 @@ bool lattice_tile(int MW, int MH, int* wt, int* ht, int* nt) {
   return true;
 }
 
-bool dense_cl(int64_t sn, int64_t sh, int64_t sw, int64_t sc, int H, int W, int C) {
-  return sc == 1 && sw == C && sh == (int64_t)W * C && sn == (int64_t)H * W * C;
+// dense channels-last; strides of size-1 dimensions are irrelevant (a [b,K] matrix viewed as [b,K,1,1])
+bool dense_cl(int64_t sn, int64_t sh, int64_t sw, int64_t sc, int N, int H, int W, int C) {
+  return sc == 1 && (W == 1 || sw == C) && (H == 1 || sh == (int64_t)W * C) && (N == 1 || sn == (int64_t)H * W * C);
 }
 
 int fwd_smem_bytes() { return kStages * (kABytes + kBBytes) + 1024 + 256; }
@@ -487,9 +488,10 @@ extern "C" int lcgan_tapconv_tc_eligible(const lcgan_tapconv* d) {
   if (!d) return 0;
   if (d->x_dtype != LCGAN_BF16) return 0;
   if (d->Cin % kBlockK != 0 || d->Cout % 16 != 0) return 0;
-  if (!dense_cl(d->xs_n, d->xs_h, d->xs_w, d->xs_c, d->IH, d->IW, d->Cin)) return 0;
+  if (!dense_cl(d->xs_n, d->xs_h, d->xs_w, d->xs_c, d->N, d->IH, d->IW, d->Cin)) return 0;
   // output: channel-innermost, 16-byte aligned pixel rows (dense channels-last or any such strides)
-  if (d->ys_c != 1 || d->ys_w % 8 != 0 || d->ys_h % 8 != 0 || d->ys_n % 8 != 0) return 0;
+  if (d->ys_c != 1 || (d->OW > 1 && d->ys_w % 8 != 0) || (d->OH > 1 && d->ys_h % 8 != 0) ||
+      (d->N > 1 && d->ys_n % 8 != 0)) return 0;
   int wt, ht, nt;
   if (!lattice_tile(d->MW, d->MH, &wt, &ht, &nt)) return 0;
   if (d->is < 1 || d->is > 2 || d->os < 1 || d->os > 2) return 0;
@@ -538,7 +540,7 @@ extern "C" int lcgan_tapconv_wgrad_tc(const lcgan_tapconv* d, const void* x, con
   // here the descriptor's X side is the layer input and its Y side is the output gradient G
   LCGAN_CHECK(lcgan_tapconv_tc_eligible(d), "tapconv_wgrad_tc: descriptor not eligible");
   LCGAN_CHECK(d->y_dtype == LCGAN_BF16 && d->Cout % 64 == 0 &&
-              dense_cl(d->ys_n, d->ys_h, d->ys_w, d->ys_c, d->OH, d->OW, d->Cout),
+              dense_cl(d->ys_n, d->ys_h, d->ys_w, d->ys_c, d->N, d->OH, d->OW, d->Cout),
               "tapconv_wgrad_tc: G must be dense channels-last bf16 with Cout %% 64 == 0");
   LCGAN_CHECK(x && g && dw2 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)dw2 % 16 == 0) &&
               d->w_ld % 4 == 0, "tapconv_wgrad_tc: bad pointers/alignment");

@@ -78,6 +78,61 @@ box3_kernel(const T* __restrict__ a, const T* __restrict__ mask, T* __restrict__
   }
 }
 
+// Strip variant: one thread owns a column of R output rows for one channel vector and slides a
+// window of horizontal 3-sums down it, so each input vector is loaded 3(R+2)/R times instead of 9.
+template <typename T, int V, int R>
+__global__ void __launch_bounds__(kThreads)
+box3_strip_kernel(const T* __restrict__ a, const T* __restrict__ mask, T* __restrict__ out, int N, int H,
+                  int W, int C, float pre_slope, float pre_gain, float post_slope, float post_gain) {
+  const int cv = C / V, HS = H / R;
+  const int64_t total = (int64_t)N * HS * W * cv;
+  for (int64_t idx = blockIdx.x * (int64_t)kThreads + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * kThreads) {
+    const int c = (int)(idx % cv) * V;
+    int64_t p = idx / cv;
+    const int x = (int)(p % W); p /= W;
+    const int y0 = (int)(p % HS) * R;
+    const int b = (int)(p / HS);
+    const int64_t img = (int64_t)b * H * W * C;
+    float h0[V], h1[V], h2[V];     // horizontal sums of rows y-1, y, y+1
+    auto hsum = [&](int yy, float* h) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) h[i] = 0.f;
+      if (yy < 0 || yy >= H) return;
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int xx = x + dx;
+        if (xx < 0 || xx >= W) continue;
+        const int64_t off = img + ((int64_t)yy * W + xx) * C + c;
+        float f[V];
+        ldv<T, V>(a + off, f);
+        if (mask) {
+          float m[V];
+          ldv<T, V>(mask + off, m);
+#pragma unroll
+          for (int i = 0; i < V; ++i) f[i] *= (m[i] > 0.f ? pre_gain : pre_gain * pre_slope);
+        }
+#pragma unroll
+        for (int i = 0; i < V; ++i) h[i] += f[i];
+      }
+    };
+    hsum(y0 - 1, h0);
+    hsum(y0, h1);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      hsum(y0 + r + 1, h2);
+      float o[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float v = (h0[i] + h1[i] + h2[i]) * (1.f / 9.f);
+        o[i] = (v > 0.f ? v : v * post_slope) * post_gain;
+        h0[i] = h1[i]; h1[i] = h2[i];
+      }
+      stv<T, V>(out + img + ((int64_t)(y0 + r) * W + x) * C + c, o);
+    }
+  }
+}
+
 template <typename T, int V>
 __global__ void __launch_bounds__(kThreads)
 pool2_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, float scale) {
@@ -291,11 +346,19 @@ extern "C" int lcgan_box3(const void* a, const void* mask, void* out, int dt, in
                           float pre_slope, float pre_gain, float post_slope, float post_gain, void* stream) {
   LCGAN_CHECK(a && out && N > 0 && H > 0 && W > 0 && C > 0, "box3: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
+  if (H % 8 == 0 && (int64_t)N * (H / 8) * W * (C / 8) >= 148LL * 64) {
+#define CALL(T, V)                                                                              \
+  box3_strip_kernel<T, V, 8><<<grid_for((int64_t)N * (H / 8) * W * (C / V)), kThreads, 0, s>>>( \
+      (const T*)a, (const T*)mask, (T*)out, N, H, W, C, pre_slope, pre_gain, post_slope, post_gain)
+    DISPATCH_TV(dt, C, CALL);
+#undef CALL
+  } else {
 #define CALL(T, V)                                                                              \
   box3_kernel<T, V><<<grid_for((int64_t)N * H * W * (C / V)), kThreads, 0, s>>>(                \
       (const T*)a, (const T*)mask, (T*)out, N, H, W, C, pre_slope, pre_gain, post_slope, post_gain)
-  DISPATCH_TV(dt, C, CALL);
+    DISPATCH_TV(dt, C, CALL);
 #undef CALL
+  }
   LCGAN_LAUNCH_CHECK();
   return 0;
 }

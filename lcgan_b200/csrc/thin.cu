@@ -1,0 +1,424 @@
+// Memory-bound contractions that are not GEMM-shaped (SURVEY "first/last layers are not GEMM-shaped"):
+//   thin-out  : Cout <= 4  (flow layers C->2, to-RGB C->3, data-gradient of from-RGB)     reads X once
+//   thin-in   : Cin  <= 4  (from-RGB 3->C, data-gradients of the flow / to-RGB layers)    writes Y once
+//   thin-wgrad: weight gradient when one side has <= 4 channels                           reads both once
+//   skinny    : linear layers with batch <= 32 rows (mapping network, style affines, demod
+//               coefficients, heads' weight gradients)                                   reads W once
+// They are selected inside lcgan_tapconv_simt / lcgan_tapconv_wgrad_simt, so the C ABI is unchanged.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxThin = 4;
+constexpr int kSmemFloats = 11 * 1024;   // 44 KiB of weights in static shared memory
+
+template <typename T, int V> __device__ __forceinline__ void ldv(const T* p, float* f) {
+  if constexpr (V == 1) f[0] = ldf(p); else { Vec16<T> v; v.load(p); v.unpack(f); }
+}
+template <typename T, int V> __device__ __forceinline__ void stv(T* p, const float* f) {
+  if constexpr (V == 1) stf(p, f[0]); else { Vec16<T> v; v.pack(f); v.store(p); }
+}
+
+__device__ __forceinline__ float ldw(const void* w, int w_dtype, int64_t i) {
+  return w_dtype == LCGAN_F32 ? reinterpret_cast<const float*>(w)[i]
+                              : __bfloat162float(reinterpret_cast<const bf16*>(w)[i]);
+}
+
+__device__ __forceinline__ float epilogue(const lcgan_tapconv& d, float acc, int b, int o, const float* rowscale,
+                                          const float* bias) {
+  float v = acc * d.acc_scale;
+  if (rowscale) v *= rowscale[(int64_t)b * d.Cout + o];
+  if (bias) v += bias[o] * d.bias_scale;
+  return (v > 0.f ? v : v * d.slope) * d.gain;
+}
+
+// ------------------------------------------------------------------------------------------
+// thin-out: a group of G lanes owns one lattice point and strides over X's channel vectors
+// ------------------------------------------------------------------------------------------
+template <typename TX, typename TY, int V>
+__global__ void __launch_bounds__(kThreads)
+thin_out_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const void* __restrict__ w, TY* __restrict__ y,
+                const float* __restrict__ rowscale, const float* __restrict__ bias, const TY* __restrict__ residual,
+                int G) {
+  __shared__ float ws[kSmemFloats];          // [o][t][c]
+  const int tc = d.ntaps * d.Cin;
+  for (int i = threadIdx.x; i < d.Cout * tc; i += kThreads) {
+    const int o = i / tc, r = i - o * tc, t = r / d.Cin, c = r - t * d.Cin;
+    ws[i] = ldw(w, d.w_dtype, (int64_t)o * d.w_ld + (int64_t)d.wtap[t] * d.Cin + c);
+  }
+  __syncthreads();
+  const int cv = d.Cin / V;
+  const int64_t rows = (int64_t)d.N * d.MH * d.MW;
+  const int gl = threadIdx.x % G, gpb = kThreads / G;
+  const int64_t rows_pad = (rows + gpb - 1) / gpb * gpb;
+  for (int64_t r = (int64_t)blockIdx.x * gpb + threadIdx.x / G; r < rows_pad; r += (int64_t)gridDim.x * gpb) {
+    const bool live = r < rows;
+    float acc[kMaxThin] = {0.f, 0.f, 0.f, 0.f};
+    int b = 0, m = 0, n = 0;
+    if (live) {
+      n = (int)(r % d.MW);
+      const int64_t q = r / d.MW;
+      m = (int)(q % d.MH);
+      b = (int)(q / d.MH);
+      for (int t = 0; t < d.ntaps; ++t) {
+        const int iy = m * d.is + d.dy[t], ix = n * d.is + d.dx[t];
+        if (iy < 0 || iy >= d.IH || ix < 0 || ix >= d.IW) continue;
+        const TX* xp = x + b * d.xs_n + iy * d.xs_h + ix * d.xs_w;
+        for (int v = gl; v < cv; v += G) {
+          float f[V];
+          if constexpr (V == 1) f[0] = ldf(xp + (int64_t)v * d.xs_c); else ldv<TX, V>(xp + v * V, f);
+#pragma unroll
+          for (int o = 0; o < kMaxThin; ++o) {
+            if (o < d.Cout) {
+              const float* wp = ws + (o * d.ntaps + t) * d.Cin + v * V;
+#pragma unroll
+              for (int i = 0; i < V; ++i) acc[o] = fmaf(f[i], wp[i], acc[o]);
+            }
+          }
+        }
+      }
+    }
+    for (int s = G >> 1; s > 0; s >>= 1) {
+#pragma unroll
+      for (int o = 0; o < kMaxThin; ++o) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], s);
+    }
+    if (live && gl == 0) {
+      const int64_t base = b * d.ys_n + (int64_t)(m * d.os + d.py) * d.ys_h + (int64_t)(n * d.os + d.px) * d.ys_w;
+      for (int o = 0; o < d.Cout; ++o) {
+        float v = epilogue(d, acc[o], b, o, rowscale, bias);
+        if (residual) v += ldf(residual + base + o * d.ys_c);
+        stf(y + base + o * d.ys_c, v);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// thin-in: one thread = one output channel vector of one lattice point
+// ------------------------------------------------------------------------------------------
+template <typename TX, typename TY, int V>
+__global__ void __launch_bounds__(kThreads)
+thin_in_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const void* __restrict__ w, TY* __restrict__ y,
+               const float* __restrict__ rowscale, const float* __restrict__ bias, const TY* __restrict__ residual) {
+  __shared__ float ws[kSmemFloats];          // [t][c][o]
+  const int tc = d.ntaps * d.Cin;
+  for (int i = threadIdx.x; i < d.Cout * tc; i += kThreads) {
+    const int o = i % d.Cout, r = i / d.Cout, t = r / d.Cin, c = r - t * d.Cin;
+    ws[i] = ldw(w, d.w_dtype, (int64_t)o * d.w_ld + (int64_t)d.wtap[t] * d.Cin + c);
+  }
+  __syncthreads();
+  const int ov = d.Cout / V;
+  const int64_t total = (int64_t)d.N * d.MH * d.MW * ov;
+  for (int64_t idx = blockIdx.x * (int64_t)kThreads + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * kThreads) {
+    const int o0 = (int)(idx % ov) * V;
+    int64_t r = idx / ov;
+    const int n = (int)(r % d.MW); r /= d.MW;
+    const int m = (int)(r % d.MH);
+    const int b = (int)(r / d.MH);
+    float acc[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = 0.f;
+    for (int t = 0; t < d.ntaps; ++t) {
+      const int iy = m * d.is + d.dy[t], ix = n * d.is + d.dx[t];
+      if (iy < 0 || iy >= d.IH || ix < 0 || ix >= d.IW) continue;
+      const TX* xp = x + b * d.xs_n + iy * d.xs_h + ix * d.xs_w;
+      for (int c = 0; c < d.Cin; ++c) {
+        const float xv = ldf(xp + c * d.xs_c);
+        const float* wp = ws + (t * d.Cin + c) * d.Cout + o0;
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] = fmaf(xv, wp[i], acc[i]);
+      }
+    }
+    const int64_t base = b * d.ys_n + (int64_t)(m * d.os + d.py) * d.ys_h + (int64_t)(n * d.os + d.px) * d.ys_w;
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = epilogue(d, acc[i], b, o0 + i, rowscale, bias);
+    if constexpr (V == 1) {
+      if (residual) acc[0] += ldf(residual + base + o0 * d.ys_c);
+      stf(y + base + o0 * d.ys_c, acc[0]);
+    } else {
+      if (residual) {
+        float rr[V];
+        ldv<TY, V>(residual + base + o0, rr);
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] += rr[i];
+      }
+      stv<TY, V>(y + base + o0, acc);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// thin-wgrad: thread = (wide channel vector, tap, pixel lane); accumulates acc[thin][V] over its
+// lattice points, then one atomic per element.  kThinIsG: the thin side is G (Cout <= 4) and the
+// wide side is X at the tap-shifted position; otherwise thin = X (Cin <= 4), wide = G.
+// ------------------------------------------------------------------------------------------
+template <typename TW, typename TT, int V, bool kThinIsG>
+__global__ void __launch_bounds__(kThreads)
+thin_wgrad_kernel(const lcgan_tapconv d, const TW* __restrict__ wide, const TT* __restrict__ thin,
+                  float* __restrict__ dw, float scale, int cv, int lanes, int64_t rows_per_block) {
+  __shared__ float red[kThreads * kMaxThin * V / 2];   // half the threads park their partials at a time
+  const int per_lane = cv * d.ntaps;
+  const int lane = threadIdx.x / per_lane;
+  const bool active = lane < lanes;
+  const int rem = threadIdx.x - lane * per_lane;
+  const int t = active ? rem / cv : 0, v = active ? rem - t * cv : 0;
+  const int nthin = kThinIsG ? d.Cout : d.Cin;
+  const int64_t rows = (int64_t)d.N * d.MH * d.MW;
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r_end = min(rows, r_begin + rows_per_block);
+  float acc[kMaxThin][V];
+#pragma unroll
+  for (int o = 0; o < kMaxThin; ++o)
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[o][i] = 0.f;
+  if (active) {
+    // incremental (b, m, n) decode: one division pair up front, then carries
+    int64_t r = r_begin + lane;
+    int n = (int)(r % d.MW);
+    int64_t q = r / d.MW;
+    int m = (int)(q % d.MH);
+    int b = (int)(q / d.MH);
+    for (; r < r_end; r += lanes) {
+      const int iy = m * d.is + d.dy[t], ix = n * d.is + d.dx[t];
+      if (iy >= 0 && iy < d.IH && ix >= 0 && ix < d.IW) {
+        const int oy = m * d.os + d.py, ox = n * d.os + d.px;
+        float f[V], th[kMaxThin];
+        if constexpr (kThinIsG) {
+          ldv<TW, V>(wide + b * d.xs_n + iy * d.xs_h + ix * d.xs_w + v * V, f);
+          const TT* tp = thin + b * d.ys_n + oy * d.ys_h + ox * d.ys_w;
+#pragma unroll
+          for (int o = 0; o < kMaxThin; ++o) th[o] = o < nthin ? ldf(tp + o * d.ys_c) : 0.f;
+        } else {
+          ldv<TW, V>(wide + b * d.ys_n + oy * d.ys_h + ox * d.ys_w + v * V, f);
+          const TT* tp = thin + b * d.xs_n + iy * d.xs_h + ix * d.xs_w;
+#pragma unroll
+          for (int o = 0; o < kMaxThin; ++o) th[o] = o < nthin ? ldf(tp + o * d.xs_c) : 0.f;
+        }
+#pragma unroll
+        for (int o = 0; o < kMaxThin; ++o)
+#pragma unroll
+          for (int i = 0; i < V; ++i) acc[o][i] = fmaf(th[o], f[i], acc[o][i]);
+      }
+      n += lanes;
+      while (n >= d.MW) { n -= d.MW; if (++m == d.MH) { m = 0; ++b; } }
+    }
+  }
+  // tree-reduce the pixel lanes through shared memory, then ONE atomic per weight element per block
+  int span = 1;
+  while (span < lanes) span <<= 1;
+  for (int h = span >> 1; h >= 1; h >>= 1) {
+    const bool writer = active && lane >= h && lane < 2 * h;
+    const bool reader = active && lane < h && lane + h < lanes;
+    __syncthreads();
+    if (writer) {
+      float* p = red + ((lane - h) * per_lane + rem) * (kMaxThin * V);
+#pragma unroll
+      for (int o = 0; o < kMaxThin; ++o)
+#pragma unroll
+        for (int i = 0; i < V; ++i) p[o * V + i] = acc[o][i];
+    }
+    __syncthreads();
+    if (reader) {
+      const float* p = red + (lane * per_lane + rem) * (kMaxThin * V);
+#pragma unroll
+      for (int o = 0; o < kMaxThin; ++o)
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[o][i] += p[o * V + i];
+    }
+  }
+  if (active && lane == 0) {
+    const int64_t wcol0 = (int64_t)d.wtap[t] * d.Cin;
+    for (int o = 0; o < nthin; ++o)
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        if constexpr (kThinIsG) atomicAdd(dw + (int64_t)o * d.w_ld + wcol0 + v * V + i, acc[o][i] * scale);
+        else atomicAdd(dw + (int64_t)(v * V + i) * d.w_ld + wcol0 + o, acc[o][i] * scale);
+      }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// skinny linear: out[m][n] = sum_k x[m][k] w[n][k], m <= 32.  One warp per output feature, lanes
+// stride over K (coalesced w row), 32 accumulators per lane, shuffle reduction.
+// ------------------------------------------------------------------------------------------
+template <typename TX, typename TWt, typename TY>
+__global__ void __launch_bounds__(kThreads)
+skinny_linear_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const TWt* __restrict__ w, TY* __restrict__ y,
+                     const float* __restrict__ rowscale, const float* __restrict__ bias, const TY* __restrict__ residual) {
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int n = blockIdx.x * (kThreads / 32) + warp;
+  if (n >= d.Cout) return;
+  const int M = d.N, K = d.Cin;
+  float acc[32];
+#pragma unroll
+  for (int m = 0; m < 32; ++m) acc[m] = 0.f;
+  const TWt* wr = w + (int64_t)n * d.w_ld;
+  for (int k = lane; k < K; k += 32) {
+    const float wv = ldf(wr + k);
+#pragma unroll
+    for (int m = 0; m < 32; ++m)
+      if (m < M) acc[m] = fmaf(ldf(x + m * d.xs_n + k * d.xs_c), wv, acc[m]);
+  }
+#pragma unroll
+  for (int m = 0; m < 32; ++m) acc[m] = warp_sum(acc[m]);
+  // lane m writes row m
+  float mine = 0.f;
+#pragma unroll
+  for (int m = 0; m < 32; ++m) if (lane == m) mine = acc[m];
+  if (lane < M) {
+    float v = epilogue(d, mine, lane, n, rowscale, bias);
+    const int64_t off = lane * d.ys_n + n * d.ys_c;
+    if (residual) v += ldf(residual + off);
+    stf(y + off, v);
+  }
+}
+
+// dW[n][k] += scale * sum_m g[m][n] x[m][k]; thread = one (n, 4 consecutive k)
+template <typename TX, typename TG>
+__global__ void __launch_bounds__(kThreads)
+skinny_wgrad_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const TG* __restrict__ g, float* __restrict__ dw,
+                    float scale) {
+  const int K4 = (d.Cin + 3) / 4;
+  const int64_t total = (int64_t)d.Cout * K4;
+  for (int64_t idx = blockIdx.x * (int64_t)kThreads + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * kThreads) {
+    const int k0 = (int)(idx % K4) * 4;
+    const int n = (int)(idx / K4);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int m = 0; m < d.N; ++m) {
+      const float gv = ldf(g + m * d.ys_n + n * d.ys_c);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (k0 + i < d.Cin) acc[i] = fmaf(gv, ldf(x + m * d.xs_n + (k0 + i) * d.xs_c), acc[i]);
+    }
+    float* o = dw + (int64_t)n * d.w_ld + k0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (k0 + i < d.Cin) o[i] += acc[i] * scale;
+  }
+}
+
+inline int pow2_group(int cv) { return (cv & (cv - 1)) ? 1 : (cv < 32 ? cv : 32); }
+
+inline bool is_point(const lcgan_tapconv& d) {
+  return d.IH == 1 && d.IW == 1 && d.OH == 1 && d.OW == 1 && d.ntaps == 1 && d.MH == 1 && d.MW == 1;
+}
+
+inline bool dense_inner(int64_t sc, int64_t sw, int64_t sh, int64_t sn, int C, int vec) {
+  return sc == 1 && C % vec == 0 && sw % vec == 0 && sh % vec == 0 && sn % vec == 0;
+}
+
+inline int grid_cap(int64_t blocks, int per_sm) {
+  const int64_t cap = 148LL * per_sm;
+  return (int)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
+}
+
+}  // namespace
+
+// returns -1 when the descriptor is not one of the special shapes (caller falls back to the tiled kernel)
+int lcgan_thin_forward(const lcgan_tapconv& d, const void* x, const void* w, void* y, const float* rowscale,
+                       const float* bias, const void* residual, cudaStream_t s) {
+  const bool xf = d.x_dtype == LCGAN_F32, yf = d.y_dtype == LCGAN_F32;
+  const int64_t rows = (int64_t)d.N * d.MH * d.MW;
+  // ---- skinny linear -------------------------------------------------------------------
+  if (is_point(d) && d.N <= 32) {
+    const int grid = (d.Cout + kThreads / 32 - 1) / (kThreads / 32);
+#define SK(TXT, TWT, TYT)                                                                                   \
+    skinny_linear_kernel<TXT, TWT, TYT><<<grid, kThreads, 0, s>>>(d, (const TXT*)x, (const TWT*)w, (TYT*)y, \
+                                                                  rowscale, bias, (const TYT*)residual)
+    const bool wf = d.w_dtype == LCGAN_F32;
+    if (xf && wf && yf) SK(float, float, float);
+    else if (xf && wf && !yf) SK(float, float, bf16);
+    else if (!xf && !wf && yf) SK(bf16, bf16, float);
+    else if (!xf && !wf && !yf) SK(bf16, bf16, bf16);
+    else return -1;
+#undef SK
+    LCGAN_LAUNCH_CHECK();
+    return 0;
+  }
+  // ---- thin-out --------------------------------------------------------------------------
+  if (d.Cout <= kMaxThin && d.Cout * d.ntaps * d.Cin <= kSmemFloats) {
+    const int vec = xf ? 4 : 8;
+    const bool v_ok = dense_inner(d.xs_c, d.xs_w, d.xs_h, d.xs_n, d.Cin, vec) && ((uintptr_t)x % 16 == 0);
+#define TO(TXT, TYT, VV)                                                                                    \
+    do {                                                                                                    \
+      const int G = pow2_group(d.Cin / VV);                                                                 \
+      const int grid = grid_cap((rows + kThreads / G - 1) / (kThreads / G), 16);                            \
+      thin_out_kernel<TXT, TYT, VV><<<grid, kThreads, 0, s>>>(d, (const TXT*)x, w, (TYT*)y, rowscale, bias, \
+                                                              (const TYT*)residual, G);                     \
+    } while (0)
+    if (xf && yf) { if (v_ok) TO(float, float, 4); else TO(float, float, 1); }
+    else if (xf && !yf) { if (v_ok) TO(float, bf16, 4); else TO(float, bf16, 1); }
+    else if (!xf && yf) { if (v_ok) TO(bf16, float, 8); else TO(bf16, float, 1); }
+    else { if (v_ok) TO(bf16, bf16, 8); else TO(bf16, bf16, 1); }
+#undef TO
+    LCGAN_LAUNCH_CHECK();
+    return 0;
+  }
+  // ---- thin-in ---------------------------------------------------------------------------
+  if (d.Cin <= kMaxThin && d.Cout * d.ntaps * d.Cin <= kSmemFloats) {
+    const int vec = yf ? 4 : 8;
+    const bool v_ok = dense_inner(d.ys_c, d.ys_w, d.ys_h, d.ys_n, d.Cout, vec) && ((uintptr_t)y % 16 == 0) &&
+                      (!residual || (uintptr_t)residual % 16 == 0);
+#define TI(TXT, TYT, VV)                                                                                    \
+    do {                                                                                                    \
+      const int grid = grid_cap((rows * (d.Cout / VV) + kThreads - 1) / kThreads, 32);                      \
+      thin_in_kernel<TXT, TYT, VV><<<grid, kThreads, 0, s>>>(d, (const TXT*)x, w, (TYT*)y, rowscale, bias,  \
+                                                             (const TYT*)residual);                         \
+    } while (0)
+    if (xf && yf) { if (v_ok) TI(float, float, 4); else TI(float, float, 1); }
+    else if (xf && !yf) { if (v_ok) TI(float, bf16, 8); else TI(float, bf16, 1); }
+    else if (!xf && yf) { if (v_ok) TI(bf16, float, 4); else TI(bf16, float, 1); }
+    else { if (v_ok) TI(bf16, bf16, 8); else TI(bf16, bf16, 1); }
+#undef TI
+    LCGAN_LAUNCH_CHECK();
+    return 0;
+  }
+  return -1;
+}
+
+int lcgan_thin_wgrad(const lcgan_tapconv& d, const void* x, const void* g, float* dw, float scale, cudaStream_t s) {
+  const bool xf = d.x_dtype == LCGAN_F32, gf = d.y_dtype == LCGAN_F32;
+  const int64_t rows = (int64_t)d.N * d.MH * d.MW;
+  if (is_point(d) && d.N <= 32) {
+    const int64_t total = (int64_t)d.Cout * ((d.Cin + 3) / 4);
+    const int grid = grid_cap((total + kThreads - 1) / kThreads, 32);
+#define SW(TXT, TGT) skinny_wgrad_kernel<TXT, TGT><<<grid, kThreads, 0, s>>>(d, (const TXT*)x, (const TGT*)g, dw, scale)
+    if (xf && gf) SW(float, float); else if (xf) SW(float, bf16); else if (gf) SW(bf16, float); else SW(bf16, bf16);
+#undef SW
+    LCGAN_LAUNCH_CHECK();
+    return 0;
+  }
+  const bool thin_g = d.Cout <= kMaxThin, thin_x = d.Cin <= kMaxThin;
+  if (!thin_g && !thin_x) return -1;
+  // the wide side must be channel-innermost with 16-byte vectors
+  const bool wide_is_x = thin_g;
+  const int Cw = wide_is_x ? d.Cin : d.Cout;
+  const bool wf = wide_is_x ? xf : gf;
+  const int vec = wf ? 4 : 8;
+  const bool ok = wide_is_x ? (dense_inner(d.xs_c, d.xs_w, d.xs_h, d.xs_n, d.Cin, vec) && (uintptr_t)x % 16 == 0)
+                            : (dense_inner(d.ys_c, d.ys_w, d.ys_h, d.ys_n, d.Cout, vec) && (uintptr_t)g % 16 == 0);
+  if (!ok) return -1;
+  const int cv = Cw / vec;
+  const int per_lane = cv * d.ntaps;
+  if (per_lane > kThreads) return -1;
+  int lanes = 1;
+  while (lanes * 2 * per_lane <= kThreads) lanes *= 2;     // power of two (tree reduction in smem)
+  int64_t blocks = 148LL * 4;
+  int64_t rpb = (rows + blocks - 1) / blocks;
+  if (rpb < 8LL * lanes) rpb = 8LL * lanes;
+  blocks = (rows + rpb - 1) / rpb;
+#define TWG(TWIDE, TTHIN, VV, THIN_G)                                                                        \
+  thin_wgrad_kernel<TWIDE, TTHIN, VV, THIN_G><<<(int)blocks, kThreads, 0, s>>>(                              \
+      d, (const TWIDE*)(THIN_G ? x : g), (const TTHIN*)(THIN_G ? g : x), dw, scale, cv, lanes, rpb)
+  if (thin_g) {
+    if (xf && gf) TWG(float, float, 4, true); else if (xf) TWG(float, bf16, 4, true);
+    else if (gf) TWG(bf16, float, 8, true); else TWG(bf16, bf16, 8, true);
+  } else {
+    if (gf && xf) TWG(float, float, 4, false); else if (gf) TWG(float, bf16, 4, false);
+    else if (xf) TWG(bf16, float, 8, false); else TWG(bf16, bf16, 8, false);
+  }
+#undef TWG
+  LCGAN_LAUNCH_CHECK();
+  return 0;
+}

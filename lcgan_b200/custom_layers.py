@@ -14,6 +14,7 @@ import math
 import numpy as np
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import ops, plans
 
@@ -265,7 +266,17 @@ class DiscriminatorEpilogue(nn.Module):
 
     def forward(self, x):
         x = self.mb_std(_as_act(x))
-        x = self.conv(x, slope=0.2)
+        pad = (-x.shape[1]) % 64
+        if pad and ops.act_dtype() == torch.bfloat16:
+            # 513 -> 576 zero channels (a [b,.,4,4] tensor and a 2.6 M-element weight: tiny) so the
+            # layer runs on the tensor-core path, which needs Cin % 64 == 0
+            x = _as_act(F.pad(x, (0, 0, 0, 0, 0, pad)))
+            w = F.pad(self.conv.weight.weight, (0, 0, 0, 0, 0, pad))
+            x = ops.conv_act(x, w, self.conv.bias, None, None, wscale=float(self.conv.weight.c),
+                             plan=plans.conv(3, 1, x.shape[2], x.shape[3]), slope=0.2,
+                             bias_scale=float(self.conv.lr_mul))
+        else:
+            x = self.conv(x, slope=0.2)
         return self.linear(x.flatten(1), slope=0.2)
 
 

@@ -175,6 +175,17 @@ def _fill_desc(d: TapConvDesc, l: plans.Launch, x, y, cin, cout, w2, slope, gain
     d.acc_scale, d.bias_scale, d.slope, d.gain = acc_scale, bias_scale, slope, gain
 
 
+_PROFILE_SHAPES = os.environ.get("LCGAN_PROFILE_SHAPES", "0") == "1"
+
+
+def _shape_tag(fn, d):
+    name = fn.replace("lcgan_", "")
+    if not _PROFILE_SHAPES:
+        return name
+    return (f"{name}|N{d.N} {d.IH}x{d.IW}->{d.OH}x{d.OW} C{d.Cin}->{d.Cout} taps{d.ntaps} is{d.is_} os{d.os} "
+            f"x{d.x_dtype}y{d.y_dtype}")
+
+
 def tapconv(x, w2, y, plan: plans.Plan, rowscale=None, bias=None, residual=None, slope=1.0, gain=1.0,
             bias_scale=1.0, acc_scale=1.0):
     """y = epilogue(tapconv(x, w2)) for every launch of the plan; x, y logical NCHW."""
@@ -193,6 +204,7 @@ def tapconv(x, w2, y, plan: plans.Plan, rowscale=None, bias=None, residual=None,
         fn = "lcgan_tapconv_tc" if (_USE_TC and lib.lcgan_tapconv_tc_eligible(C.byref(d))) else "lcgan_tapconv_simt"
         rows = x.shape[0] * l.MH * l.MW
         _lib.call(fn, C.byref(d), _ptr(x), _ptr(w2), _ptr(y), _ptr(rowscale), _ptr(bias), _ptr(residual), st,
+                  tag=_shape_tag(fn, d),
                   flops=2.0 * rows * len(l.taps) * cin * cout,
                   nbytes=(x.numel() * x.element_size() + y.numel() * y.element_size()) / len(plan.launches)
                   + w2.numel() * w2.element_size() * len(l.taps) / (plan.k * plan.k))
@@ -215,6 +227,7 @@ def tapconv_wgrad(x, g, plan: plans.Plan, cin, cout, scale=1.0):
                                           and _wgrad_tc_ok(d)) else "lcgan_tapconv_wgrad_simt"
         rows = x.shape[0] * l.MH * l.MW
         _lib.call(fn, C.byref(d), _ptr(x), _ptr(g), _ptr(dw2), C.c_float(scale), st,
+                  tag=_shape_tag(fn, d),
                   flops=2.0 * rows * len(l.taps) * cin * cout,
                   nbytes=(x.numel() * x.element_size() + g.numel() * g.element_size()) / len(plan.launches))
     return dw2
@@ -230,8 +243,9 @@ def set_wgrad_tensor_cores(flag: bool):
 
 def _wgrad_tc_ok(d):
     # the wgrad kernel additionally needs G dense channels-last bf16 with Cout % 64 == 0
-    return (_USE_WGRAD_TC and d.y_dtype == BF16 and d.Cout % 64 == 0 and d.ys_c == 1 and d.ys_w == d.Cout
-            and d.ys_h == d.OW * d.Cout and d.ys_n == d.OH * d.OW * d.Cout)
+    return (_USE_WGRAD_TC and d.y_dtype == BF16 and d.Cout % 64 == 0 and d.ys_c == 1
+            and (d.OW == 1 or d.ys_w == d.Cout) and (d.OH == 1 or d.ys_h == d.OW * d.Cout)
+            and (d.N == 1 or d.ys_n == d.OH * d.OW * d.Cout))
 
 
 def _alloc_out(n, c, h, w, dtype, device, nchw):

@@ -147,6 +147,25 @@ def test_resample_ops(mode, C):
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_box_filter_strip_kernel(mode):
+    """Large enough for the row-reusing strip kernel (H % 8 == 0, many threads)."""
+    ops, _ = _ops()
+    dt = torch.float32 if mode == "fp32" else torch.bfloat16
+    tol = FP32_TOL if mode == "fp32" else BF16_TOL
+    x = _cl(torch.randn(4, 64, 64, 48, device="cuda").to(dt))
+    xf = x.float().contiguous()
+    assert rel_l2(ops.Box3.apply(x).float(), F.avg_pool2d(xf, 3, 1, 1)) < tol
+    xr = xf.clone().requires_grad_(); xm = x.clone().requires_grad_()
+    g = torch.randn(4, 64, 64, 48, device="cuda").to(dt)
+    ref = F.leaky_relu(F.avg_pool2d(xr, 3, 1, 1), 0.2) * 1.4
+    ref.backward(g.float())
+    y = ops.Box3Act.apply(xm, 0.2, 1.4)
+    y.backward(_cl(g))
+    assert rel_l2(y.float(), ref.detach()) < tol
+    assert rel_l2(xm.grad.float(), xr.grad) < tol * 2
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
 @pytest.mark.parametrize("C", [32, 6, 512])
 def test_modulate_and_warp(mode, C):
     ops, _ = _ops()
