@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--freeze-d", action="store_true", help="post-freezeD schedule (worker.py:127-131)")
     return ap.parse_args()
 
@@ -196,7 +197,9 @@ def main():
         G = DDP(G, device_ids=[local_rank], broadcast_buffers=False, find_unused_parameters=True)
         D = DDP(D, device_ids=[local_rank], broadcast_buffers=False, find_unused_parameters=True)
     fl = {256: 3, 512: 4, 1024: 5}.get(res, 3)
-    tr = T.Trainer(G, D, hp, freeze_d_start=0 if args.freeze_d else 10 ** 9, freeze_d_layer=fl)
+    use_graphs = world == 1 and not args.no_graphs
+    kw = dict(freeze_d_start=0 if args.freeze_d else 10 ** 9, freeze_d_layer=fl)
+    tr = T.GraphedTrainer(G, D, hp, b, dev, **kw) if use_graphs else T.Trainer(G, D, hp, **kw)
 
     gcpu = torch.Generator().manual_seed(1000 + rank)
     n_pool = 2
@@ -211,20 +214,50 @@ def main():
         zd = {k: torch.randn(b, 64, device=dev) for k in ("rand1", "rand2")}
         return z, zd
 
-    def step_resident(it):
+    def step_eager(it):
         z, zd = latents()                                     # device RNG, like worker.py:145-146,182-185
         gl = tr.g_step(it, z)
         tr.ema.update(it)
         dl = tr.d_step(it, zd, resident[it % n_pool])
         return gl, dl
 
+    def step_graph(it):
+        # fresh latents (device RNG) and the step's images into the graphs' static input buffers
+        for t in list(tr.z.values()) + list(tr.zd.values()):
+            t.normal_()
+        for k, v in resident[it % n_pool].items():
+            tr.data[k].copy_(v)
+        graph_launches[0] += tr.iteration_graphed(it)
+
     def step_e2e(it):
         h, hz = host[it % n_pool], host_z[it % n_pool]
+        if use_graphs:
+            for k, v in h.items():
+                tr.data[k].copy_(v, non_blocking=True)       # pinned host -> static device buffers
+            for k in ("rand1", "rand2", "resample1", "resample2"):
+                tr.z[k].copy_(hz[k], non_blocking=True)
+            tr.zd["rand1"].copy_(hz["drand1"], non_blocking=True)
+            tr.zd["rand2"].copy_(hz["drand2"], non_blocking=True)
+            tr.replay_g(it)
+            gl = tr.g_loss.item()                             # the reference reads both losses back every
+            tr.replay_d(it)                                   # iteration (worker.py:177,214)
+            return gl, tr.d_loss.item()
         data = {k: v.to(dev, non_blocking=True) for k, v in h.items()}
         zs = {k: v.to(dev, non_blocking=True) for k, v in hz.items()}
         z = {k: zs[k] for k in ("rand1", "rand2", "resample1", "resample2")}
         zd = {"rand1": zs["drand1"], "rand2": zs["drand2"]}
-        return tr.iteration(it, z, zd, data)                  # .item() on both losses (worker.py:177,214)
+        return tr.iteration(it, z, zd, data)
+
+    def step_eager_for_profile(it):
+        z, zd = latents()
+        T.Trainer.g_step(tr, it, z)
+        tr.ema.update(it)
+        T.Trainer.d_step(tr, it, zd, resident[it % n_pool])
+
+    graph_launches = [0]
+    if use_graphs:
+        tr.capture(warmup=2)
+    step_resident = step_graph if use_graphs else step_eager
 
     def sync_all():
         if world > 1:
@@ -234,7 +267,7 @@ def main():
     def timed(fn, first_it, k):
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        launches0 = _lib.launches
+        launches0, gl0 = _lib.launches, graph_launches[0]
         e0.record()
         for i in range(k):
             fn(first_it + i)
@@ -243,7 +276,7 @@ def main():
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms), _lib.launches - launches0
+        return float(ms), (_lib.launches - launches0) + (graph_launches[0] - gl0)
 
     K, W = args.steps, max(args.warmup, 3)
     it0 = 0
@@ -268,7 +301,7 @@ def main():
 
     roof, kernels = None, None
     if not args.no_roofline and rank == 0:
-        roof, kernels = roofline_pass(step_resident, it0, _lib, peaks())
+        roof, kernels = roofline_pass(step_eager_for_profile, it0, _lib, peaks())
     if world > 1:
         dist.barrier()
 
@@ -291,7 +324,7 @@ def main():
             "config": {"workload": workload_name(res, args.batch), "global_batch": args.batch, "local_batch": b,
                        "resolution": res, "parallelism": f"dp{world}", "schedule": "timed region = iterations "
                        f"{it0 - 2 * ((K + 7) // 8) * 8 - (8 if not args.no_e2e else 0)}..+{K} (cycle-aligned)",
-                       "freezeD": bool(args.freeze_d), "l2": "activations per layer exceed the 126 MB L2; no flush needed",
+                       "freezeD": bool(args.freeze_d), "cuda_graphs": bool(use_graphs), "l2": "activations per layer exceed the 126 MB L2; no flush needed",
                        "model_tflop_per_img_iter": flop / 1e12 if flop else None,
                        "model_tflops_achieved": value * flop / 1e12 if flop else None,
                        "frac_of_bf16_peak_sustained": (value * flop / 1e12) / (world * pk["tensor_sustained"]) if flop else None,

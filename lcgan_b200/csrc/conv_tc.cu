@@ -20,7 +20,9 @@
 
 namespace {
 
-constexpr int kStages = 3;
+constexpr int kStages = 3;                     // weight-gradient kernel: 3 x 64 KiB
+constexpr int kFwdStages = 4;                  // forward kernel: 4 x 32 KiB
+constexpr int kAccStages = 2;                  // TMEM accumulator double buffer (2 x 128 columns)
 constexpr int kTileM = 128;                    // lattice points (fwd) / pixels per k-block (wgrad)
 constexpr int kBlockK = 64;                    // channels per k-block = one 128-byte swizzle row
 constexpr int kMaxBN = 128;
@@ -34,7 +36,7 @@ struct TcParams {
   int is, os, py, px;
   int ntaps, kpt;                               // kpt = Cin / 64
   int dy[LCGAN_MAX_TAPS], dx[LCGAN_MAX_TAPS], wtap[LCGAN_MAX_TAPS];
-  int BN;
+  int BN, n_tiles, total_tiles;
   long long ys_n, ys_h, ys_w;
   int y_f32;
   float acc_scale, bias_scale, slope, gain;
@@ -62,6 +64,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
@@ -149,56 +154,54 @@ __device__ __forceinline__ uint32_t make_idesc(int n, bool a_mn_major, bool b_mn
 }
 
 struct Smem {
-  uint8_t* a[kStages];
-  uint8_t* b[kStages];
+  uint8_t* base;          // 1024-byte aligned; stage i: A at base + i*stage_bytes, B right after A
+  uint32_t stage_bytes, a_bytes;
   uint64_t* full;
   uint64_t* empty;
-  uint64_t* done;
+  uint64_t* done;         // [kAccStages] accumulator-full barriers (wgrad uses done[0] only)
+  uint64_t* acc_empty;    // [kAccStages]
   uint32_t* tmem_slot;
+  __device__ __forceinline__ uint8_t* a(int st) const { return base + (size_t)st * stage_bytes; }
+  __device__ __forceinline__ uint8_t* b(int st) const { return base + (size_t)st * stage_bytes + a_bytes; }
 };
 
-__device__ __forceinline__ Smem carve(uint8_t* raw, int a_bytes, int b_bytes) {
+__device__ __forceinline__ Smem carve(uint8_t* raw, int stages, int a_bytes, int b_bytes) {
   Smem s;
-  uint8_t* base = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
-  for (int i = 0; i < kStages; ++i) {
-    s.a[i] = base + (size_t)i * (a_bytes + b_bytes);
-    s.b[i] = s.a[i] + a_bytes;
-  }
-  uint8_t* tail = base + (size_t)kStages * (a_bytes + b_bytes);
+  s.base = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+  s.stage_bytes = a_bytes + b_bytes;
+  s.a_bytes = a_bytes;
+  uint8_t* tail = s.base + (size_t)stages * s.stage_bytes;
   s.full = (uint64_t*)tail;
-  s.empty = s.full + kStages;
-  s.done = s.empty + kStages;
-  s.tmem_slot = (uint32_t*)(s.done + 1);
+  s.empty = s.full + stages;
+  s.done = s.empty + stages;
+  s.acc_empty = s.done + kAccStages;
+  s.tmem_slot = (uint32_t*)(s.acc_empty + kAccStages);
   return s;
 }
 
 // ---------------------------------------------------------------------------------------------
 // forward-type kernel
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 1)
 tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmw, const TcParams p,
                   void* __restrict__ y, const float* __restrict__ rowscale, const float* __restrict__ bias,
                   const void* __restrict__ residual) {
+  // Persistent: one CTA per SM walks tiles blockIdx.x, +gridDim.x, ...  Three decoupled roles:
+  //   warp 0   TMA producer, runs ahead through the 4-stage smem ring across tile boundaries
+  //   warp 1   MMA issuer, accumulates tile i into TMEM stage i%2
+  //   warps2-5 epilogue of tile i overlaps the MMAs of tile i+1 (TMEM double buffer)
   extern __shared__ uint8_t smem_raw[];
-  Smem s = carve(smem_raw, kABytes, kBBytes);
+  const Smem s = carve(smem_raw, kFwdStages, kABytes, kBBytes);
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-
-  // tile coordinates
-  int t = blockIdx.x;
-  const int tw = t % p.tiles_w; t /= p.tiles_w;
-  const int th = t % p.tiles_h;
-  const int tb = t / p.tiles_h;
-  const int n0 = tw * p.wt, m0 = th * p.ht, b0 = tb * p.nt;
-  const int o0 = blockIdx.y * p.BN;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmx);
     tma_prefetch_desc(&tmw);
-    for (int i = 0; i < kStages; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
-    mbar_init(s.done, 1);
+    for (int i = 0; i < kFwdStages; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    for (int i = 0; i < kAccStages; ++i) { mbar_init(&s.done[i], 1); mbar_init(&s.acc_empty[i], 4); }
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc<kMaxBN>(s.tmem_slot);
+  if (warp == 0) tmem_alloc<kAccStages * kMaxBN>(s.tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -208,107 +211,137 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
   if (warp == 0) {
     if (lane == 0) {
       const uint32_t tx_bytes = kABytes + p.BN * kBlockK * 2;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int st = kb % kStages, ph = (kb / kStages) & 1;
-        mbar_wait(&s.empty[st], ph ^ 1);
-        const int tap = kb / p.kpt, cb = kb - tap * p.kpt;
-        mbar_expect_tx(&s.full[st], tx_bytes);
-        tma_load_4d(s.a[st], &tmx, &s.full[st], cb * kBlockK, n0 * p.is + p.dx[tap], m0 * p.is + p.dy[tap], b0);
-        tma_load_2d(s.b[st], &tmw, &s.full[st], p.wtap[tap] * p.Cin + cb * kBlockK, o0);
+      int g = 0;                                            // k-block counter across tiles
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt_i = tile % p.n_tiles;
+        int t = tile / p.n_tiles;
+        const int tw = t % p.tiles_w; t /= p.tiles_w;
+        const int th = t % p.tiles_h;
+        const int tb = t / p.tiles_h;
+        const int n0 = tw * p.wt, m0 = th * p.ht, b0 = tb * p.nt, o0 = nt_i * p.BN;
+        for (int kb = 0; kb < nkb; ++kb, ++g) {
+          const int st = g % kFwdStages, ph = (g / kFwdStages) & 1;
+          mbar_wait(&s.empty[st], ph ^ 1);
+          const int tap = kb / p.kpt, cb = kb - tap * p.kpt;
+          mbar_expect_tx(&s.full[st], tx_bytes);
+          tma_load_4d(s.a(st), &tmx, &s.full[st], cb * kBlockK, n0 * p.is + p.dx[tap], m0 * p.is + p.dy[tap], b0);
+          tma_load_2d(s.b(st), &tmw, &s.full[st], p.wtap[tap] * p.Cin + cb * kBlockK, o0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc(p.BN, false, false);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int st = kb % kStages, ph = (kb / kStages) & 1;
-        mbar_wait(&s.full[st], ph);
+      int g = 0, li = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li) {
+        const int as = li % kAccStages, aph = (li / kAccStages) & 1;
+        mbar_wait(&s.acc_empty[as], aph ^ 1);               // epilogue has drained this TMEM stage
         tc_fence_after();
-        const uint64_t ad = make_desc(smem_u32(s.a[st]), 16, 1024);
-        const uint64_t bd = make_desc(smem_u32(s.b[st]), 16, 1024);
+        const uint32_t tacc = tmem_base + (uint32_t)(as * kMaxBN);
+        for (int kb = 0; kb < nkb; ++kb, ++g) {
+          const int st = g % kFwdStages, ph = (g / kFwdStages) & 1;
+          mbar_wait(&s.full[st], ph);
+          tc_fence_after();
+          const uint64_t ad = make_desc(smem_u32(s.a(st)), 16, 1024);
+          const uint64_t bd = make_desc(smem_u32(s.b(st)), 16, 1024);
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k)   // +32 bytes along K inside the 128-byte swizzle row
-          umma_f16(tmem_base, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
-        umma_commit(&s.empty[st]);
+          for (int k = 0; k < kBlockK / 16; ++k)   // +32 bytes along K inside the 128-byte swizzle row
+            umma_f16(tacc, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(&s.empty[st]);
+        }
+        umma_commit(&s.done[as]);
       }
-      umma_commit(s.done);
     }
   } else {
     // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31  (= tile rows)
     const int q = warp % 4;
     const int r = q * 32 + lane;
     const int ni = r % p.wt, mi = (r / p.wt) % p.ht, bi = r / (p.wt * p.ht);
-    const int b = b0 + bi;
-    const bool live = b < p.N;
-    const long long pix = (long long)b * p.ys_n + (long long)((m0 + mi) * p.os + p.py) * p.ys_h +
-                          (long long)((n0 + ni) * p.os + p.px) * p.ys_w;
-    mbar_wait(s.done, 0);
-    tc_fence_after();
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int c = 0; c < p.BN; c += 16) {
-      uint32_t v[16];
-      tmem_ld16(trow + c, v);
-      tmem_ld_wait();
-      const int o = o0 + c;
-      if (live && o < p.Cout) {
-        float f[16];
+    int li = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li) {
+      const int nt_i = tile % p.n_tiles;
+      int t = tile / p.n_tiles;
+      const int tw = t % p.tiles_w; t /= p.tiles_w;
+      const int th = t % p.tiles_h;
+      const int tb = t / p.tiles_h;
+      const int n0 = tw * p.wt, m0 = th * p.ht, b0 = tb * p.nt, o0 = nt_i * p.BN;
+      const int b = b0 + bi;
+      const bool live = b < p.N;
+      const long long pix = (long long)b * p.ys_n + (long long)((m0 + mi) * p.os + p.py) * p.ys_h +
+                            (long long)((n0 + ni) * p.os + p.px) * p.ys_w;
+      const int as = li % kAccStages, aph = (li / kAccStages) & 1;
+      mbar_wait(&s.done[as], aph);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kMaxBN);
+      for (int c = 0; c < p.BN; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(trow + c, v);
+        tmem_ld_wait();
+        const int o = o0 + c;
+        if (live && o < p.Cout) {
+          float f[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * p.acc_scale;
-        if (rowscale) {
-          const float4* rs = reinterpret_cast<const float4*>(rowscale + (long long)b * p.Cout + o);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 sc = rs[i];
-            f[4 * i] *= sc.x; f[4 * i + 1] *= sc.y; f[4 * i + 2] *= sc.z; f[4 * i + 3] *= sc.w;
-          }
-        }
-        if (bias) {
-          const float4* bp = reinterpret_cast<const float4*>(bias + o);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 bb = bp[i];
-            f[4 * i] += bb.x * p.bias_scale; f[4 * i + 1] += bb.y * p.bias_scale;
-            f[4 * i + 2] += bb.z * p.bias_scale; f[4 * i + 3] += bb.w * p.bias_scale;
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = (f[i] > 0.f ? f[i] : f[i] * p.slope) * p.gain;
-        if (p.y_f32) {
-          float* yp = reinterpret_cast<float*>(y) + pix + o;
-          if (residual) {
-            const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(residual) + pix + o);
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * p.acc_scale;
+          if (rowscale) {
+            const float4* rs = reinterpret_cast<const float4*>(rowscale + (long long)b * p.Cout + o);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float4 rr = rp[i];
-              f[4 * i] += rr.x; f[4 * i + 1] += rr.y; f[4 * i + 2] += rr.z; f[4 * i + 3] += rr.w;
+              const float4 sc = rs[i];
+              f[4 * i] *= sc.x; f[4 * i + 1] *= sc.y; f[4 * i + 2] *= sc.z; f[4 * i + 3] *= sc.w;
+            }
+          }
+          if (bias) {
+            const float4* bp = reinterpret_cast<const float4*>(bias + o);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 bb = bp[i];
+              f[4 * i] += bb.x * p.bias_scale; f[4 * i + 1] += bb.y * p.bias_scale;
+              f[4 * i + 2] += bb.z * p.bias_scale; f[4 * i + 3] += bb.w * p.bias_scale;
             }
           }
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            reinterpret_cast<float4*>(yp)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-        } else {
-          bf16* yp = reinterpret_cast<bf16*>(y) + pix + o;
-          if (residual) {
-            const bf16* rp = reinterpret_cast<const bf16*>(residual) + pix + o;
-            Vec16<bf16> r0, r1;
-            r0.load(rp); r1.load(rp + 8);
-            float g[16];
-            r0.unpack(g); r1.unpack(g + 8);
+          for (int i = 0; i < 16; ++i) f[i] = (f[i] > 0.f ? f[i] : f[i] * p.slope) * p.gain;
+          if (p.y_f32) {
+            float* yp = reinterpret_cast<float*>(y) + pix + o;
+            if (residual) {
+              const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(residual) + pix + o);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] += g[i];
+              for (int i = 0; i < 4; ++i) {
+                const float4 rr = rp[i];
+                f[4 * i] += rr.x; f[4 * i + 1] += rr.y; f[4 * i + 2] += rr.z; f[4 * i + 3] += rr.w;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              reinterpret_cast<float4*>(yp)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          } else {
+            bf16* yp = reinterpret_cast<bf16*>(y) + pix + o;
+            if (residual) {
+              const bf16* rp = reinterpret_cast<const bf16*>(residual) + pix + o;
+              Vec16<bf16> r0, r1;
+              r0.load(rp); r1.load(rp + 8);
+              float g[16];
+              r0.unpack(g); r1.unpack(g + 8);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] += g[i];
+            }
+            Vec16<bf16> o0v, o1v;
+            o0v.pack(f); o1v.pack(f + 8);
+            o0v.store(yp); o1v.store(yp + 8);
           }
-          Vec16<bf16> o0v, o1v;
-          o0v.pack(f); o1v.pack(f + 8);
-          o0v.store(yp); o1v.store(yp + 8);
         }
       }
+      // this warp is done reading the TMEM stage: hand it back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.acc_empty[as]);
     }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc<kMaxBN>(tmem_base);
+    tmem_dealloc<kAccStages * kMaxBN>(tmem_base);
   }
 }
 
@@ -322,7 +355,7 @@ __global__ void __launch_bounds__(kThreads)
 tapconv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUtensorMap tmx,
                         const WgParams p, float* __restrict__ dw) {
   extern __shared__ uint8_t smem_raw[];
-  Smem s = carve(smem_raw, kWgABytes, kWgBBytes);
+  const Smem s = carve(smem_raw, kStages, kWgABytes, kWgBBytes);
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int o0 = (blockIdx.x / p.ctiles) * 128, c0 = (blockIdx.x % p.ctiles) * p.BN;
   const int tap = blockIdx.y;
@@ -334,7 +367,7 @@ tapconv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmg, const __grid_co
     tma_prefetch_desc(&tmg);
     tma_prefetch_desc(&tmx);
     for (int i = 0; i < kStages; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
-    mbar_init(s.done, 1);
+    mbar_init(&s.done[0], 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<kMaxBN>(s.tmem_slot);
@@ -357,9 +390,9 @@ tapconv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmg, const __grid_co
         const int n0 = tw * p.wt, m0 = th * p.ht, b0 = tb * p.nt;
         mbar_expect_tx(&s.full[st], tx_bytes);
         for (int j = 0; j < 2; ++j)
-          tma_load_4d(s.a[st] + j * kABytes, &tmg, &s.full[st], o0 + 64 * j, n0 * p.os + p.px, m0 * p.os + p.py, b0);
+          tma_load_4d(s.a(st) + j * kABytes, &tmg, &s.full[st], o0 + 64 * j, n0 * p.os + p.px, m0 * p.os + p.py, b0);
         for (int j = 0; j < nbx; ++j)
-          tma_load_4d(s.b[st] + j * kABytes, &tmx, &s.full[st], c0 + 64 * j, n0 * p.is + p.dx[tap],
+          tma_load_4d(s.b(st) + j * kABytes, &tmx, &s.full[st], c0 + 64 * j, n0 * p.is + p.dx[tap],
                       m0 * p.is + p.dy[tap], b0);
       }
     }
@@ -372,19 +405,19 @@ tapconv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmg, const __grid_co
         tc_fence_after();
         // MN-major SWIZZLE_128B: 64-channel x 8-pixel atoms of 1024 B; LBO = next 64 channels (one box),
         // SBO = next 8 pixels; one MMA consumes 16 pixels = 2048 B along K.
-        const uint64_t ad = make_desc(smem_u32(s.a[st]), kABytes, 1024);
-        const uint64_t bd = make_desc(smem_u32(s.b[st]), kABytes, 1024);
+        const uint64_t ad = make_desc(smem_u32(s.a(st)), kABytes, 1024);
+        const uint64_t bd = make_desc(smem_u32(s.b(st)), kABytes, 1024);
 #pragma unroll
         for (int k = 0; k < kTileM / 16; ++k)
           umma_f16(tmem_base, ad + (uint64_t)(k * 128), bd + (uint64_t)(k * 128), idesc, (kb | k) != 0);
         umma_commit(&s.empty[st]);
       }
-      umma_commit(s.done);
+      umma_commit(&s.done[0]);
     }
   } else {
     const int q = warp % 4;
     const int o = o0 + q * 32 + lane;
-    mbar_wait(s.done, 0);
+    mbar_wait(&s.done[0], 0);
     tc_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     float* row = dw + (long long)o * p.w_ld + (long long)p.wtap[tap] * p.Cin + c0;
@@ -479,7 +512,17 @@ bool dense_cl(int64_t sn, int64_t sh, int64_t sw, int64_t sc, int N, int H, int 
   return sc == 1 && (W == 1 || sw == C) && (H == 1 || sh == (int64_t)W * C) && (N == 1 || sn == (int64_t)H * W * C);
 }
 
-int fwd_smem_bytes() { return kStages * (kABytes + kBBytes) + 1024 + 256; }
+int fwd_smem_bytes() { return kFwdStages * (kABytes + kBBytes) + 1024 + 256; }
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
 int wg_smem_bytes() { return kStages * (kWgABytes + kWgBBytes) + 1024 + 256; }
 
 }  // namespace
@@ -529,7 +572,9 @@ extern "C" int lcgan_tapconv_tc(const lcgan_tapconv* d, const void* x, const voi
     attr_err = cudaFuncSetAttribute(tapconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem_bytes());
   });
   LCGAN_CHECK(attr_err == cudaSuccess, "tapconv_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(attr_err));
-  dim3 grid(p.tiles_w * p.tiles_h * tiles_b, (d->Cout + p.BN - 1) / p.BN);
+  p.n_tiles = (d->Cout + p.BN - 1) / p.BN;
+  p.total_tiles = p.tiles_w * p.tiles_h * tiles_b * p.n_tiles;
+  const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();   // persistent: one CTA per SM
   tapconv_tc_kernel<<<grid, kThreads, fwd_smem_bytes(), (cudaStream_t)stream>>>(tmx, tmw, p, y, rowscale, bias, residual);
   LCGAN_LAUNCH_CHECK();
   return 0;

@@ -34,14 +34,16 @@ __device__ __forceinline__ float epilogue(const lcgan_tapconv& d, float acc, int
 }
 
 // ------------------------------------------------------------------------------------------
-// thin-out: a group of G lanes owns one lattice point and strides over X's channel vectors
+// thin-out: one thread owns one lattice point and walks X's channel vectors; the weights are read
+// from shared memory as warp-wide broadcasts (every lane needs the same [o][t][c] vector), so no
+// cross-lane reduction is needed.  Lanes of a warp cover consecutive pixels: each 16-byte load is
+// a separate sector of the same cache lines the next iterations consume.
 // ------------------------------------------------------------------------------------------
 template <typename TX, typename TY, int V>
 __global__ void __launch_bounds__(kThreads)
 thin_out_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const void* __restrict__ w, TY* __restrict__ y,
-                const float* __restrict__ rowscale, const float* __restrict__ bias, const TY* __restrict__ residual,
-                int G) {
-  __shared__ float ws[kSmemFloats];          // [o][t][c]
+                const float* __restrict__ rowscale, const float* __restrict__ bias, const TY* __restrict__ residual) {
+  __shared__ __align__(16) float ws[kSmemFloats];          // [o][t][c]
   const int tc = d.ntaps * d.Cin;
   for (int i = threadIdx.x; i < d.Cout * tc; i += kThreads) {
     const int o = i / tc, r = i - o * tc, t = r / d.Cin, c = r - t * d.Cin;
@@ -50,28 +52,33 @@ thin_out_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const void* __r
   __syncthreads();
   const int cv = d.Cin / V;
   const int64_t rows = (int64_t)d.N * d.MH * d.MW;
-  const int gl = threadIdx.x % G, gpb = kThreads / G;
-  const int64_t rows_pad = (rows + gpb - 1) / gpb * gpb;
-  for (int64_t r = (int64_t)blockIdx.x * gpb + threadIdx.x / G; r < rows_pad; r += (int64_t)gridDim.x * gpb) {
-    const bool live = r < rows;
+  for (int64_t r = blockIdx.x * (int64_t)kThreads + threadIdx.x; r < rows; r += (int64_t)gridDim.x * kThreads) {
+    const int n = (int)(r % d.MW);
+    const int64_t q = r / d.MW;
+    const int m = (int)(q % d.MH);
+    const int b = (int)(q / d.MH);
     float acc[kMaxThin] = {0.f, 0.f, 0.f, 0.f};
-    int b = 0, m = 0, n = 0;
-    if (live) {
-      n = (int)(r % d.MW);
-      const int64_t q = r / d.MW;
-      m = (int)(q % d.MH);
-      b = (int)(q / d.MH);
-      for (int t = 0; t < d.ntaps; ++t) {
-        const int iy = m * d.is + d.dy[t], ix = n * d.is + d.dx[t];
-        if (iy < 0 || iy >= d.IH || ix < 0 || ix >= d.IW) continue;
-        const TX* xp = x + b * d.xs_n + iy * d.xs_h + ix * d.xs_w;
-        for (int v = gl; v < cv; v += G) {
-          float f[V];
-          if constexpr (V == 1) f[0] = ldf(xp + (int64_t)v * d.xs_c); else ldv<TX, V>(xp + v * V, f);
+    for (int t = 0; t < d.ntaps; ++t) {
+      const int iy = m * d.is + d.dy[t], ix = n * d.is + d.dx[t];
+      if (iy < 0 || iy >= d.IH || ix < 0 || ix >= d.IW) continue;
+      const TX* xp = x + b * d.xs_n + iy * d.xs_h + ix * d.xs_w;
+      const float* wt = ws + t * d.Cin;
+#pragma unroll 4
+      for (int v = 0; v < cv; ++v) {
+        float f[V];
+        if constexpr (V == 1) f[0] = ldf(xp + (int64_t)v * d.xs_c); else ldv<TX, V>(xp + v * V, f);
 #pragma unroll
-          for (int o = 0; o < kMaxThin; ++o) {
-            if (o < d.Cout) {
-              const float* wp = ws + (o * d.ntaps + t) * d.Cin + v * V;
+        for (int o = 0; o < kMaxThin; ++o) {
+          if (o < d.Cout) {
+            const float* wp = wt + o * tc + v * V;
+            if constexpr (V % 4 == 0) {
+#pragma unroll
+              for (int i = 0; i < V; i += 4) {
+                const float4 w4 = *reinterpret_cast<const float4*>(wp + i);
+                acc[o] = fmaf(f[i], w4.x, acc[o]); acc[o] = fmaf(f[i + 1], w4.y, acc[o]);
+                acc[o] = fmaf(f[i + 2], w4.z, acc[o]); acc[o] = fmaf(f[i + 3], w4.w, acc[o]);
+              }
+            } else {
 #pragma unroll
               for (int i = 0; i < V; ++i) acc[o] = fmaf(f[i], wp[i], acc[o]);
             }
@@ -79,17 +86,11 @@ thin_out_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const void* __r
         }
       }
     }
-    for (int s = G >> 1; s > 0; s >>= 1) {
-#pragma unroll
-      for (int o = 0; o < kMaxThin; ++o) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], s);
-    }
-    if (live && gl == 0) {
-      const int64_t base = b * d.ys_n + (int64_t)(m * d.os + d.py) * d.ys_h + (int64_t)(n * d.os + d.px) * d.ys_w;
-      for (int o = 0; o < d.Cout; ++o) {
-        float v = epilogue(d, acc[o], b, o, rowscale, bias);
-        if (residual) v += ldf(residual + base + o * d.ys_c);
-        stf(y + base + o * d.ys_c, v);
-      }
+    const int64_t base = b * d.ys_n + (int64_t)(m * d.os + d.py) * d.ys_h + (int64_t)(n * d.os + d.px) * d.ys_w;
+    for (int o = 0; o < d.Cout; ++o) {
+      float v = epilogue(d, acc[o], b, o, rowscale, bias);
+      if (residual) v += ldf(residual + base + o * d.ys_c);
+      stf(y + base + o * d.ys_c, v);
     }
   }
 }
@@ -101,7 +102,7 @@ template <typename TX, typename TY, int V>
 __global__ void __launch_bounds__(kThreads)
 thin_in_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const void* __restrict__ w, TY* __restrict__ y,
                const float* __restrict__ rowscale, const float* __restrict__ bias, const TY* __restrict__ residual) {
-  __shared__ float ws[kSmemFloats];          // [t][c][o]
+  __shared__ __align__(16) float ws[kSmemFloats];          // [t][c][o]
   const int tc = d.ntaps * d.Cin;
   for (int i = threadIdx.x; i < d.Cout * tc; i += kThreads) {
     const int o = i % d.Cout, r = i / d.Cout, t = r / d.Cin, c = r - t * d.Cin;
@@ -126,8 +127,17 @@ thin_in_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const void* __re
       for (int c = 0; c < d.Cin; ++c) {
         const float xv = ldf(xp + c * d.xs_c);
         const float* wp = ws + (t * d.Cin + c) * d.Cout + o0;
+        if constexpr (V % 4 == 0) {
 #pragma unroll
-        for (int i = 0; i < V; ++i) acc[i] = fmaf(xv, wp[i], acc[i]);
+          for (int i = 0; i < V; i += 4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wp + i);
+            acc[i] = fmaf(xv, w4.x, acc[i]); acc[i + 1] = fmaf(xv, w4.y, acc[i + 1]);
+            acc[i + 2] = fmaf(xv, w4.z, acc[i + 2]); acc[i + 3] = fmaf(xv, w4.w, acc[i + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < V; ++i) acc[i] = fmaf(xv, wp[i], acc[i]);
+        }
       }
     }
     const int64_t base = b * d.ys_n + (int64_t)(m * d.os + d.py) * d.ys_h + (int64_t)(n * d.os + d.px) * d.ys_w;
@@ -242,31 +252,47 @@ thin_wgrad_kernel(const lcgan_tapconv d, const TW* __restrict__ wide, const TT* 
 // skinny linear: out[m][n] = sum_k x[m][k] w[n][k], m <= 32.  One warp per output feature, lanes
 // stride over K (coalesced w row), 32 accumulators per lane, shuffle reduction.
 // ------------------------------------------------------------------------------------------
+constexpr int kSkinnyKC = 256;    // K chunk staged in shared memory: 32 rows x 256 floats = 32 KiB
+
 template <typename TX, typename TWt, typename TY>
 __global__ void __launch_bounds__(kThreads)
 skinny_linear_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const TWt* __restrict__ w, TY* __restrict__ y,
                      const float* __restrict__ rowscale, const float* __restrict__ bias, const TY* __restrict__ residual) {
+  __shared__ float xs[32][kSkinnyKC];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int n = blockIdx.x * (kThreads / 32) + warp;
-  if (n >= d.Cout) return;
+  const bool nlive = n < d.Cout;
   const int M = d.N, K = d.Cin;
   float acc[32];
 #pragma unroll
   for (int m = 0; m < 32; ++m) acc[m] = 0.f;
-  const TWt* wr = w + (int64_t)n * d.w_ld;
-  for (int k = lane; k < K; k += 32) {
-    const float wv = ldf(wr + k);
+  const TWt* wr = w + (int64_t)(nlive ? n : 0) * d.w_ld;
+  for (int k0 = 0; k0 < K; k0 += kSkinnyKC) {
+    const int kc = min(kSkinnyKC, K - k0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * kSkinnyKC; i += kThreads) {
+      const int m = i / kSkinnyKC, k = i - m * kSkinnyKC;
+      xs[m][k] = (m < M && k < kc) ? ldf(x + m * d.xs_n + (int64_t)(k0 + k) * d.xs_c) : 0.f;
+    }
+    __syncthreads();
+    float wv[kSkinnyKC / 32];
 #pragma unroll
-    for (int m = 0; m < 32; ++m)
-      if (m < M) acc[m] = fmaf(ldf(x + m * d.xs_n + k * d.xs_c), wv, acc[m]);
+    for (int j = 0; j < kSkinnyKC / 32; ++j) {
+      const int k = lane + 32 * j;
+      wv[j] = (nlive && k < kc) ? ldf(wr + k0 + k) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < kSkinnyKC / 32; ++j) {
+#pragma unroll
+      for (int m = 0; m < 32; ++m) acc[m] = fmaf(xs[m][lane + 32 * j], wv[j], acc[m]);
+    }
   }
 #pragma unroll
   for (int m = 0; m < 32; ++m) acc[m] = warp_sum(acc[m]);
-  // lane m writes row m
   float mine = 0.f;
 #pragma unroll
   for (int m = 0; m < 32; ++m) if (lane == m) mine = acc[m];
-  if (lane < M) {
+  if (nlive && lane < M) {
     float v = epilogue(d, mine, lane, n, rowscale, bias);
     const int64_t off = lane * d.ys_n + n * d.ys_c;
     if (residual) v += ldf(residual + off);
@@ -342,10 +368,9 @@ int lcgan_thin_forward(const lcgan_tapconv& d, const void* x, const void* w, voi
     const bool v_ok = dense_inner(d.xs_c, d.xs_w, d.xs_h, d.xs_n, d.Cin, vec) && ((uintptr_t)x % 16 == 0);
 #define TO(TXT, TYT, VV)                                                                                    \
     do {                                                                                                    \
-      const int G = pow2_group(d.Cin / VV);                                                                 \
-      const int grid = grid_cap((rows + kThreads / G - 1) / (kThreads / G), 16);                            \
+      const int grid = grid_cap((rows + kThreads - 1) / kThreads, 16);                                      \
       thin_out_kernel<TXT, TYT, VV><<<grid, kThreads, 0, s>>>(d, (const TXT*)x, w, (TYT*)y, rowscale, bias, \
-                                                              (const TYT*)residual, G);                     \
+                                                              (const TYT*)residual);                        \
     } while (0)
     if (xf && yf) { if (v_ok) TO(float, float, 4); else TO(float, float, 1); }
     else if (xf && !yf) { if (v_ok) TO(float, bf16, 4); else TO(float, bf16, 1); }

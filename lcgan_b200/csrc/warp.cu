@@ -53,6 +53,31 @@ template <typename T, int V> __device__ __forceinline__ void stv(T* p, const flo
   if constexpr (V == 1) stf(p, f[0]); else { Vec16<T> v; v.pack(f); v.store(p); }
 }
 
+// Tap table of one output pixel: 16 (offset, weight) pairs with out-of-range taps clamped to a
+// valid address and given weight 0, so the gather below is branch-free and all 16 vector loads of a
+// channel vector are in flight together.
+struct Taps {
+  int off[16];     // pixel offset (y*W + x) inside the image
+  float w[16];
+};
+
+__device__ __forceinline__ void make_taps(const PixCoord& pc, int H, int W, const float* wx, const float* wy, Taps& t) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int yy = pc.y0 - 1 + j;
+    const bool oky = yy >= 0 && yy < H;
+    const int yc = min(max(yy, 0), H - 1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int xx = pc.x0 - 1 + i;
+      const bool ok = oky && xx >= 0 && xx < W;
+      const int xc = min(max(xx, 0), W - 1);
+      t.off[j * 4 + i] = yc * W + xc;
+      t.w[j * 4 + i] = ok ? wy[j] * wx[i] : 0.f;
+    }
+  }
+}
+
 template <typename T, int V>
 __global__ void __launch_bounds__(kThreads)
 warp_fwd_kernel(const T* __restrict__ x, const float* __restrict__ flow, T* __restrict__ out, int N, int H,
@@ -69,26 +94,20 @@ warp_fwd_kernel(const T* __restrict__ x, const float* __restrict__ flow, T* __re
     float wx[4], wy[4];
     cubic_w(pc.tx, wx);
     cubic_w(pc.ty, wy);
+    Taps tp;
+    make_taps(pc, H, W, wx, wy, tp);
     const T* xb = x + (int64_t)b * H * W * C;
     for (int v = gl; v < cv; v += G) {
+      float f[16][V];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) ldv<T, V>(xb + (int64_t)tp.off[k] * C + v * V, f[k]);
       float acc[V];
 #pragma unroll
       for (int i = 0; i < V; ++i) acc[i] = 0.f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int yy = pc.y0 - 1 + j;
-        if (yy < 0 || yy >= H) continue;
+      for (int k = 0; k < 16; ++k)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int xx = pc.x0 - 1 + i;
-          if (xx < 0 || xx >= W) continue;
-          float f[V];
-          ldv<T, V>(xb + ((int64_t)yy * W + xx) * C + v * V, f);
-          const float wgt = wy[j] * wx[i];
-#pragma unroll
-          for (int k = 0; k < V; ++k) acc[k] = fmaf(f[k], wgt, acc[k]);
-        }
-      }
+        for (int i = 0; i < V; ++i) acc[i] = fmaf(f[k][i], tp.w[k], acc[i]);
       stv<T, V>(out + pix * C + v * V, acc);
     }
   }
@@ -117,35 +136,35 @@ warp_bwd_kernel(const T* __restrict__ x, const float* __restrict__ flow, const T
       float wx[4], wy[4], dwx[4], dwy[4];
       cubic_w(pc.tx, wx); cubic_w(pc.ty, wy);
       cubic_dw(pc.tx, dwx); cubic_dw(pc.ty, dwy);
+      Taps tp, tgx, tgy;                       // value weights and the two derivative weight sets
+      make_taps(pc, H, W, wx, wy, tp);
+      make_taps(pc, H, W, dwx, wy, tgx);
+      make_taps(pc, H, W, wx, dwy, tgy);
       const int64_t boff = (int64_t)b * H * W * C;
       for (int v = gl; v < cv; v += G) {
         float g[V];
         ldv<T, V>(dout + pix * C + v * V, g);
+        float f[16][V];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int yy = pc.y0 - 1 + j;
-          if (yy < 0 || yy >= H) continue;
+        for (int k = 0; k < 16; ++k) ldv<T, V>(x + boff + (int64_t)tp.off[k] * C + v * V, f[k]);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int xx = pc.x0 - 1 + i;
-            if (xx < 0 || xx >= W) continue;
-            const int64_t off = boff + ((int64_t)yy * W + xx) * C + v * V;
-            float f[V];
-            ldv<T, V>(x + off, f);
-            float dot = 0.f;
+        for (int k = 0; k < 16; ++k) {
+          float dot = 0.f;
 #pragma unroll
-            for (int k = 0; k < V; ++k) dot = fmaf(f[k], g[k], dot);
-            gix = fmaf(dot, wy[j] * dwx[i], gix);
-            giy = fmaf(dot, dwy[j] * wx[i], giy);
-            const float wgt = wy[j] * wx[i];
+          for (int i = 0; i < V; ++i) dot = fmaf(f[k][i], g[i], dot);
+          gix = fmaf(dot, tgx.w[k], gix);
+          giy = fmaf(dot, tgy.w[k], giy);
+          const float wgt = tp.w[k];
+          if (wgt != 0.f) {
+            float* dp = dx + boff + (int64_t)tp.off[k] * C + v * V;
             if constexpr (V % 4 == 0) {
 #pragma unroll
-              for (int k = 0; k < V; k += 4)
-                atomicAdd(reinterpret_cast<float4*>(dx + off + k),
-                          make_float4(g[k] * wgt, g[k + 1] * wgt, g[k + 2] * wgt, g[k + 3] * wgt));
+              for (int i = 0; i < V; i += 4)
+                atomicAdd(reinterpret_cast<float4*>(dp + i),
+                          make_float4(g[i] * wgt, g[i + 1] * wgt, g[i + 2] * wgt, g[i + 3] * wgt));
             } else {
 #pragma unroll
-              for (int k = 0; k < V; ++k) atomicAdd(dx + off + k, g[k] * wgt);
+              for (int i = 0; i < V; ++i) atomicAdd(dp + i, g[i] * wgt);
             }
           }
         }

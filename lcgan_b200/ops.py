@@ -146,6 +146,13 @@ def pack_weight(w: torch.Tensor, transposed: bool, dtype: torch.dtype) -> torch.
     return p
 
 
+def clear_pack_cache():
+    """Drop every cached weight pack (called around CUDA-graph capture so that each graph records
+    its own packing kernels and no eager path keeps a graph-pool tensor)."""
+    with _pack_lock:
+        _pack_cache.clear()
+
+
 def unpack_wgrad(dw2: torch.Tensor, wshape, transposed: bool) -> torch.Tensor:
     if len(wshape) == 2:
         o, i = wshape
@@ -668,6 +675,9 @@ class SumSq(torch.autograd.Function):
         return dx
 
 
+_ema_tables = {}
+
+
 def ema_lerp_(dst_tensors, src_tensors, decay: float):
     """dst = src.lerp(dst, decay) for every tensor pair, in ONE launch (ema.py:26-32)."""
     pairs = [(d, s) for d, s in zip(dst_tensors, src_tensors) if d.numel() > 0]
@@ -677,9 +687,13 @@ def ema_lerp_(dst_tensors, src_tensors, decay: float):
     _need_cuda(pairs[0][0])
     for d, s in pairs:
         assert d.dtype == torch.float32 and s.dtype == torch.float32 and d.is_contiguous() and s.is_contiguous()
-    table = torch.tensor([[d.data_ptr() for d, _ in pairs], [s.data_ptr() for _, s in pairs],
-                          [d.numel() for d, _ in pairs]], dtype=torch.int64).to(dev, non_blocking=True)
+    key = tuple((d.data_ptr(), s.data_ptr(), d.numel()) for d, s in pairs)
+    table = _ema_tables.get(key)
+    if table is None:
+        # pointer table built once per parameter set (H2D copy outside any graph capture)
+        table = torch.tensor([[k[0] for k in key], [k[1] for k in key], [k[2] for k in key]],
+                             dtype=torch.int64).to(dev)
+        _ema_tables.clear()
+        _ema_tables[key] = table
     _lib.call("lcgan_ema_lerp", _ptr(table[0]), _ptr(table[1]), _ptr(table[2]), len(pairs), C.c_float(decay),
-              _stream(pairs[0][0]))
-    # keep the table alive until the kernel has consumed it
-    table.record_stream(torch.cuda.current_stream(dev))
+              _stream(pairs[0][0]), nbytes=3 * 4 * sum(k[2] for k in key))

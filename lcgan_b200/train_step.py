@@ -111,3 +111,93 @@ class Trainer:
         self.ema.update(it)
         d = self.d_step(it, zd, data).item()
         return g, d
+
+
+class GraphedTrainer(Trainer):
+    """The same iteration with every step variant captured once into a CUDA graph and replayed:
+    the ~1900 kernel launches of an iteration are then issued by the driver, not by Python
+    (B200 guide: "capture launch-bound inner loops in CUDA graphs").  Five graphs cover the
+    reference schedule: G even / G odd (+EMA), D even / D odd / D odd with R1.  Inputs are static
+    device buffers that the caller fills before each replay; losses are left in device buffers.
+    Single-process only (DDP's reducer is not captured); requires_grad / freezeD flags are frozen
+    at capture time.
+    """
+
+    VARIANTS = ("g_even", "g_odd", "d_even", "d_odd", "d_r1")
+
+    def __init__(self, G, D, hp, batch, device, **kw):
+        super().__init__(G, D, hp, **kw)
+        for opt in (self.g_opt, self.d_opt):          # Adam state on device so step() is capturable
+            for grp in opt.param_groups:
+                grp["capturable"] = True
+        res = _bare(G).img_resolution
+        self.z = {k: torch.zeros(batch, 64, device=device) for k in ("rand1", "rand2", "resample1", "resample2")}
+        self.zd = {k: torch.zeros(batch, 64, device=device) for k in ("rand1", "rand2")}
+        self.data = {k: torch.zeros(batch, 3, res, res, device=device)
+                     for k in ("image", "geometry_change", "appearance_change")}
+        self.g_loss = torch.zeros((), device=device)
+        self.d_loss = torch.zeros((), device=device)
+        self.graphs = {}
+        self.launches = {}
+
+    @staticmethod
+    def variant(it, which):
+        if which == "g":
+            return "g_even" if it % 2 == 0 else "g_odd"
+        return "d_even" if it % 2 == 0 else ("d_r1" if it % 8 == 1 else "d_odd")
+
+    def _run(self, name):
+        it = {"g_even": 0, "g_odd": 3, "d_even": 0, "d_odd": 3, "d_r1": 1}[name]
+        if name.startswith("g"):
+            loss = self.g_step(it, self.z)
+            self.ema.update(it)
+            self.g_loss.copy_(loss.detach())
+        else:
+            loss = self.d_step(it, self.zd, self.data)
+            self.d_loss.copy_(loss.detach())
+
+    def capture(self, warmup=3):
+        from . import _lib, ops
+        dev = self.g_loss.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                   # eager warm-up: lazy inits, Adam state
+            for _ in range(warmup):
+                for name in self.VARIANTS:
+                    self._run(name)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        pool = None
+        for name in self.VARIANTS:
+            ops.clear_pack_cache()
+            g = torch.cuda.CUDAGraph()
+            n0 = _lib.launches
+            with torch.cuda.graph(g, pool=pool):
+                self._run(name)
+            self.launches[name] = _lib.launches - n0
+            pool = g.pool()
+            self.graphs[name] = g
+        ops.clear_pack_cache()
+        torch.cuda.synchronize(dev)
+
+    def reset_optimizer_state(self):
+        """Zero Adam moments / step counters in place (the graphs hold their addresses)."""
+        for opt in (self.g_opt, self.d_opt):
+            for st in opt.state.values():
+                for v in st.values():
+                    if torch.is_tensor(v):
+                        v.zero_()
+
+    def iteration_graphed(self, it):
+        """One iteration from the static input buffers; returns the number of our kernels replayed."""
+        return self.replay_g(it) + self.replay_d(it)
+
+    def replay_g(self, it):
+        v = self.variant(it, "g")
+        self.graphs[v].replay()
+        return self.launches[v]
+
+    def replay_d(self, it):
+        v = self.variant(it, "d")
+        self.graphs[v].replay()
+        return self.launches[v]

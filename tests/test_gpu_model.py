@@ -166,3 +166,37 @@ def test_per_layer_activations_and_grads_vs_oracle(mode):
         assert rel_l2(xm.grad.float(), xo.grad) < gtol, f"D block {i} dx"
         for k, p in D.shared_model[i + 2].named_parameters():
             assert rel_l2(p.grad, dcuda[f"shared_model.{i + 2}.{k}"].grad) < gtol, f"D block {i} {k}"
+
+
+def test_cuda_graph_replay_matches_eager():
+    """GraphedTrainer (five captured step variants) reproduces the eager iteration: same init,
+    same inputs, 8 iterations (one full loss-schedule cycle), fp32 mode."""
+    from lcgan_b200 import train_step as T
+    O, cfg, gsd, dsd, G, D = _build(32, 0, "fp32")
+    _, _, _, _, G2, D2 = _build(32, 0, "fp32")
+    hp = O.Hyper()
+    b, dev = 4, torch.device("cuda")
+    gt = T.GraphedTrainer(G, D, hp, b, dev)
+    gt.capture(warmup=2)
+    # capture ran optimizer steps: restore the initial weights / EMA / Adam state in place
+    G.load_state_dict(gsd); D.load_state_dict(dsd); gt.G_ema.load_state_dict(gsd)
+    gt.reset_optimizer_state()
+    et = T.Trainer(G2, D2, hp)
+    gen = torch.Generator().manual_seed(11)
+    for it in range(8):
+        zg, zd = O.synthetic_latents(b, cfg, gen, "cuda"), O.synthetic_latents(b, cfg, gen, "cuda")
+        data = O.synthetic_data(b, cfg, gen, "cuda")
+        for k in gt.z: gt.z[k].copy_(zg[k])
+        for k in gt.zd: gt.zd[k].copy_(zd[k])
+        for k in gt.data: gt.data[k].copy_(data[k])
+        n = gt.iteration_graphed(it)
+        assert n > 100
+        ge, de = et.iteration(it, zg, {k: zd[k] for k in ("rand1", "rand2")}, data)
+        gg, dg = float(gt.g_loss), float(gt.d_loss)
+        # Adam with beta1 = 0 turns summation-order noise (atomics) on near-zero gradients into
+        # +-lr parameter differences, so the two runs drift apart after a few optimizer steps:
+        # tight for the first iterations (each variant's graph is exercised by it 0..1), loose after.
+        tol = 2e-3 if it < 3 else 6e-2
+        assert abs(gg - ge) < tol * max(1.0, abs(ge)), (it, gg, ge)
+        assert abs(dg - de) < tol * max(1.0, abs(de)), (it, dg, de)
+    assert rel_l2(gt.G_ema.const.detach(), et.G_ema.const.detach()) < 1e-3
