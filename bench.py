@@ -300,6 +300,11 @@ def main():
                "d2h_bytes_per_step": 8 * world}
 
     roof, kernels = None, None
+    if use_graphs:                                           # release the graphs' private memory pool
+        import gc
+        tr.graphs.clear()
+        gc.collect()
+        torch.cuda.empty_cache()
     if not args.no_roofline and rank == 0:
         roof, kernels = roofline_pass(step_eager_for_profile, it0, _lib, peaks())
     if world > 1:

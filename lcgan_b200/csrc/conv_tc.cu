@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <mutex>
+#include <stdlib.h>
 
 namespace {
 
@@ -24,7 +25,7 @@ constexpr int kStages = 3;                     // weight-gradient kernel: 3 x 64
 constexpr int kFwdStages = 4;                  // forward kernel: 4 x 32 KiB
 constexpr int kAccStages = 2;                  // TMEM accumulator double buffer (2 x 128 columns)
 constexpr int kTileM = 128;                    // lattice points (fwd) / pixels per k-block (wgrad)
-constexpr int kBlockK = 64;                    // channels per k-block = one 128-byte swizzle row
+constexpr int kBlockK = 64;                    // max channels per k-block (one 128-byte swizzle row); 32 -> 64-byte rows
 constexpr int kMaxBN = 128;
 constexpr int kABytes = kTileM * kBlockK * 2;  // 16 KiB
 constexpr int kBBytes = kMaxBN * kBlockK * 2;  // 16 KiB
@@ -34,9 +35,12 @@ struct TcParams {
   int N, Cin, Cout;
   int wt, ht, nt, tiles_w, tiles_h;
   int is, os, py, px;
-  int ntaps, kpt;                               // kpt = Cin / 64
+  int ntaps, kpt, kc;                           // kc = channels per k-block (64 or 32), kpt = Cin / kc
   int dy[LCGAN_MAX_TAPS], dx[LCGAN_MAX_TAPS], wtap[LCGAN_MAX_TAPS];
   int BN, n_tiles, total_tiles;
+  int rowshare;                                 // 3x3 stride-1: one tall A tile per dx serves the 3 dy taps
+  int grp_wtap[3][3];                           // [dx+1][dy+1] -> weight tap index
+  int stages, a_bytes, b_bytes;
   long long ys_n, ys_h, ys_w;
   int y_f32;
   float acc_scale, bias_scale, slope, gain;
@@ -48,7 +52,7 @@ struct WgParams {
   int is, os, py, px;
   int ntaps;
   int dy[LCGAN_MAX_TAPS], dx[LCGAN_MAX_TAPS], wtap[LCGAN_MAX_TAPS];
-  int BN, ctiles;
+  int BN, ctiles, kcg, kcx;                     // channels per TMA box of G and of X (64 or 32)
   int tiles_per_split;
   long long w_ld;
   float scale;
@@ -131,13 +135,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100 version 1, SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// kc = channels per swizzle row: 64 -> SWIZZLE_128B (layout 2), 32 -> SWIZZLE_64B (layout 4).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, int kc) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;     // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;     // LayoutType::SWIZZLE_128B
+  d |= (uint64_t)(kc == 64 ? 2 : 4) << 61;     // LayoutType::SWIZZLE_128B / SWIZZLE_64B
   return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): bf16 x bf16 -> f32, M=128.
@@ -191,13 +196,13 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
   //   warp 1   MMA issuer, accumulates tile i into TMEM stage i%2
   //   warps2-5 epilogue of tile i overlaps the MMAs of tile i+1 (TMEM double buffer)
   extern __shared__ uint8_t smem_raw[];
-  const Smem s = carve(smem_raw, kFwdStages, kABytes, kBBytes);
+  const Smem s = carve(smem_raw, p.stages, p.a_bytes, p.b_bytes);
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmx);
     tma_prefetch_desc(&tmw);
-    for (int i = 0; i < kFwdStages; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
     for (int i = 0; i < kAccStages; ++i) { mbar_init(&s.done[i], 1); mbar_init(&s.acc_empty[i], 4); }
     fence_barrier_init();
   }
@@ -206,11 +211,12 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s.tmem_slot;
-  const int nkb = p.ntaps * p.kpt;
+  const int nkb = (p.rowshare ? 3 : p.ntaps) * p.kpt;
+  const uint32_t wtile = (uint32_t)p.BN * p.kc * 2;           // bytes of one tap's weight tile
 
   if (warp == 0) {
     if (lane == 0) {
-      const uint32_t tx_bytes = kABytes + p.BN * kBlockK * 2;
+      const uint32_t tx_bytes = p.rowshare ? (uint32_t)p.a_bytes + 3 * wtile : (kTileM + p.BN) * p.kc * 2;
       int g = 0;                                            // k-block counter across tiles
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int nt_i = tile % p.n_tiles;
@@ -220,12 +226,20 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
         const int tb = t / p.tiles_h;
         const int n0 = tw * p.wt, m0 = th * p.ht, b0 = tb * p.nt, o0 = nt_i * p.BN;
         for (int kb = 0; kb < nkb; ++kb, ++g) {
-          const int st = g % kFwdStages, ph = (g / kFwdStages) & 1;
+          const int st = g % p.stages, ph = (g / p.stages) & 1;
           mbar_wait(&s.empty[st], ph ^ 1);
           const int tap = kb / p.kpt, cb = kb - tap * p.kpt;
           mbar_expect_tx(&s.full[st], tx_bytes);
-          tma_load_4d(s.a(st), &tmx, &s.full[st], cb * kBlockK, n0 * p.is + p.dx[tap], m0 * p.is + p.dy[tap], b0);
-          tma_load_2d(s.b(st), &tmw, &s.full[st], p.wtap[tap] * p.Cin + cb * kBlockK, o0);
+          if (p.rowshare) {
+            // `tap` is the dx group: a (ht+2)-row tile starting one row above serves dy = -1, 0, +1
+            tma_load_4d(s.a(st), &tmx, &s.full[st], cb * p.kc, n0 + tap - 1, m0 - 1, b0);
+#pragma unroll
+            for (int dyi = 0; dyi < 3; ++dyi)
+              tma_load_2d(s.b(st) + dyi * wtile, &tmw, &s.full[st], p.grp_wtap[tap][dyi] * p.Cin + cb * p.kc, o0);
+          } else {
+            tma_load_4d(s.a(st), &tmx, &s.full[st], cb * p.kc, n0 * p.is + p.dx[tap], m0 * p.is + p.dy[tap], b0);
+            tma_load_2d(s.b(st), &tmw, &s.full[st], p.wtap[tap] * p.Cin + cb * p.kc, o0);
+          }
         }
       }
     }
@@ -239,14 +253,18 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(as * kMaxBN);
         for (int kb = 0; kb < nkb; ++kb, ++g) {
-          const int st = g % kFwdStages, ph = (g / kFwdStages) & 1;
+          const int st = g % p.stages, ph = (g / p.stages) & 1;
           mbar_wait(&s.full[st], ph);
           tc_fence_after();
-          const uint64_t ad = make_desc(smem_u32(s.a(st)), 16, 1024);
-          const uint64_t bd = make_desc(smem_u32(s.b(st)), 16, 1024);
+          const int ndy = p.rowshare ? 3 : 1;
+          for (int dyi = 0; dyi < ndy; ++dyi) {
+            // row-shared: the dy tap's 128 rows start dyi*16 pixels (= whole swizzle atoms) into the tile
+            const uint64_t ad = make_desc(smem_u32(s.a(st)) + dyi * 16 * p.kc * 2, 16, 16 * p.kc, p.kc);   // SBO = 8 rows
+            const uint64_t bd = make_desc(smem_u32(s.b(st)) + dyi * wtile, 16, 16 * p.kc, p.kc);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)   // +32 bytes along K inside the 128-byte swizzle row
-            umma_f16(tacc, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < kBlockK / 16; ++k)   // +32 bytes along K inside the swizzle row
+              if (k * 16 < p.kc) umma_f16(tacc, ad + 2 * k, bd + 2 * k, idesc, (kb | dyi | k) != 0);
+          }
           umma_commit(&s.empty[st]);
         }
         umma_commit(&s.done[as]);
@@ -375,11 +393,12 @@ tapconv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmg, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s.tmem_slot;
-  const int nbx = p.BN / 64;                      // 64-channel boxes of the X operand
+  const int nbx = p.BN / p.kcx, nbg = 128 / p.kcg;   // TMA boxes of the X and G operands
+  const uint32_t gbox = kTileM * p.kcg * 2, xbox = kTileM * p.kcx * 2;   // bytes per box
 
   if (warp == 0) {
     if (lane == 0) {
-      const uint32_t tx_bytes = kWgABytes + nbx * kABytes;
+      const uint32_t tx_bytes = kWgABytes + nbx * xbox;
       for (int kb = 0; kb < nkb; ++kb) {
         const int st = kb % kStages, ph = (kb / kStages) & 1;
         mbar_wait(&s.empty[st], ph ^ 1);
@@ -389,10 +408,10 @@ tapconv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmg, const __grid_co
         const int tb = t / p.tiles_h;
         const int n0 = tw * p.wt, m0 = th * p.ht, b0 = tb * p.nt;
         mbar_expect_tx(&s.full[st], tx_bytes);
-        for (int j = 0; j < 2; ++j)
-          tma_load_4d(s.a(st) + j * kABytes, &tmg, &s.full[st], o0 + 64 * j, n0 * p.os + p.px, m0 * p.os + p.py, b0);
+        for (int j = 0; j < nbg; ++j)      // boxes past Cout are out of range: TMA zero-fills them
+          tma_load_4d(s.a(st) + j * gbox, &tmg, &s.full[st], o0 + p.kcg * j, n0 * p.os + p.px, m0 * p.os + p.py, b0);
         for (int j = 0; j < nbx; ++j)
-          tma_load_4d(s.b(st) + j * kABytes, &tmx, &s.full[st], c0 + 64 * j, n0 * p.is + p.dx[tap],
+          tma_load_4d(s.b(st) + j * xbox, &tmx, &s.full[st], c0 + p.kcx * j, n0 * p.is + p.dx[tap],
                       m0 * p.is + p.dy[tap], b0);
       }
     }
@@ -405,11 +424,11 @@ tapconv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmg, const __grid_co
         tc_fence_after();
         // MN-major SWIZZLE_128B: 64-channel x 8-pixel atoms of 1024 B; LBO = next 64 channels (one box),
         // SBO = next 8 pixels; one MMA consumes 16 pixels = 2048 B along K.
-        const uint64_t ad = make_desc(smem_u32(s.a(st)), kABytes, 1024);
-        const uint64_t bd = make_desc(smem_u32(s.b(st)), kABytes, 1024);
+        const uint64_t ad = make_desc(smem_u32(s.a(st)), gbox, 16 * p.kcg, p.kcg);
+        const uint64_t bd = make_desc(smem_u32(s.b(st)), xbox, 16 * p.kcx, p.kcx);
 #pragma unroll
-        for (int k = 0; k < kTileM / 16; ++k)
-          umma_f16(tmem_base, ad + (uint64_t)(k * 128), bd + (uint64_t)(k * 128), idesc, (kb | k) != 0);
+        for (int k = 0; k < kTileM / 16; ++k)   // 16 pixels = 16 rows of kc*2 bytes along K
+          umma_f16(tmem_base, ad + (uint64_t)(k * 2 * p.kcg), bd + (uint64_t)(k * 2 * p.kcx), idesc, (kb | k) != 0);
         umma_commit(&s.empty[st]);
       }
       umma_commit(&s.done[0]);
@@ -466,30 +485,33 @@ EncodeTiledFn get_encode() {
 
 // 4-D map over a dense channels-last bf16 tensor [N, H, W, C]: box {64, wt, ht, nt} walked with
 // element stride `es` along W and H.
-int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int wt, int ht, int nt, int es) {
+int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int wt, int ht, int nt, int es, int kc,
+                 int extra_rows = 0) {
   EncodeTiledFn enc = get_encode();
   LCGAN_CHECK(enc != nullptr, "cuTensorMapEncodeTiled unavailable (driver too old?)");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(wt * es), (cuuint32_t)(ht * es), (cuuint32_t)nt};
+  cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)(wt * es), (cuuint32_t)(ht * es + extra_rows), (cuuint32_t)nt};
   cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   LCGAN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation) failed: %d (N=%d H=%d W=%d C=%d box=%d,%d,%d es=%d)",
               (int)r, N, H, W, C, wt, ht, nt, es);
   return 0;
 }
 
-int make_w_map(CUtensorMap* m, const void* base, int rows, long long ld, int box_rows) {
+int make_w_map(CUtensorMap* m, const void* base, int rows, long long ld, int box_rows, int kc) {
   EncodeTiledFn enc = get_encode();
   LCGAN_CHECK(enc != nullptr, "cuTensorMapEncodeTiled unavailable (driver too old?)");
   cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   LCGAN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight) failed: %d (rows=%d ld=%lld)", (int)r, rows, ld);
   return 0;
@@ -512,7 +534,7 @@ bool dense_cl(int64_t sn, int64_t sh, int64_t sw, int64_t sc, int N, int H, int 
   return sc == 1 && (W == 1 || sw == C) && (H == 1 || sh == (int64_t)W * C) && (N == 1 || sn == (int64_t)H * W * C);
 }
 
-int fwd_smem_bytes() { return kFwdStages * (kABytes + kBBytes) + 1024 + 256; }
+int fwd_smem_bytes() { return 3 * (20 * 1024 + 3 * kBBytes) + 1024 + 256; }   // row-shared mode is the larger one
 
 int sm_count() {
   static int n = 0;
@@ -530,7 +552,7 @@ int wg_smem_bytes() { return kStages * (kWgABytes + kWgBBytes) + 1024 + 256; }
 extern "C" int lcgan_tapconv_tc_eligible(const lcgan_tapconv* d) {
   if (!d) return 0;
   if (d->x_dtype != LCGAN_BF16) return 0;
-  if (d->Cin % kBlockK != 0 || d->Cout % 16 != 0) return 0;
+  if (d->Cin % 32 != 0 || d->Cout % 16 != 0) return 0;
   if (!dense_cl(d->xs_n, d->xs_h, d->xs_w, d->xs_c, d->N, d->IH, d->IW, d->Cin)) return 0;
   // output: channel-innermost, 16-byte aligned pixel rows (dense channels-last or any such strides)
   if (d->ys_c != 1 || (d->OW > 1 && d->ys_w % 8 != 0) || (d->OH > 1 && d->ys_h % 8 != 0) ||
@@ -555,16 +577,37 @@ extern "C" int lcgan_tapconv_tc(const lcgan_tapconv* d, const void* x, const voi
   p.tiles_w = d->MW / p.wt; p.tiles_h = d->MH / p.ht;
   const int tiles_b = (d->N + p.nt - 1) / p.nt;
   p.is = d->is; p.os = d->os; p.py = d->py; p.px = d->px;
-  p.ntaps = d->ntaps; p.kpt = d->Cin / kBlockK;
+  p.kc = d->Cin % 64 == 0 ? 64 : 32;
+  p.ntaps = d->ntaps; p.kpt = d->Cin / p.kc;
   for (int t = 0; t < d->ntaps; ++t) { p.dy[t] = d->dy[t]; p.dx[t] = d->dx[t]; p.wtap[t] = d->wtap[t]; }
   p.BN = d->Cout >= kMaxBN ? kMaxBN : d->Cout;       // Cout % 16 == 0
   p.ys_n = d->ys_n; p.ys_h = d->ys_h; p.ys_w = d->ys_w;
   p.y_f32 = d->y_dtype == LCGAN_F32;
   p.acc_scale = d->acc_scale; p.bias_scale = d->bias_scale; p.slope = d->slope; p.gain = d->gain;
 
+  // row-shared mode: full 3x3 stride-1 tap set on a 16-wide, 8-tall, single-image tile
+  p.rowshare = 0;
+  if (d->ntaps == 9 && d->is == 1 && p.wt == 16 && p.ht == 8 && p.nt == 1) {
+    int seen = 0;
+    for (int t = 0; t < 9; ++t) {
+      const int dy = d->dy[t], dx = d->dx[t];
+      if (dy < -1 || dy > 1 || dx < -1 || dx > 1) { seen = -1; break; }
+      p.grp_wtap[dx + 1][dy + 1] = d->wtap[t];
+      seen |= 1 << ((dy + 1) * 3 + dx + 1);
+    }
+    p.rowshare = (seen == 0x1FF) && getenv("LCGAN_NO_ROWSHARE") == nullptr;
+  }
+  if (p.rowshare) {
+    p.a_bytes = (p.ht + 2) * 16 * p.kc * 2;                 // 20 KiB (kc=64) / 10 KiB (kc=32)
+    p.b_bytes = 3 * p.BN * p.kc * 2;
+    p.stages = 3;
+    if ((p.a_bytes + p.b_bytes) * 6 <= 3 * (20 * 1024 + 3 * kBBytes)) p.stages = 6;
+  } else {
+    p.a_bytes = kABytes; p.b_bytes = kBBytes; p.stages = kFwdStages;
+  }
   CUtensorMap tmx, tmw;
-  if (int e = make_act_map(&tmx, x, d->N, d->IH, d->IW, d->Cin, p.wt, p.ht, p.nt, d->is)) return e;
-  if (int e = make_w_map(&tmw, w2, d->Cout, d->w_ld, p.BN)) return e;
+  if (int e = make_act_map(&tmx, x, d->N, d->IH, d->IW, d->Cin, p.wt, p.ht, p.nt, d->is, p.kc, p.rowshare ? 2 : 0)) return e;
+  if (int e = make_w_map(&tmw, w2, d->Cout, d->w_ld, p.BN, p.kc)) return e;
 
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
@@ -584,9 +627,9 @@ extern "C" int lcgan_tapconv_wgrad_tc(const lcgan_tapconv* d, const void* x, con
                                       void* stream) {
   // here the descriptor's X side is the layer input and its Y side is the output gradient G
   LCGAN_CHECK(lcgan_tapconv_tc_eligible(d), "tapconv_wgrad_tc: descriptor not eligible");
-  LCGAN_CHECK(d->y_dtype == LCGAN_BF16 && d->Cout % 64 == 0 &&
+  LCGAN_CHECK(d->y_dtype == LCGAN_BF16 && d->Cout % 32 == 0 &&
               dense_cl(d->ys_n, d->ys_h, d->ys_w, d->ys_c, d->N, d->OH, d->OW, d->Cout),
-              "tapconv_wgrad_tc: G must be dense channels-last bf16 with Cout %% 64 == 0");
+              "tapconv_wgrad_tc: G must be dense channels-last bf16 with Cout %% 32 == 0");
   LCGAN_CHECK(x && g && dw2 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)dw2 % 16 == 0) &&
               d->w_ld % 4 == 0, "tapconv_wgrad_tc: bad pointers/alignment");
   WgParams p{};
@@ -598,7 +641,9 @@ extern "C" int lcgan_tapconv_wgrad_tc(const lcgan_tapconv* d, const void* x, con
   p.is = d->is; p.os = d->os; p.py = d->py; p.px = d->px;
   p.ntaps = d->ntaps;
   for (int t = 0; t < d->ntaps; ++t) { p.dy[t] = d->dy[t]; p.dx[t] = d->dx[t]; p.wtap[t] = d->wtap[t]; }
-  p.BN = d->Cin >= kMaxBN ? kMaxBN : 64;            // Cin % 64 == 0
+  p.kcx = d->Cin % 64 == 0 ? 64 : 32;
+  p.kcg = d->Cout % 64 == 0 ? 64 : 32;
+  p.BN = d->Cin >= kMaxBN ? kMaxBN : d->Cin;   // multiple of kcx, <= 128 (a partial last tile is zero-filled)
   p.ctiles = (d->Cin + p.BN - 1) / p.BN;
   const int otiles = (d->Cout + 127) / 128;
   const int base = otiles * p.ctiles * d->ntaps;
@@ -610,8 +655,8 @@ extern "C" int lcgan_tapconv_wgrad_tc(const lcgan_tapconv* d, const void* x, con
   p.w_ld = d->w_ld; p.scale = scale;
 
   CUtensorMap tmg, tmx;
-  if (int e = make_act_map(&tmg, g, d->N, d->OH, d->OW, d->Cout, p.wt, p.ht, p.nt, d->os)) return e;
-  if (int e = make_act_map(&tmx, x, d->N, d->IH, d->IW, d->Cin, p.wt, p.ht, p.nt, d->is)) return e;
+  if (int e = make_act_map(&tmg, g, d->N, d->OH, d->OW, d->Cout, p.wt, p.ht, p.nt, d->os, p.kcg)) return e;
+  if (int e = make_act_map(&tmx, x, d->N, d->IH, d->IW, d->Cin, p.wt, p.ht, p.nt, d->is, p.kcx)) return e;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {

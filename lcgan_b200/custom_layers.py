@@ -102,13 +102,12 @@ class ModulatedConv2d(nn.Module):
         wsq = (wq * c).square().sum(dim=(2, 3))
         s = s.float()
         d = torch.rsqrt(ops.linear_act(s * s, wsq, None, wscale=1.0, bias_scale=1.0) + self.eps)
-        xs = ops.Modulate.apply(_as_act(x), s)
         if self.up > 1:
             plan = plans.conv_transpose_up2(self.kernel_size, x.shape[2], x.shape[3])
         else:
             plan = plans.conv(self.kernel_size, 1, x.shape[2], x.shape[3])
-        return ops.conv_act(xs, w, self.bias, d, None, wscale=c, plan=plan, slope=slope, gain=gain,
-                            bias_scale=float(self.lr_mul), out_dtype=out_dtype, out_nchw=out_nchw)
+        return ops.ModConvAct.apply(_as_act(x), s.contiguous(), w, self.bias, d.contiguous(), c, plan, slope, gain,
+                                    float(self.lr_mul), out_dtype or ops.act_dtype(), out_nchw)
 
 
 class SynthesisLayer(nn.Module):

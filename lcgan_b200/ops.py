@@ -250,7 +250,7 @@ def set_wgrad_tensor_cores(flag: bool):
 
 def _wgrad_tc_ok(d):
     # the wgrad kernel additionally needs G dense channels-last bf16 with Cout % 64 == 0
-    return (_USE_WGRAD_TC and d.y_dtype == BF16 and d.Cout % 64 == 0 and d.ys_c == 1
+    return (_USE_WGRAD_TC and d.y_dtype == BF16 and d.Cout % 32 == 0 and d.ys_c == 1
             and (d.OW == 1 or d.ys_w == d.Cout) and (d.OH == 1 or d.ys_h == d.OW * d.Cout)
             and (d.N == 1 or d.ys_n == d.OH * d.OW * d.Cout))
 
@@ -558,6 +558,77 @@ class Modulate(torch.autograd.Function):
         _lib.call("lcgan_modulate_bwd", _ptr(x), _ptr(t), _ptr(s), _ptr(dx), _ptr(ds), _dt(x), n, h * w, c,
                   _stream(x), nbytes=3 * x.numel() * x.element_size())
         return dx, ds
+
+
+def _act_bwd_raw(dy, y, d, slope, gain, want_r0, want_r1):
+    n, c, h, w = y.shape
+    gout = torch.empty_like(y)
+    r0 = torch.zeros((n, c), dtype=torch.float32, device=y.device) if want_r0 else None
+    r1 = torch.zeros((n, c), dtype=torch.float32, device=y.device) if want_r1 else None
+    _lib.call("lcgan_act_bwd", _ptr(dy), _ptr(y), _ptr(gout), _ptr(d), _ptr(r0), _ptr(r1), _dt(y),
+              n, h * w, c, C.c_float(slope), C.c_float(gain), _stream(y), nbytes=3 * y.numel() * y.element_size())
+    return gout, r0, r1
+
+
+def _modulate_raw(x, s):
+    n, c, h, w = x.shape
+    xs = torch.empty_like(x)
+    _lib.call("lcgan_modulate", _ptr(x), _ptr(s), _ptr(xs), _dt(x), n, h * w, c, _stream(x),
+              nbytes=2 * x.numel() * x.element_size())
+    return xs
+
+
+class ModConvAct(torch.autograd.Function):
+    """Modulated convolution of the generator in one autograd node (custom_layers.py:60-86 + the
+    leaky-relu that follows):  y = lrelu(d[b,o] * conv(x * s[b,c], w*c) + bias, slope) * gain.
+    The modulated activations x*s are a temporary: they are NOT saved for backward but recomputed
+    there (one elementwise pass) - at 1024x1024 they would be 40 % of the generator's saved bytes.
+    First order only (the generator is never on the R1 path)."""
+
+    @staticmethod
+    def forward(ctx, x, s, w, bias, d, wscale, plan, slope, gain, bias_scale, out_dtype, out_nchw):
+        _need_cuda(x, s, w)
+        assert _is_cl(x) and s.is_contiguous() and d.is_contiguous() and s.dtype == d.dtype == torch.float32
+        compute = torch.float32 if x.dtype == torch.float32 else torch.bfloat16
+        xs = _modulate_raw(x, s)
+        w2 = pack_weight(w, False, compute)
+        y = _alloc_out(x.shape[0], w2.shape[0], plan.OH, plan.OW, out_dtype, x.device, out_nchw)
+        tapconv(xs, w2, y, plan, d, bias, None, slope, gain, bias_scale, wscale)
+        del xs
+        ctx.save_for_backward(x, s, w, bias, d, y)
+        ctx.cfg = (wscale, plan, slope, gain, bias_scale)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, s, w, bias, d, y = ctx.saved_tensors
+        wscale, plan, slope, gain, bias_scale = ctx.cfg
+        need_x, need_s, need_w, need_b, need_d = ctx.needs_input_grad[:5]
+        compute = torch.float32 if x.dtype == torch.float32 else torch.bfloat16
+        ycl = y if _is_cl(y) else _cl(y)
+        g, r0, r1 = _act_bwd_raw(_cl(dy, ycl.dtype), ycl, d, slope, gain, need_b or need_d, need_d)
+        # (g stays fp32 for the fp32-output layers - flow field, RGB - the thin kernels mix dtypes)
+        dx = ds = dw = db = dd = None
+        if need_x or need_s:
+            t = empty_cl(x.shape[0], x.shape[1], x.shape[2], x.shape[3], x.dtype, x.device)
+            tapconv(g, pack_weight(w, True, compute), t, plans.adjoint(plan), acc_scale=wscale)
+            dx = torch.empty_like(x)
+            ds = torch.zeros_like(s)
+            n, c, h, wd = x.shape
+            _lib.call("lcgan_modulate_bwd", _ptr(x), _ptr(t), _ptr(s), _ptr(dx), _ptr(ds), _dt(x), n, h * wd, c,
+                      _stream(x), nbytes=3 * x.numel() * x.element_size())
+            del t
+        if need_w and _wgrad_enabled():
+            xs = _modulate_raw(x, s)
+            dw2 = tapconv_wgrad(xs, g, plan, x.shape[1], w.shape[0], scale=wscale)
+            dw = unpack_wgrad(dw2, tuple(w.shape), False).contiguous()
+            del xs
+        if need_b:
+            db = r0.sum(0) * bias_scale
+        if need_d:
+            dd = (r1 - (bias * bias_scale)[None] * r0) / d
+        return dx, ds, dw, db, dd, None, None, None, None, None, None, None
 
 
 class Warp(torch.autograd.Function):
