@@ -23,7 +23,7 @@ namespace {
 
 constexpr int kStages = 3;                     // weight-gradient kernel: 3 x 64 KiB
 constexpr int kFwdStages = 4;                  // forward kernel: 4 x 32 KiB
-constexpr int kAccStages = 2;                  // TMEM accumulator double buffer (2 x 128 columns)
+constexpr int kAccStages = 4;                  // TMEM accumulator ring (4 x 128 columns = all 512)
 constexpr int kTileM = 128;                    // lattice points (fwd) / pixels per k-block (wgrad)
 constexpr int kBlockK = 64;                    // max channels per k-block (one 128-byte swizzle row); 32 -> 64-byte rows
 constexpr int kMaxBN = 128;
@@ -40,7 +40,7 @@ struct TcParams {
   int BN, n_tiles, total_tiles;
   int rowshare;                                 // 3x3 stride-1: one tall A tile per dx serves the 3 dy taps
   int grp_wtap[3][3];                           // [dx+1][dy+1] -> weight tap index
-  int stages, a_bytes, b_bytes;
+  int stages, a_bytes, b_bytes, wres_bytes;     // rowshare == 2: all 9 taps' weights stay resident in smem
   long long ys_n, ys_h, ys_w;
   int y_f32;
   float acc_scale, bias_scale, slope, gain;
@@ -165,14 +165,17 @@ struct Smem {
   uint64_t* empty;
   uint64_t* done;         // [kAccStages] accumulator-full barriers (wgrad uses done[0] only)
   uint64_t* acc_empty;    // [kAccStages]
+  uint64_t* wfull;        // resident-weight region filled
+  uint8_t* wres;          // resident weights (small-channel mode), 1024-byte aligned
   uint32_t* tmem_slot;
   __device__ __forceinline__ uint8_t* a(int st) const { return base + (size_t)st * stage_bytes; }
   __device__ __forceinline__ uint8_t* b(int st) const { return base + (size_t)st * stage_bytes + a_bytes; }
 };
 
-__device__ __forceinline__ Smem carve(uint8_t* raw, int stages, int a_bytes, int b_bytes) {
+__device__ __forceinline__ Smem carve(uint8_t* raw, int stages, int a_bytes, int b_bytes, int wres_bytes = 0) {
   Smem s;
-  s.base = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+  s.wres = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+  s.base = s.wres + wres_bytes;
   s.stage_bytes = a_bytes + b_bytes;
   s.a_bytes = a_bytes;
   uint8_t* tail = s.base + (size_t)stages * s.stage_bytes;
@@ -180,7 +183,8 @@ __device__ __forceinline__ Smem carve(uint8_t* raw, int stages, int a_bytes, int
   s.empty = s.full + stages;
   s.done = s.empty + stages;
   s.acc_empty = s.done + kAccStages;
-  s.tmem_slot = (uint32_t*)(s.acc_empty + kAccStages);
+  s.wfull = s.acc_empty + kAccStages;
+  s.tmem_slot = (uint32_t*)(s.wfull + 1);
   return s;
 }
 
@@ -196,13 +200,14 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
   //   warp 1   MMA issuer, accumulates tile i into TMEM stage i%2
   //   warps2-5 epilogue of tile i overlaps the MMAs of tile i+1 (TMEM double buffer)
   extern __shared__ uint8_t smem_raw[];
-  const Smem s = carve(smem_raw, p.stages, p.a_bytes, p.b_bytes);
+  const Smem s = carve(smem_raw, p.stages, p.a_bytes, p.b_bytes, p.wres_bytes);
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmx);
     tma_prefetch_desc(&tmw);
     for (int i = 0; i < p.stages; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    mbar_init(s.wfull, 1);
     for (int i = 0; i < kAccStages; ++i) { mbar_init(&s.done[i], 1); mbar_init(&s.acc_empty[i], 4); }
     fence_barrier_init();
   }
@@ -218,6 +223,30 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
     if (lane == 0) {
       const uint32_t tx_bytes = p.rowshare ? (uint32_t)p.a_bytes + 3 * wtile : (kTileM + p.BN) * p.kc * 2;
       int g = 0;                                            // k-block counter across tiles
+      if (p.rowshare == 2) {
+        // small-channel mode: the 9 taps' weights are loaded once and stay in smem; one stage = the
+        // three tall (dx = -1,0,+1) A tiles of a whole output tile -> 3*kpt TMA issues per tile
+        const uint32_t a_tile = (uint32_t)(p.ht + 2) * 16 * p.kc * 2;
+        mbar_expect_tx(s.wfull, 9 * p.kpt * wtile);
+        for (int j = 0; j < 3; ++j)
+          for (int dyi = 0; dyi < 3; ++dyi)
+            for (int cb = 0; cb < p.kpt; ++cb)
+              tma_load_2d(s.wres + ((j * 3 + dyi) * p.kpt + cb) * wtile, &tmw, s.wfull,
+                          p.grp_wtap[j][dyi] * p.Cin + cb * p.kc, 0);
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++g) {
+          int t = tile;
+          const int tw = t % p.tiles_w; t /= p.tiles_w;
+          const int th = t % p.tiles_h;
+          const int tb = t / p.tiles_h;
+          const int st = g % p.stages, ph = (g / p.stages) & 1;
+          mbar_wait(&s.empty[st], ph ^ 1);
+          mbar_expect_tx(&s.full[st], 3 * p.kpt * a_tile);
+          for (int j = 0; j < 3; ++j)
+            for (int cb = 0; cb < p.kpt; ++cb)
+              tma_load_4d(s.a(st) + (j * p.kpt + cb) * a_tile, &tmx, &s.full[st], cb * p.kc, tw * p.wt + j - 1,
+                          th * p.ht - 1, tb * p.nt);
+        }
+      } else
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int nt_i = tile % p.n_tiles;
         int t = tile / p.n_tiles;
@@ -247,6 +276,47 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
     if (lane == 0) {
       const uint32_t idesc = make_idesc(p.BN, false, false);
       int g = 0, li = 0;
+      if (p.rowshare == 2) {
+        const uint32_t a_tile = (uint32_t)(p.ht + 2) * 16 * p.kc * 2;
+        mbar_wait(s.wfull, 0);
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li, ++g) {
+          const int as = li % kAccStages, aph = (li / kAccStages) & 1;
+          mbar_wait(&s.acc_empty[as], aph ^ 1);
+          const int st = g % p.stages, ph = (g / p.stages) & 1;
+          mbar_wait(&s.full[st], ph);
+          tc_fence_after();
+          const uint32_t tacc = tmem_base + (uint32_t)(as * kMaxBN);
+          // descriptors differ only in the 14-bit start-address field (16-byte units): one make_desc
+          // per tile, then integer offsets - the issue loop must stay far below the 16..64 cycles an
+          // N = 32..128 MMA takes
+          const uint64_t ad0 = make_desc(smem_u32(s.a(st)), 16, 16 * p.kc, p.kc);
+          const uint64_t bd0 = make_desc(smem_u32(s.wres), 16, 16 * p.kc, p.kc);
+          const uint32_t a_tl = a_tile >> 4, a_dy = (uint32_t)(16 * p.kc * 2) >> 4, w_tl = wtile >> 4;
+          uint32_t first = 0;
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+            for (int cb = 0; cb < p.kpt; ++cb) {
+              const uint64_t aj = ad0 + (uint32_t)((j * p.kpt + cb) * a_tl);
+#pragma unroll
+              for (int dyi = 0; dyi < 3; ++dyi) {
+                const uint64_t ad = aj + (uint32_t)(dyi * a_dy);
+                const uint64_t bd = bd0 + (uint32_t)(((j * 3 + dyi) * p.kpt + cb) * w_tl);
+                if (p.kc == 32) {
+                  umma_f16(tacc, ad, bd, idesc, first);
+                  umma_f16(tacc, ad + 2, bd + 2, idesc, 1);
+                } else {
+                  umma_f16(tacc, ad, bd, idesc, first);
+                  umma_f16(tacc, ad + 2, bd + 2, idesc, 1);
+                  umma_f16(tacc, ad + 4, bd + 4, idesc, 1);
+                  umma_f16(tacc, ad + 6, bd + 6, idesc, 1);
+                }
+                first = 1;
+              }
+            }
+          umma_commit(&s.empty[st]);
+          umma_commit(&s.done[as]);
+        }
+      } else
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li) {
         const int as = li % kAccStages, aph = (li / kAccStages) & 1;
         mbar_wait(&s.acc_empty[as], aph ^ 1);               // epilogue has drained this TMEM stage
@@ -464,6 +534,116 @@ tapconv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmg, const __grid_co
 }
 
 // ---------------------------------------------------------------------------------------------
+// weight-gradient kernel for small channel counts ("taps along N"): one CTA accumulates ALL taps
+//   D[128 out-ch x (ntaps*Cin)] += G[128 px x 128 ch]^T * [X_tap0 | X_tap1 | ...][128 px x ntaps*Cin]
+// The tap tiles sit side by side in shared memory, one TMA box each, so a single MN-major B
+// descriptor (LBO = box bytes) spans them: each 16-pixel K step is 1-2 wide MMAs (N <= 256) instead
+// of ntaps narrow ones, and the G tile is read once per step instead of once per tap.
+// Needs ntaps*Cin <= 288 (TMEM columns, 2 smem stages): the 32-channel 3x3 layers and the 64->x
+// transposed-conv phases of the 512/1024 models.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTnStages = 2;
+constexpr int kTnMaxN = 288;
+constexpr int kTnXBytes = kTileM * kTnMaxN * 2;   // 72 KiB
+
+__global__ void __launch_bounds__(kThreads, 1)
+tapconv_wgrad_tn_kernel(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUtensorMap tmx,
+                        const WgParams p, float* __restrict__ dw) {
+  extern __shared__ uint8_t smem_raw[];
+  const Smem s = carve(smem_raw, kTnStages, kWgABytes, kTnXBytes);
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int o0 = blockIdx.x * 128;
+  const int t_begin = blockIdx.y * p.tiles_per_split;
+  const int t_end = min(p.tiles_total, t_begin + p.tiles_per_split);
+  const int nkb = t_end - t_begin;
+  const int ntot = p.ntaps * p.Cin;                 // accumulator columns
+  const int bpt = p.Cin / p.kcx;                    // X boxes per tap
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmg);
+    tma_prefetch_desc(&tmx);
+    for (int i = 0; i < kTnStages; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    mbar_init(&s.done[0], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(s.tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s.tmem_slot;
+  const int nbg = 128 / p.kcg;
+  const uint32_t gbox = kTileM * p.kcg * 2, xbox = kTileM * p.kcx * 2;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t tx_bytes = kWgABytes + p.ntaps * bpt * xbox;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int st = kb % kTnStages, ph = (kb / kTnStages) & 1;
+        mbar_wait(&s.empty[st], ph ^ 1);
+        int t = t_begin + kb;
+        const int tw = t % p.tiles_w; t /= p.tiles_w;
+        const int th = t % p.tiles_h;
+        const int tb = t / p.tiles_h;
+        const int n0 = tw * p.wt, m0 = th * p.ht, b0 = tb * p.nt;
+        mbar_expect_tx(&s.full[st], tx_bytes);
+        for (int j = 0; j < nbg; ++j)
+          tma_load_4d(s.a(st) + j * gbox, &tmg, &s.full[st], o0 + p.kcg * j, n0 * p.os + p.px, m0 * p.os + p.py, b0);
+        for (int tap = 0; tap < p.ntaps; ++tap)
+          for (int j = 0; j < bpt; ++j)
+            tma_load_4d(s.b(st) + (tap * bpt + j) * xbox, &tmx, &s.full[st], p.kcx * j, n0 * p.is + p.dx[tap],
+                        m0 * p.is + p.dy[tap], b0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int st = kb % kTnStages, ph = (kb / kTnStages) & 1;
+        mbar_wait(&s.full[st], ph);
+        tc_fence_after();
+        const uint64_t ad = make_desc(smem_u32(s.a(st)), gbox, 16 * p.kcg, p.kcg);
+        for (int n0c = 0; n0c < ntot; n0c += 256) {          // N chunks of whole boxes, <= 256 columns
+          const int nn = min(256, ntot - n0c);
+          const uint32_t idesc = make_idesc(nn, true, true);
+          const uint64_t bd = make_desc(smem_u32(s.b(st)) + (n0c / p.kcx) * xbox, xbox, 16 * p.kcx, p.kcx);
+#pragma unroll
+          for (int k = 0; k < kTileM / 16; ++k)
+            umma_f16(tmem_base + (uint32_t)n0c, ad + (uint64_t)(k * 2 * p.kcg), bd + (uint64_t)(k * 2 * p.kcx), idesc,
+                     (kb | k) != 0);
+        }
+        umma_commit(&s.empty[st]);
+      }
+      umma_commit(&s.done[0]);
+    }
+  } else {
+    const int q = warp % 4;
+    const int o = o0 + q * 32 + lane;
+    mbar_wait(&s.done[0], 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int c = 0; c < ntot; c += 16) {
+      uint32_t v[16];
+      tmem_ld16(trow + c, v);
+      tmem_ld_wait();
+      if (o < p.Cout && nkb > 0) {
+        const int tap = c / p.Cin, ci = c - tap * p.Cin;      // 16 | Cin, so a 16-column group stays in one tap
+        float* row = dw + (long long)o * p.w_ld + (long long)p.wtap[tap] * p.Cin + ci;
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+          atomicAdd(reinterpret_cast<float4*>(row + i),
+                    make_float4(__uint_as_float(v[i]) * p.scale, __uint_as_float(v[i + 1]) * p.scale,
+                                __uint_as_float(v[i + 2]) * p.scale, __uint_as_float(v[i + 3]) * p.scale));
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -546,6 +726,7 @@ int sm_count() {
   return n;
 }
 int wg_smem_bytes() { return kStages * (kWgABytes + kWgBBytes) + 1024 + 256; }
+int tn_smem_bytes() { return kTnStages * (kWgABytes + kTnXBytes) + 1024 + 256; }
 
 }  // namespace
 
@@ -597,11 +778,25 @@ extern "C" int lcgan_tapconv_tc(const lcgan_tapconv* d, const void* x, const voi
     }
     p.rowshare = (seen == 0x1FF) && getenv("LCGAN_NO_ROWSHARE") == nullptr;
   }
-  if (p.rowshare) {
+  p.wres_bytes = 0;
+  const int budget = 3 * (20 * 1024 + 3 * kBBytes);        // bytes available for the operand ring
+  if (p.rowshare && d->Cout <= kMaxBN && 9 * p.BN * d->Cin * 2 <= 80 * 1024 && getenv("LCGAN_NO_RESIDENT") == nullptr) {
+    // small-channel layers: resident weights, one stage per output tile
+    p.rowshare = 2;
+    p.wres_bytes = 9 * p.BN * d->Cin * 2;
+    p.a_bytes = 3 * p.kpt * (p.ht + 2) * 16 * p.kc * 2;
+    p.b_bytes = 0;
+    p.stages = (budget - p.wres_bytes) / p.a_bytes;
+    if (p.stages > 8) p.stages = 8;
+    if (p.stages < 2) { p.rowshare = 1; p.wres_bytes = 0; }
+  }
+  if (p.rowshare == 1 && p.kc == 64 && getenv("LCGAN_ROWSHARE_WIDE") == nullptr) p.rowshare = 0;   // measured slower on 64-ch k-blocks
+  if (p.rowshare == 2) {
+  } else if (p.rowshare) {
     p.a_bytes = (p.ht + 2) * 16 * p.kc * 2;                 // 20 KiB (kc=64) / 10 KiB (kc=32)
     p.b_bytes = 3 * p.BN * p.kc * 2;
     p.stages = 3;
-    if ((p.a_bytes + p.b_bytes) * 6 <= 3 * (20 * 1024 + 3 * kBBytes)) p.stages = 6;
+    if ((p.a_bytes + p.b_bytes) * 6 <= budget) p.stages = 6;
   } else {
     p.a_bytes = kABytes; p.b_bytes = kBBytes; p.stages = kFwdStages;
   }
@@ -653,6 +848,29 @@ extern "C" int lcgan_tapconv_wgrad_tc(const lcgan_tapconv* d, const void* x, con
   p.tiles_per_split = (p.tiles_total + splits - 1) / splits;
   splits = (p.tiles_total + p.tiles_per_split - 1) / p.tiles_per_split;
   p.w_ld = d->w_ld; p.scale = scale;
+
+  if (d->ntaps * d->Cin <= kTnMaxN && d->Cin % 16 == 0 && getenv("LCGAN_NO_WGRAD_TN") == nullptr) {
+    // small-channel layers: all taps along N, persistent-ish K split (one CTA per SM)
+    int tsplits = sm_count() / otiles;
+    if (tsplits > p.tiles_total) tsplits = p.tiles_total;
+    if (tsplits < 1) tsplits = 1;
+    p.tiles_per_split = (p.tiles_total + tsplits - 1) / tsplits;
+    tsplits = (p.tiles_total + p.tiles_per_split - 1) / p.tiles_per_split;
+    CUtensorMap tmg2, tmx2;
+    if (int e = make_act_map(&tmg2, g, d->N, d->OH, d->OW, d->Cout, p.wt, p.ht, p.nt, d->os, p.kcg)) return e;
+    if (int e = make_act_map(&tmx2, x, d->N, d->IH, d->IW, d->Cin, p.wt, p.ht, p.nt, d->is, p.kcx)) return e;
+    static std::once_flag once2;
+    static cudaError_t attr_err2 = cudaSuccess;
+    std::call_once(once2, [] {
+      attr_err2 = cudaFuncSetAttribute(tapconv_wgrad_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tn_smem_bytes());
+    });
+    LCGAN_CHECK(attr_err2 == cudaSuccess, "tapconv_wgrad_tn: cannot raise dynamic shared memory: %s",
+                cudaGetErrorString(attr_err2));
+    dim3 grid2(otiles, tsplits);
+    tapconv_wgrad_tn_kernel<<<grid2, kThreads, tn_smem_bytes(), (cudaStream_t)stream>>>(tmg2, tmx2, p, dw2);
+    LCGAN_LAUNCH_CHECK();
+    return 0;
+  }
 
   CUtensorMap tmg, tmx;
   if (int e = make_act_map(&tmg, g, d->N, d->OH, d->OW, d->Cout, p.wt, p.ht, p.nt, d->os, p.kcg)) return e;

@@ -1,0 +1,41 @@
+"""Micro-benchmark of individual launches at real 1024^2 shapes (CUDA events, L2 flushed by size)."""
+import sys, torch
+sys.path.insert(0, '.')
+from lcgan_b200 import ops, plans, _lib
+ops.set_precision("bf16")
+dev = 'cuda'
+def cl(x): return x.contiguous(memory_format=torch.channels_last)
+def timeit(fn, n=5):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+which = sys.argv[1:] or ["fwd32", "wg32", "fwd64", "wg64", "fwd128", "box", "actbwd", "warpf", "warpb"]
+N = 32
+for w in which:
+    if w.startswith("fwd") or w.startswith("wg"):
+        C = int(w[3:] if w.startswith("fwd") else w[2:]); R = {32: 1024, 64: 512, 128: 256, 256: 128}[C]
+        x = cl(torch.randn(N, C, R, R, device=dev).bfloat16()); g = cl(torch.randn(N, C, R, R, device=dev).bfloat16())
+        w2 = torch.randn(C, 9 * C, device=dev).bfloat16(); plan = plans.conv(3, 1, R, R)
+        y = ops.empty_cl(N, C, R, R, torch.bfloat16, dev); bias = torch.randn(C, device=dev)
+        flops = 2.0 * N * R * R * 9 * C * C; nbytes = 2 * x.numel() * 2
+        if w.startswith("fwd"):
+            ms = timeit(lambda: ops.tapconv(x, w2, y, plan, None, bias, None, slope=0.2, gain=1.4))
+        else:
+            ms = timeit(lambda: ops.tapconv_wgrad(x, g, plan, C, C))
+        print(f"{w:8s} {ms:8.3f} ms  {flops/ms/1e9:8.1f} TF/s  {nbytes/ms/1e6:8.0f} GB/s (algorithmic)")
+    else:
+        C, R = 32, 1024
+        x = cl(torch.randn(N, C, R, R, device=dev).bfloat16()); g = cl(torch.randn(N, C, R, R, device=dev).bfloat16())
+        nb = x.numel() * 2
+        if w == "box": ms = timeit(lambda: ops.Box3.apply(x)); tr = 2 * nb
+        elif w == "actbwd": ms = timeit(lambda: ops._act_bwd_raw(g, x, None, 0.2, 1.4, True, False)); tr = 3 * nb
+        elif w == "warpf":
+            flow = cl(torch.randn(N, 2, R, R, device=dev)); ms = timeit(lambda: ops.Warp.apply(x, flow, 0.1)); tr = 2 * nb
+        elif w == "warpb":
+            flow = cl(torch.randn(N, 2, R, R, device=dev)); xr = x.clone().requires_grad_(); fr = flow.clone().requires_grad_()
+            out = ops.Warp.apply(xr, fr, 0.1)
+            ms = timeit(lambda: torch.autograd.grad(out, (xr, fr), g, retain_graph=True)); tr = 4 * nb
+        print(f"{w:8s} {ms:8.3f} ms  {tr/ms/1e6:8.0f} GB/s (algorithmic)")
