@@ -158,14 +158,28 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": v, "unit": "img/s", "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def _emit(line):
+    """Print the one JSON line on the process's real stdout (libraries such as NCCL write their own
+    banners to fd 1; everything else is routed to stderr)."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -182,7 +196,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     if rank == 0:
         _lib.build()          # quiet: stdout carries exactly one JSON line
     if world > 1:
@@ -195,14 +210,16 @@ def main():
     hp = Hyper(lr=1e-3 if res == 1024 else 2e-3)             # README.md:29/45/49
     torch.manual_seed(0)
     G, D = cnn.Generator(cfg.namespace()).to(dev), cnn.Discriminator(cfg.namespace()).to(dev)
-    if world > 1:
+    use_graphs = not args.no_graphs
+    if world > 1 and not use_graphs:
         from torch.nn.parallel import DistributedDataParallel as DDP     # worker.py:88-96
         G = DDP(G, device_ids=[local_rank], broadcast_buffers=False, find_unused_parameters=True)
         D = DDP(D, device_ids=[local_rank], broadcast_buffers=False, find_unused_parameters=True)
     fl = {256: 3, 512: 4, 1024: 5}.get(res, 3)
-    use_graphs = world == 1 and not args.no_graphs
     kw = dict(freeze_d_start=0 if args.freeze_d else 10 ** 9, freeze_d_layer=fl)
-    tr = T.GraphedTrainer(G, D, hp, b, dev, **kw) if use_graphs else T.Trainer(G, D, hp, **kw)
+    # graphs: data parallel with the gradient all-reduce captured in the graphs; eager: torch DDP as
+    # the reference wraps it
+    tr = T.GraphedTrainer(G, D, hp, b, dev, world=world, **kw) if use_graphs else T.Trainer(G, D, hp, **kw)
 
     gcpu = torch.Generator().manual_seed(1000 + rank)
     n_pool = 2
@@ -253,9 +270,9 @@ def main():
 
     def step_eager_for_profile(it):
         z, zd = latents()
-        T.Trainer.g_step(tr, it, z)
+        tr.g_step(it, z)
         tr.ema.update(it)
-        T.Trainer.d_step(tr, it, zd, resident[it % n_pool])
+        tr.d_step(it, zd, resident[it % n_pool])
 
     graph_launches = [0]
     if use_graphs:
@@ -308,7 +325,8 @@ def main():
         tr.graphs.clear()
         gc.collect()
         torch.cuda.empty_cache()
-    if not args.no_roofline and rank == 0:
+    if not args.no_roofline:
+        # every rank runs the instrumented cycle (the steps contain DDP collectives); rank 0 reports
         roof, kernels = roofline_pass(step_eager_for_profile, it0, _lib, peaks())
     if world > 1:
         dist.barrier()
@@ -339,7 +357,7 @@ def main():
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
             "kernels": kernels,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 

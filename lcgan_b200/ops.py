@@ -158,6 +158,8 @@ def unpack_wgrad(dw2: torch.Tensor, wshape, transposed: bool) -> torch.Tensor:
         o, i = wshape
         return dw2.t() if transposed else dw2
     o, i, kh, kw = wshape
+    if kh == 1 and kw == 1:      # keep plain contiguous strides (DDP's bucket views expect them)
+        return (dw2.t().contiguous() if transposed else dw2).reshape(wshape)
     if transposed:
         return dw2.view(i, kh, kw, o).permute(3, 0, 1, 2)
     return dw2.view(o, kh, kw, i).permute(0, 3, 1, 2)

@@ -125,8 +125,17 @@ class GraphedTrainer(Trainer):
 
     VARIANTS = ("g_even", "g_odd", "d_even", "d_odd", "d_r1")
 
-    def __init__(self, G, D, hp, batch, device, **kw):
+    def __init__(self, G, D, hp, batch, device, world=1, **kw):
         super().__init__(G, D, hp, **kw)
+        self.world = world
+        if world > 1:
+            # data parallel without the DDP wrapper: rank 0's initial weights are broadcast (what DDP's
+            # constructor does, worker.py:88-96) and the gradient all-reduce is issued explicitly after
+            # backward, so it is captured into the graphs together with the kernels
+            import torch.distributed as dist
+            for t in list(G.parameters()) + list(G.buffers()) + list(D.parameters()) + list(D.buffers()):
+                dist.broadcast(t.data, 0)
+            self.G_ema.load_state_dict(_bare(G).state_dict())
         for opt in (self.g_opt, self.d_opt):          # Adam state on device so step() is capturable
             for grp in opt.param_groups:
                 grp["capturable"] = True
@@ -145,6 +154,51 @@ class GraphedTrainer(Trainer):
         if which == "g":
             return "g_even" if it % 2 == 0 else "g_odd"
         return "d_even" if it % 2 == 0 else ("d_r1" if it % 8 == 1 else "d_odd")
+
+    def _allreduce_mean(self, params):
+        """Bucketed gradient all-reduce (mean) over NCCL - the one exchange step of the path."""
+        import torch.distributed as dist
+        grads = [p.grad for p in params if p.grad is not None]
+        bucket, size, cap = [], 0, 64 << 20
+        def flush():
+            if not bucket:
+                return
+            flat = torch.cat([g.reshape(-1) for g in bucket])
+            dist.all_reduce(flat)
+            flat.div_(self.world)
+            off = 0
+            for g in bucket:
+                g.copy_(flat[off:off + g.numel()].view_as(g))
+                off += g.numel()
+        for g in grads:
+            bucket.append(g); size += g.numel() * 4
+            if size >= cap:
+                flush(); bucket, size = [], 0
+        flush()
+
+    def g_step(self, it, z):
+        if self.world == 1:
+            return super().g_step(it, z)
+        requires_grad(self.G, True); requires_grad(self.D, False)
+        self.g_opt.zero_grad()
+        loss = generator_loss(self.G, self.D, self.hp, it, z)
+        loss.backward()
+        self._allreduce_mean(list(self.G.parameters()))
+        self.g_opt.step()
+        return loss
+
+    def d_step(self, it, z, data):
+        if self.world == 1:
+            return super().d_step(it, z, data)
+        requires_grad(self.G, False); requires_grad(self.D, True)
+        if it >= self.freeze_d_start:
+            freeze_discriminator(self.D, self.freeze_d_layer)
+        self.d_opt.zero_grad()
+        loss = discriminator_loss(self.G, self.D, self.hp, it, z, data)
+        loss.backward()
+        self._allreduce_mean(list(self.D.parameters()))
+        self.d_opt.step()
+        return loss
 
     def _run(self, name):
         it = {"g_even": 0, "g_odd": 3, "d_even": 0, "d_odd": 3, "d_r1": 1}[name]
