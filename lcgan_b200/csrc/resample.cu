@@ -94,39 +94,43 @@ box3_strip_kernel(const T* __restrict__ a, const T* __restrict__ mask, T* __rest
     const int y0 = (int)(p % HS) * R;
     const int b = (int)(p / HS);
     const int64_t img = (int64_t)b * H * W * C;
-    float h0[V], h1[V], h2[V];     // horizontal sums of rows y-1, y, y+1
-    auto hsum = [&](int yy, float* h) {
+    // all (R+2)*3 vector loads are issued before any is consumed (memory-level parallelism), then the
+    // horizontal 3-sums h[r] of rows y0-1 .. y0+R are combined vertically
+    float h[R + 2][V];
 #pragma unroll
-      for (int i = 0; i < V; ++i) h[i] = 0.f;
-      if (yy < 0 || yy >= H) return;
+    for (int r = 0; r < R + 2; ++r) {
+      const int yy = y0 - 1 + r;
+      const bool oky = yy >= 0 && yy < H;
+      const int yc = min(max(yy, 0), H - 1);
+      float f[3][V];
 #pragma unroll
       for (int dx = -1; dx <= 1; ++dx) {
         const int xx = x + dx;
-        if (xx < 0 || xx >= W) continue;
-        const int64_t off = img + ((int64_t)yy * W + xx) * C + c;
-        float f[V];
-        ldv<T, V>(a + off, f);
+        const bool ok = oky && xx >= 0 && xx < W;
+        const int xc = min(max(xx, 0), W - 1);
+        const int64_t off = img + ((int64_t)yc * W + xc) * C + c;
+        ldv<T, V>(a + off, f[dx + 1]);
         if (mask) {
           float m[V];
           ldv<T, V>(mask + off, m);
 #pragma unroll
-          for (int i = 0; i < V; ++i) f[i] *= (m[i] > 0.f ? pre_gain : pre_gain * pre_slope);
+          for (int i = 0; i < V; ++i) f[dx + 1][i] *= (m[i] > 0.f ? pre_gain : pre_gain * pre_slope);
         }
+        if (!ok) {
 #pragma unroll
-        for (int i = 0; i < V; ++i) h[i] += f[i];
+          for (int i = 0; i < V; ++i) f[dx + 1][i] = 0.f;
+        }
       }
-    };
-    hsum(y0 - 1, h0);
-    hsum(y0, h1);
+#pragma unroll
+      for (int i = 0; i < V; ++i) h[r][i] = f[0][i] + f[1][i] + f[2][i];
+    }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      hsum(y0 + r + 1, h2);
       float o[V];
 #pragma unroll
       for (int i = 0; i < V; ++i) {
-        const float v = (h0[i] + h1[i] + h2[i]) * (1.f / 9.f);
+        const float v = (h[r][i] + h[r + 1][i] + h[r + 2][i]) * (1.f / 9.f);
         o[i] = (v > 0.f ? v : v * post_slope) * post_gain;
-        h0[i] = h1[i]; h1[i] = h2[i];
       }
       stv<T, V>(out + img + ((int64_t)(y0 + r) * W + x) * C + c, o);
     }

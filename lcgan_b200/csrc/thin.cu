@@ -98,10 +98,12 @@ thin_out_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const void* __r
 // ------------------------------------------------------------------------------------------
 // thin-in: one thread = one output channel vector of one lattice point
 // ------------------------------------------------------------------------------------------
-template <typename TX, typename TY, int V>
+template <typename TX, typename TY, int V, int VPT>
 __global__ void __launch_bounds__(kThreads)
 thin_in_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const void* __restrict__ w, TY* __restrict__ y,
                const float* __restrict__ rowscale, const float* __restrict__ bias, const TY* __restrict__ residual) {
+  // one thread = VPT consecutive output channel vectors of one lattice point (index math and the
+  // <= 36 input scalars are amortised over VPT*V outputs; a warp stores a contiguous run)
   __shared__ __align__(16) float ws[kSmemFloats];          // [t][c][o]
   const int tc = d.ntaps * d.Cin;
   for (int i = threadIdx.x; i < d.Cout * tc; i += kThreads) {
@@ -109,17 +111,19 @@ thin_in_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const void* __re
     ws[i] = ldw(w, d.w_dtype, (int64_t)o * d.w_ld + (int64_t)d.wtap[t] * d.Cin + c);
   }
   __syncthreads();
-  const int ov = d.Cout / V;
-  const int64_t total = (int64_t)d.N * d.MH * d.MW * ov;
+  const int og = d.Cout / (V * VPT);
+  const int64_t total = (int64_t)d.N * d.MH * d.MW * og;
   for (int64_t idx = blockIdx.x * (int64_t)kThreads + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * kThreads) {
-    const int o0 = (int)(idx % ov) * V;
-    int64_t r = idx / ov;
+    const int o0 = (int)(idx % og) * (V * VPT);
+    int64_t r = idx / og;
     const int n = (int)(r % d.MW); r /= d.MW;
     const int m = (int)(r % d.MH);
     const int b = (int)(r / d.MH);
-    float acc[V];
+    float acc[VPT][V];
 #pragma unroll
-    for (int i = 0; i < V; ++i) acc[i] = 0.f;
+    for (int j = 0; j < VPT; ++j)
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[j][i] = 0.f;
     for (int t = 0; t < d.ntaps; ++t) {
       const int iy = m * d.is + d.dy[t], ix = n * d.is + d.dx[t];
       if (iy < 0 || iy >= d.IH || ix < 0 || ix >= d.IW) continue;
@@ -127,33 +131,40 @@ thin_in_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const void* __re
       for (int c = 0; c < d.Cin; ++c) {
         const float xv = ldf(xp + c * d.xs_c);
         const float* wp = ws + (t * d.Cin + c) * d.Cout + o0;
-        if constexpr (V % 4 == 0) {
 #pragma unroll
-          for (int i = 0; i < V; i += 4) {
-            const float4 w4 = *reinterpret_cast<const float4*>(wp + i);
-            acc[i] = fmaf(xv, w4.x, acc[i]); acc[i + 1] = fmaf(xv, w4.y, acc[i + 1]);
-            acc[i + 2] = fmaf(xv, w4.z, acc[i + 2]); acc[i + 3] = fmaf(xv, w4.w, acc[i + 3]);
+        for (int j = 0; j < VPT; ++j) {
+          if constexpr (V % 4 == 0) {
+#pragma unroll
+            for (int i = 0; i < V; i += 4) {
+              const float4 w4 = *reinterpret_cast<const float4*>(wp + j * V + i);
+              acc[j][i] = fmaf(xv, w4.x, acc[j][i]); acc[j][i + 1] = fmaf(xv, w4.y, acc[j][i + 1]);
+              acc[j][i + 2] = fmaf(xv, w4.z, acc[j][i + 2]); acc[j][i + 3] = fmaf(xv, w4.w, acc[j][i + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < V; ++i) acc[j][i] = fmaf(xv, wp[j * V + i], acc[j][i]);
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < V; ++i) acc[i] = fmaf(xv, wp[i], acc[i]);
         }
       }
     }
     const int64_t base = b * d.ys_n + (int64_t)(m * d.os + d.py) * d.ys_h + (int64_t)(n * d.os + d.px) * d.ys_w;
 #pragma unroll
-    for (int i = 0; i < V; ++i) acc[i] = epilogue(d, acc[i], b, o0 + i, rowscale, bias);
-    if constexpr (V == 1) {
-      if (residual) acc[0] += ldf(residual + base + o0 * d.ys_c);
-      stf(y + base + o0 * d.ys_c, acc[0]);
-    } else {
-      if (residual) {
-        float rr[V];
-        ldv<TY, V>(residual + base + o0, rr);
+    for (int j = 0; j < VPT; ++j) {
+      const int oj = o0 + j * V;
 #pragma unroll
-        for (int i = 0; i < V; ++i) acc[i] += rr[i];
+      for (int i = 0; i < V; ++i) acc[j][i] = epilogue(d, acc[j][i], b, oj + i, rowscale, bias);
+      if constexpr (V == 1) {
+        if (residual) acc[j][0] += ldf(residual + base + oj * d.ys_c);
+        stf(y + base + oj * d.ys_c, acc[j][0]);
+      } else {
+        if (residual) {
+          float rr[V];
+          ldv<TY, V>(residual + base + oj, rr);
+#pragma unroll
+          for (int i = 0; i < V; ++i) acc[j][i] += rr[i];
+        }
+        stv<TY, V>(y + base + oj, acc[j]);
       }
-      stv<TY, V>(y + base + o0, acc);
     }
   }
 }
@@ -387,9 +398,15 @@ int lcgan_thin_forward(const lcgan_tapconv& d, const void* x, const void* w, voi
                       (!residual || (uintptr_t)residual % 16 == 0);
 #define TI(TXT, TYT, VV)                                                                                    \
     do {                                                                                                    \
-      const int grid = grid_cap((rows * (d.Cout / VV) + kThreads - 1) / kThreads, 32);                      \
-      thin_in_kernel<TXT, TYT, VV><<<grid, kThreads, 0, s>>>(d, (const TXT*)x, w, (TYT*)y, rowscale, bias,  \
-                                                             (const TYT*)residual);                         \
+      if (VV > 1 && d.Cout % (VV * 4) == 0) {                                                               \
+        const int grid = grid_cap((rows * (d.Cout / (VV * 4)) + kThreads - 1) / kThreads, 32);              \
+        thin_in_kernel<TXT, TYT, VV, 4><<<grid, kThreads, 0, s>>>(d, (const TXT*)x, w, (TYT*)y, rowscale,   \
+                                                                  bias, (const TYT*)residual);              \
+      } else {                                                                                              \
+        const int grid = grid_cap((rows * (d.Cout / VV) + kThreads - 1) / kThreads, 32);                    \
+        thin_in_kernel<TXT, TYT, VV, 1><<<grid, kThreads, 0, s>>>(d, (const TXT*)x, w, (TYT*)y, rowscale,   \
+                                                                  bias, (const TYT*)residual);              \
+      }                                                                                                     \
     } while (0)
     if (xf && yf) { if (v_ok) TI(float, float, 4); else TI(float, float, 1); }
     else if (xf && !yf) { if (v_ok) TI(float, bf16, 8); else TI(float, bf16, 1); }
