@@ -30,6 +30,7 @@ constexpr int kMaxBN = 128;
 constexpr int kABytes = kTileM * kBlockK * 2;  // 16 KiB
 constexpr int kBBytes = kMaxBN * kBlockK * 2;  // 16 KiB
 constexpr int kThreads = 192;                  // warp0: TMA, warp1: MMA, warps 2-5: epilogue
+constexpr int kFwdThreads = 192;
 
 struct TcParams {
   int N, Cin, Cout;
@@ -66,8 +67,18 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+// Single-thread instructions take a `leader` flag and are predicated INSIDE the asm: the surrounding
+// loop is executed by all 32 lanes with warp-uniform values, so descriptor/coordinate arithmetic
+// stays in the uniform datapath instead of per-operand R2UR moves under a divergent `if (lane == 0)`
+// (measured: ~150 cycles of issue overhead per MMA with the divergent form vs a 45-64 cycle MMA).
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes, uint32_t leader) {
+  asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %2, 0;\n@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n}\n"
+               ::"r"(smem_u32(bar)), "r"(bytes), "r"(leader) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -87,15 +98,18 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                            uint32_t leader) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+      "{\n.reg .pred q;\nsetp.ne.b32 q, %7, 0;\n"
+      "@q cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n}\n"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(leader) : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint32_t leader) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+      "{\n.reg .pred q;\nsetp.ne.b32 q, %5, 0;\n"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n}\n"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(leader) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -112,17 +126,21 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
 }
 
 // D[tmem] (+)= A[smem desc] * B[smem desc]
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                         uint32_t leader) {
   asm volatile(
       "{\n"
-      ".reg .pred p;\n"
+      ".reg .pred p, q;\n"
       "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+      "setp.ne.b32 q, %5, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader) : "memory");
 }
 // arrive on an mbarrier once all previously issued MMAs of this thread have completed
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void umma_commit(uint64_t* bar, uint32_t leader) {
+  asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %1, 0;\n"
+               "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n"
+               ::"r"(smem_u32(bar)), "r"(leader) : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
@@ -191,7 +209,7 @@ __device__ __forceinline__ Smem carve(uint8_t* raw, int stages, int a_bytes, int
 // ---------------------------------------------------------------------------------------------
 // forward-type kernel
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kFwdThreads, 1)
 tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmw, const TcParams p,
                   void* __restrict__ y, const float* __restrict__ rowscale, const float* __restrict__ bias,
                   const void* __restrict__ residual) {
@@ -220,19 +238,20 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
   const uint32_t wtile = (uint32_t)p.BN * p.kc * 2;           // bytes of one tap's weight tile
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
+      const uint32_t leader = elect_one();
       const uint32_t tx_bytes = p.rowshare ? (uint32_t)p.a_bytes + 3 * wtile : (kTileM + p.BN) * p.kc * 2;
       int g = 0;                                            // k-block counter across tiles
       if (p.rowshare == 2) {
         // small-channel mode: the 9 taps' weights are loaded once and stay in smem; one stage = the
         // three tall (dx = -1,0,+1) A tiles of a whole output tile -> 3*kpt TMA issues per tile
         const uint32_t a_tile = (uint32_t)(p.ht + 2) * 16 * p.kc * 2;
-        mbar_expect_tx(s.wfull, 9 * p.kpt * wtile);
+        mbar_expect_tx(s.wfull, 9 * p.kpt * wtile, leader);
         for (int j = 0; j < 3; ++j)
           for (int dyi = 0; dyi < 3; ++dyi)
             for (int cb = 0; cb < p.kpt; ++cb)
               tma_load_2d(s.wres + ((j * 3 + dyi) * p.kpt + cb) * wtile, &tmw, s.wfull,
-                          p.grp_wtap[j][dyi] * p.Cin + cb * p.kc, 0);
+                          p.grp_wtap[j][dyi] * p.Cin + cb * p.kc, 0, leader);
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++g) {
           int t = tile;
           const int tw = t % p.tiles_w; t /= p.tiles_w;
@@ -240,11 +259,11 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
           const int tb = t / p.tiles_h;
           const int st = g % p.stages, ph = (g / p.stages) & 1;
           mbar_wait(&s.empty[st], ph ^ 1);
-          mbar_expect_tx(&s.full[st], 3 * p.kpt * a_tile);
+          mbar_expect_tx(&s.full[st], 3 * p.kpt * a_tile, leader);
           for (int j = 0; j < 3; ++j)
             for (int cb = 0; cb < p.kpt; ++cb)
               tma_load_4d(s.a(st) + (j * p.kpt + cb) * a_tile, &tmx, &s.full[st], cb * p.kc, tw * p.wt + j - 1,
-                          th * p.ht - 1, tb * p.nt);
+                          th * p.ht - 1, tb * p.nt, leader);
         }
       } else
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -258,22 +277,25 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
           const int st = g % p.stages, ph = (g / p.stages) & 1;
           mbar_wait(&s.empty[st], ph ^ 1);
           const int tap = kb / p.kpt, cb = kb - tap * p.kpt;
-          mbar_expect_tx(&s.full[st], tx_bytes);
+          mbar_expect_tx(&s.full[st], tx_bytes, leader);
           if (p.rowshare) {
             // `tap` is the dx group: a (ht+2)-row tile starting one row above serves dy = -1, 0, +1
-            tma_load_4d(s.a(st), &tmx, &s.full[st], cb * p.kc, n0 + tap - 1, m0 - 1, b0);
+            tma_load_4d(s.a(st), &tmx, &s.full[st], cb * p.kc, n0 + tap - 1, m0 - 1, b0, leader);
 #pragma unroll
             for (int dyi = 0; dyi < 3; ++dyi)
-              tma_load_2d(s.b(st) + dyi * wtile, &tmw, &s.full[st], p.grp_wtap[tap][dyi] * p.Cin + cb * p.kc, o0);
+              tma_load_2d(s.b(st) + dyi * wtile, &tmw, &s.full[st], p.grp_wtap[tap][dyi] * p.Cin + cb * p.kc, o0, leader);
           } else {
-            tma_load_4d(s.a(st), &tmx, &s.full[st], cb * p.kc, n0 * p.is + p.dx[tap], m0 * p.is + p.dy[tap], b0);
-            tma_load_2d(s.b(st), &tmw, &s.full[st], p.wtap[tap] * p.Cin + cb * p.kc, o0);
+            tma_load_4d(s.a(st), &tmx, &s.full[st], cb * p.kc, n0 * p.is + p.dx[tap], m0 * p.is + p.dy[tap], b0, leader);
+            tma_load_2d(s.b(st), &tmw, &s.full[st], p.wtap[tap] * p.Cin + cb * p.kc, o0, leader);
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      // NOTE: a second issuing warp alternating tiles was tried and is WRONG as written: a warp that
+      // skips ahead waits on an mbarrier several phases in the future and the parity test aliases.
+      const uint32_t leader = elect_one();
       const uint32_t idesc = make_idesc(p.BN, false, false);
       int g = 0, li = 0;
       if (p.rowshare == 2) {
@@ -302,19 +324,19 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
                 const uint64_t ad = aj + (uint32_t)(dyi * a_dy);
                 const uint64_t bd = bd0 + (uint32_t)(((j * 3 + dyi) * p.kpt + cb) * w_tl);
                 if (p.kc == 32) {
-                  umma_f16(tacc, ad, bd, idesc, first);
-                  umma_f16(tacc, ad + 2, bd + 2, idesc, 1);
+                  umma_f16(tacc, ad, bd, idesc, first, leader);
+                  umma_f16(tacc, ad + 2, bd + 2, idesc, 1, leader);
                 } else {
-                  umma_f16(tacc, ad, bd, idesc, first);
-                  umma_f16(tacc, ad + 2, bd + 2, idesc, 1);
-                  umma_f16(tacc, ad + 4, bd + 4, idesc, 1);
-                  umma_f16(tacc, ad + 6, bd + 6, idesc, 1);
+                  umma_f16(tacc, ad, bd, idesc, first, leader);
+                  umma_f16(tacc, ad + 2, bd + 2, idesc, 1, leader);
+                  umma_f16(tacc, ad + 4, bd + 4, idesc, 1, leader);
+                  umma_f16(tacc, ad + 6, bd + 6, idesc, 1, leader);
                 }
                 first = 1;
               }
             }
-          umma_commit(&s.empty[st]);
-          umma_commit(&s.done[as]);
+          umma_commit(&s.empty[st], leader);
+          umma_commit(&s.done[as], leader);
         }
       } else
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li) {
@@ -333,14 +355,14 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
             const uint64_t bd = make_desc(smem_u32(s.b(st)) + dyi * wtile, 16, 16 * p.kc, p.kc);
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k)   // +32 bytes along K inside the swizzle row
-              if (k * 16 < p.kc) umma_f16(tacc, ad + 2 * k, bd + 2 * k, idesc, (kb | dyi | k) != 0);
+              if (k * 16 < p.kc) umma_f16(tacc, ad + 2 * k, bd + 2 * k, idesc, (kb | dyi | k) != 0, leader);
           }
-          umma_commit(&s.empty[st]);
+          umma_commit(&s.empty[st], leader);
         }
-        umma_commit(&s.done[as]);
+        umma_commit(&s.done[as], leader);
       }
     }
-  } else {
+  } else if (warp >= 2 && warp <= 5) {
     // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31  (= tile rows)
     const int q = warp % 4;
     const int r = q * 32 + lane;
@@ -467,7 +489,8 @@ tapconv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmg, const __grid_co
   const uint32_t gbox = kTileM * p.kcg * 2, xbox = kTileM * p.kcx * 2;   // bytes per box
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
+      const uint32_t leader = elect_one();
       const uint32_t tx_bytes = kWgABytes + nbx * xbox;
       for (int kb = 0; kb < nkb; ++kb) {
         const int st = kb % kStages, ph = (kb / kStages) & 1;
@@ -477,16 +500,17 @@ tapconv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmg, const __grid_co
         const int th = t % p.tiles_h;
         const int tb = t / p.tiles_h;
         const int n0 = tw * p.wt, m0 = th * p.ht, b0 = tb * p.nt;
-        mbar_expect_tx(&s.full[st], tx_bytes);
+        mbar_expect_tx(&s.full[st], tx_bytes, leader);
         for (int j = 0; j < nbg; ++j)      // boxes past Cout are out of range: TMA zero-fills them
-          tma_load_4d(s.a(st) + j * gbox, &tmg, &s.full[st], o0 + p.kcg * j, n0 * p.os + p.px, m0 * p.os + p.py, b0);
+          tma_load_4d(s.a(st) + j * gbox, &tmg, &s.full[st], o0 + p.kcg * j, n0 * p.os + p.px, m0 * p.os + p.py, b0, leader);
         for (int j = 0; j < nbx; ++j)
           tma_load_4d(s.b(st) + j * xbox, &tmx, &s.full[st], c0 + p.kcx * j, n0 * p.is + p.dx[tap],
-                      m0 * p.is + p.dy[tap], b0);
+                      m0 * p.is + p.dy[tap], b0, leader);
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      const uint32_t leader = elect_one();
       const uint32_t idesc = make_idesc(p.BN, true, true);
       for (int kb = 0; kb < nkb; ++kb) {
         const int st = kb % kStages, ph = (kb / kStages) & 1;
@@ -498,10 +522,10 @@ tapconv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmg, const __grid_co
         const uint64_t bd = make_desc(smem_u32(s.b(st)), xbox, 16 * p.kcx, p.kcx);
 #pragma unroll
         for (int k = 0; k < kTileM / 16; ++k)   // 16 pixels = 16 rows of kc*2 bytes along K
-          umma_f16(tmem_base, ad + (uint64_t)(k * 2 * p.kcg), bd + (uint64_t)(k * 2 * p.kcx), idesc, (kb | k) != 0);
-        umma_commit(&s.empty[st]);
+          umma_f16(tmem_base, ad + (uint64_t)(k * 2 * p.kcg), bd + (uint64_t)(k * 2 * p.kcx), idesc, (kb | k) != 0, leader);
+        umma_commit(&s.empty[st], leader);
       }
-      umma_commit(&s.done[0]);
+      umma_commit(&s.done[0], leader);
     }
   } else {
     const int q = warp % 4;
@@ -575,7 +599,8 @@ tapconv_wgrad_tn_kernel(const __grid_constant__ CUtensorMap tmg, const __grid_co
   const uint32_t gbox = kTileM * p.kcg * 2, xbox = kTileM * p.kcx * 2;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
+      const uint32_t leader = elect_one();
       const uint32_t tx_bytes = kWgABytes + p.ntaps * bpt * xbox;
       for (int kb = 0; kb < nkb; ++kb) {
         const int st = kb % kTnStages, ph = (kb / kTnStages) & 1;
@@ -585,17 +610,18 @@ tapconv_wgrad_tn_kernel(const __grid_constant__ CUtensorMap tmg, const __grid_co
         const int th = t % p.tiles_h;
         const int tb = t / p.tiles_h;
         const int n0 = tw * p.wt, m0 = th * p.ht, b0 = tb * p.nt;
-        mbar_expect_tx(&s.full[st], tx_bytes);
+        mbar_expect_tx(&s.full[st], tx_bytes, leader);
         for (int j = 0; j < nbg; ++j)
-          tma_load_4d(s.a(st) + j * gbox, &tmg, &s.full[st], o0 + p.kcg * j, n0 * p.os + p.px, m0 * p.os + p.py, b0);
+          tma_load_4d(s.a(st) + j * gbox, &tmg, &s.full[st], o0 + p.kcg * j, n0 * p.os + p.px, m0 * p.os + p.py, b0, leader);
         for (int tap = 0; tap < p.ntaps; ++tap)
           for (int j = 0; j < bpt; ++j)
             tma_load_4d(s.b(st) + (tap * bpt + j) * xbox, &tmx, &s.full[st], p.kcx * j, n0 * p.is + p.dx[tap],
-                        m0 * p.is + p.dy[tap], b0);
+                        m0 * p.is + p.dy[tap], b0, leader);
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      const uint32_t leader = elect_one();
       for (int kb = 0; kb < nkb; ++kb) {
         const int st = kb % kTnStages, ph = (kb / kTnStages) & 1;
         mbar_wait(&s.full[st], ph);
@@ -608,11 +634,11 @@ tapconv_wgrad_tn_kernel(const __grid_constant__ CUtensorMap tmg, const __grid_co
 #pragma unroll
           for (int k = 0; k < kTileM / 16; ++k)
             umma_f16(tmem_base + (uint32_t)n0c, ad + (uint64_t)(k * 2 * p.kcg), bd + (uint64_t)(k * 2 * p.kcx), idesc,
-                     (kb | k) != 0);
+                     (kb | k) != 0, leader);
         }
-        umma_commit(&s.empty[st]);
+        umma_commit(&s.empty[st], leader);
       }
-      umma_commit(&s.done[0]);
+      umma_commit(&s.done[0], leader);
     }
   } else {
     const int q = warp % 4;
@@ -813,7 +839,7 @@ extern "C" int lcgan_tapconv_tc(const lcgan_tapconv* d, const void* x, const voi
   p.n_tiles = (d->Cout + p.BN - 1) / p.BN;
   p.total_tiles = p.tiles_w * p.tiles_h * tiles_b * p.n_tiles;
   const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();   // persistent: one CTA per SM
-  tapconv_tc_kernel<<<grid, kThreads, fwd_smem_bytes(), (cudaStream_t)stream>>>(tmx, tmw, p, y, rowscale, bias, residual);
+  tapconv_tc_kernel<<<grid, kFwdThreads, fwd_smem_bytes(), (cudaStream_t)stream>>>(tmx, tmw, p, y, rowscale, bias, residual);
   LCGAN_LAUNCH_CHECK();
   return 0;
 }
@@ -884,6 +910,81 @@ extern "C" int lcgan_tapconv_wgrad_tc(const lcgan_tapconv* d, const void* x, con
               cudaGetErrorString(attr_err));
   dim3 grid(otiles * p.ctiles, d->ntaps, splits);
   tapconv_wgrad_tc_kernel<<<grid, kThreads, wg_smem_bytes(), (cudaStream_t)stream>>>(tmg, tmx, p, dw2);
+  LCGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Micro-benchmarks of the raw tcgen05 / TMA issue rates (used to choose tile shapes).
+// mode 0: `iters` back-to-back MMAs M=128 x N x K=16 (K-major SW128 operands in smem garbage)
+// mode 1: same with MN-major operands
+// mode 2: `iters` TMA loads of the activation box described by the tensor map into a 4-slot ring
+// out[blockIdx.x] = elapsed SM clocks.
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(128, 1)
+tc_rate_kernel(const __grid_constant__ CUtensorMap tm, int mode, int n, int iters, int box_bytes, int kc,
+               long long* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar[5];
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 5; ++i) mbar_init(&bar[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(&slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = slot;
+  long long t0 = 0, t1 = 0;
+  if (warp == 1 && lane == 0) {
+    const uint32_t leader = 1;
+    if (mode < 2) {
+      const bool mn = mode == 1;
+      const uint32_t idesc = make_idesc(n, mn, mn);
+      const uint64_t ad = make_desc(smem_u32(base), mn ? 16384 : 16, mn ? 1024 : 16 * kc, kc);
+      const uint64_t bd = make_desc(smem_u32(base) + 32768, mn ? 16384 : 16, mn ? 1024 : 16 * kc, kc);
+      t0 = clock64();
+      for (int i = 0; i < iters; ++i) umma_f16(tmem_base, ad, bd, idesc, 1, leader);
+      umma_commit(&bar[4], leader);
+      mbar_wait(&bar[4], 0);
+      t1 = clock64();
+    } else {
+      t0 = clock64();
+      for (int i = 0; i < iters; ++i) {
+        const int st = i & 3;
+        if (i >= 4) mbar_wait(&bar[st], ((i >> 2) - 1) & 1);
+        mbar_expect_tx(&bar[st], box_bytes, leader);
+        tma_load_4d(base + st * 32768, &tm, &bar[st], 0, (i * 16) & 1023, ((i >> 6) * 8) & 1023, blockIdx.x & 31, leader);
+      }
+      for (int st = 0; st < 4 && st < iters; ++st) {
+        const int last = ((iters - 1 - st) >> 2);     // index of the last use of this slot
+        if (iters > st) mbar_wait(&bar[st], last & 1);
+      }
+      t1 = clock64();
+    }
+    out[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+}  // namespace
+
+extern "C" int lcgan_debug_tc_rate(int mode, int n, int iters, const void* act, int N, int H, int W, int C, int ht,
+                                   long long* out_cycles, int blocks, void* stream) {
+  CUtensorMap tm;
+  const int kc = C % 64 == 0 ? 64 : 32;
+  if (int e = make_act_map(&tm, act, N, H, W, C, 16, ht, 1, 1, kc)) return e;
+  cudaFuncSetAttribute(tc_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 32768 + 2048);
+  tc_rate_kernel<<<blocks, 128, 4 * 32768 + 2048, (cudaStream_t)stream>>>(tm, mode, n, iters, 16 * ht * kc * 2, kc,
+                                                                       out_cycles);
   LCGAN_LAUNCH_CHECK();
   return 0;
 }

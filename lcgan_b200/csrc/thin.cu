@@ -34,15 +34,17 @@ __device__ __forceinline__ float epilogue(const lcgan_tapconv& d, float acc, int
 }
 
 // ------------------------------------------------------------------------------------------
-// thin-out: one thread owns one lattice point and walks X's channel vectors; the weights are read
-// from shared memory as warp-wide broadcasts (every lane needs the same [o][t][c] vector), so no
-// cross-lane reduction is needed.  Lanes of a warp cover consecutive pixels: each 16-byte load is
-// a separate sector of the same cache lines the next iterations consume.
+// thin-out: a group of G lanes (G = min(32, Cin/V), a power of two) owns one lattice point; lane g
+// reads channel vectors g, g+G, ... so every load instruction covers contiguous memory, then the
+// Cout (<= 4) partial sums are combined with log2(G) shuffles.  Weights sit in shared memory and are
+// read as 16-byte vectors.  (A thread-per-point variant was measured 2x slower on the 64..512-channel
+// flow layers: its strided 16-byte loads thrash L1.)
 // ------------------------------------------------------------------------------------------
 template <typename TX, typename TY, int V>
 __global__ void __launch_bounds__(kThreads)
 thin_out_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const void* __restrict__ w, TY* __restrict__ y,
-                const float* __restrict__ rowscale, const float* __restrict__ bias, const TY* __restrict__ residual) {
+                const float* __restrict__ rowscale, const float* __restrict__ bias, const TY* __restrict__ residual,
+                int G) {
   __shared__ __align__(16) float ws[kSmemFloats];          // [o][t][c]
   const int tc = d.ntaps * d.Cin;
   for (int i = threadIdx.x; i < d.Cout * tc; i += kThreads) {
@@ -52,45 +54,60 @@ thin_out_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const void* __r
   __syncthreads();
   const int cv = d.Cin / V;
   const int64_t rows = (int64_t)d.N * d.MH * d.MW;
-  for (int64_t r = blockIdx.x * (int64_t)kThreads + threadIdx.x; r < rows; r += (int64_t)gridDim.x * kThreads) {
-    const int n = (int)(r % d.MW);
-    const int64_t q = r / d.MW;
-    const int m = (int)(q % d.MH);
-    const int b = (int)(q / d.MH);
+  const int gl = threadIdx.x % G, gpb = kThreads / G;
+  const int64_t rows_pad = (rows + gpb - 1) / gpb * gpb;
+  for (int64_t r = (int64_t)blockIdx.x * gpb + threadIdx.x / G; r < rows_pad; r += (int64_t)gridDim.x * gpb) {
+    const bool live = r < rows;
     float acc[kMaxThin] = {0.f, 0.f, 0.f, 0.f};
-    for (int t = 0; t < d.ntaps; ++t) {
-      const int iy = m * d.is + d.dy[t], ix = n * d.is + d.dx[t];
-      if (iy < 0 || iy >= d.IH || ix < 0 || ix >= d.IW) continue;
-      const TX* xp = x + b * d.xs_n + iy * d.xs_h + ix * d.xs_w;
-      const float* wt = ws + t * d.Cin;
-#pragma unroll 4
-      for (int v = 0; v < cv; ++v) {
-        float f[V];
-        if constexpr (V == 1) f[0] = ldf(xp + (int64_t)v * d.xs_c); else ldv<TX, V>(xp + v * V, f);
+    int b = 0, m = 0, n = 0;
+    if (live) {
+      n = (int)(r % d.MW);
+      const int64_t q = r / d.MW;
+      m = (int)(q % d.MH);
+      b = (int)(q / d.MH);
+      for (int t = 0; t < d.ntaps; ++t) {
+        const int iy = m * d.is + d.dy[t], ix = n * d.is + d.dx[t];
+        if (iy < 0 || iy >= d.IH || ix < 0 || ix >= d.IW) continue;
+        const TX* xp = x + b * d.xs_n + iy * d.xs_h + ix * d.xs_w;
+        const float* wt = ws + t * d.Cin;
+        for (int v = gl; v < cv; v += G) {
+          float f[V];
+          if constexpr (V == 1) f[0] = ldf(xp + (int64_t)v * d.xs_c); else ldv<TX, V>(xp + v * V, f);
 #pragma unroll
-        for (int o = 0; o < kMaxThin; ++o) {
-          if (o < d.Cout) {
-            const float* wp = wt + o * tc + v * V;
-            if constexpr (V % 4 == 0) {
+          for (int o = 0; o < kMaxThin; ++o) {
+            if (o < d.Cout) {
+              const float* wp = wt + o * tc + v * V;
+              if constexpr (V % 4 == 0) {
 #pragma unroll
-              for (int i = 0; i < V; i += 4) {
-                const float4 w4 = *reinterpret_cast<const float4*>(wp + i);
-                acc[o] = fmaf(f[i], w4.x, acc[o]); acc[o] = fmaf(f[i + 1], w4.y, acc[o]);
-                acc[o] = fmaf(f[i + 2], w4.z, acc[o]); acc[o] = fmaf(f[i + 3], w4.w, acc[o]);
+                for (int i = 0; i < V; i += 4) {
+                  const float4 w4 = *reinterpret_cast<const float4*>(wp + i);
+                  acc[o] = fmaf(f[i], w4.x, acc[o]); acc[o] = fmaf(f[i + 1], w4.y, acc[o]);
+                  acc[o] = fmaf(f[i + 2], w4.z, acc[o]); acc[o] = fmaf(f[i + 3], w4.w, acc[o]);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < V; ++i) acc[o] = fmaf(f[i], wp[i], acc[o]);
               }
-            } else {
-#pragma unroll
-              for (int i = 0; i < V; ++i) acc[o] = fmaf(f[i], wp[i], acc[o]);
             }
           }
         }
       }
     }
-    const int64_t base = b * d.ys_n + (int64_t)(m * d.os + d.py) * d.ys_h + (int64_t)(n * d.os + d.px) * d.ys_w;
-    for (int o = 0; o < d.Cout; ++o) {
-      float v = epilogue(d, acc[o], b, o, rowscale, bias);
-      if (residual) v += ldf(residual + base + o * d.ys_c);
-      stf(y + base + o * d.ys_c, v);
+    for (int s = G >> 1; s > 0; s >>= 1) {
+#pragma unroll
+      for (int o = 0; o < kMaxThin; ++o)
+        if (o < d.Cout) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], s);
+    }
+    if (live && gl == 0) {
+      const int64_t base = b * d.ys_n + (int64_t)(m * d.os + d.py) * d.ys_h + (int64_t)(n * d.os + d.px) * d.ys_w;
+#pragma unroll
+      for (int o = 0; o < kMaxThin; ++o) {
+        if (o < d.Cout) {
+          float v = epilogue(d, acc[o], b, o, rowscale, bias);
+          if (residual) v += ldf(residual + base + o * d.ys_c);
+          stf(y + base + o * d.ys_c, v);
+        }
+      }
     }
   }
 }
@@ -379,9 +396,10 @@ int lcgan_thin_forward(const lcgan_tapconv& d, const void* x, const void* w, voi
     const bool v_ok = dense_inner(d.xs_c, d.xs_w, d.xs_h, d.xs_n, d.Cin, vec) && ((uintptr_t)x % 16 == 0);
 #define TO(TXT, TYT, VV)                                                                                    \
     do {                                                                                                    \
-      const int grid = grid_cap((rows + kThreads - 1) / kThreads, 16);                                      \
+      const int G = pow2_group(d.Cin / VV);                                                                 \
+      const int grid = grid_cap((rows + kThreads / G - 1) / (kThreads / G), 16);                            \
       thin_out_kernel<TXT, TYT, VV><<<grid, kThreads, 0, s>>>(d, (const TXT*)x, w, (TYT*)y, rowscale, bias, \
-                                                              (const TYT*)residual);                        \
+                                                              (const TYT*)residual, G);                     \
     } while (0)
     if (xf && yf) { if (v_ok) TO(float, float, 4); else TO(float, float, 1); }
     else if (xf && !yf) { if (v_ok) TO(float, bf16, 4); else TO(float, bf16, 1); }
