@@ -30,7 +30,7 @@ constexpr int kMaxBN = 128;
 constexpr int kABytes = kTileM * kBlockK * 2;  // 16 KiB
 constexpr int kBBytes = kMaxBN * kBlockK * 2;  // 16 KiB
 constexpr int kThreads = 192;                  // warp0: TMA, warp1: MMA, warps 2-5: epilogue
-constexpr int kFwdThreads = 192;
+constexpr int kFwdThreads = 224;               // + warp 6: second MMA issuer in the resident-weight mode
 
 struct TcParams {
   int N, Cin, Cout;
@@ -291,10 +291,14 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || (warp == 6 && p.rowshare == 2)) {
     {
-      // NOTE: a second issuing warp alternating tiles was tried and is WRONG as written: a warp that
-      // skips ahead waits on an mbarrier several phases in the future and the parity test aliases.
+      // Resident mode: two issuing warps alternate tiles - one thread needs ~120 cycles of descriptor
+      // moves per MMA while an N<=64 MMA executes in 45.  Safe only because there every tile owns
+      // exactly one smem stage and the stage / accumulator counts are even, so each mbarrier is waited
+      // on by ONE warp, in order (a warp that skipped uses of a barrier would alias its phase parity;
+      // that is why the k-block-ring mode keeps a single issuer).
+      const int mine = warp == 1 ? 0 : 1;
       const uint32_t leader = elect_one();
       const uint32_t idesc = make_idesc(p.BN, false, false);
       int g = 0, li = 0;
@@ -302,6 +306,7 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
         const uint32_t a_tile = (uint32_t)(p.ht + 2) * 16 * p.kc * 2;
         mbar_wait(s.wfull, 0);
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li, ++g) {
+          if ((li & 1) != mine) continue;
           const int as = li % kAccStages, aph = (li / kAccStages) & 1;
           mbar_wait(&s.acc_empty[as], aph ^ 1);
           const int st = g % p.stages, ph = (g / p.stages) & 1;
@@ -814,6 +819,7 @@ extern "C" int lcgan_tapconv_tc(const lcgan_tapconv* d, const void* x, const voi
     p.b_bytes = 0;
     p.stages = (budget - p.wres_bytes) / p.a_bytes;
     if (p.stages > 8) p.stages = 8;
+    p.stages &= ~1;                                         // even: see the two-issuer note in the kernel
     if (p.stages < 2) { p.rowshare = 1; p.wres_bytes = 0; }
   }
   if (p.rowshare == 1 && p.kc == 64 && getenv("LCGAN_ROWSHARE_WIDE") == nullptr) p.rowshare = 0;   // measured slower on 64-ch k-blocks

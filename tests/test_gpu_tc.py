@@ -47,6 +47,9 @@ CASES = [  # kind, k, N, Cin, Cout, H, W
     # 32-channel layers of the 1024x1024 / 512x512 models: 64-byte swizzle rows
     ("s1", 3, 2, 32, 32, 32, 32), ("s2", 3, 2, 32, 64, 32, 32), ("up2", 3, 2, 64, 32, 16, 16),
     ("s1", 1, 2, 32, 64, 16, 16), ("s2_adj", 3, 2, 64, 32, 16, 16), ("s1", 3, 1, 96, 160, 16, 16),
+    # many tiles per persistent CTA (ring wrap-around, TMEM stage reuse, the two-issuer resident mode)
+    ("s1", 3, 8, 32, 32, 128, 128), ("s1", 3, 4, 64, 64, 128, 128), ("s1", 3, 4, 128, 128, 128, 64),
+    ("s2", 3, 4, 64, 128, 128, 128),
 ]
 
 
