@@ -226,7 +226,7 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
     tma_prefetch_desc(&tmw);
     for (int i = 0; i < p.stages; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
     mbar_init(s.wfull, 1);
-    for (int i = 0; i < kAccStages; ++i) { mbar_init(&s.done[i], 1); mbar_init(&s.acc_empty[i], 4); }
+    for (int i = 0; i < kAccStages; ++i) { mbar_init(&s.done[i], p.rowshare == 2 ? 1 : 2); mbar_init(&s.acc_empty[i], 4); }
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<kAccStages * kMaxBN>(s.tmem_slot);
@@ -291,7 +291,7 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
         }
       }
     }
-  } else if (warp == 1 || (warp == 6 && p.rowshare == 2)) {
+  } else if (warp == 1 || warp == 6) {
     {
       // Resident mode: two issuing warps alternate tiles - one thread needs ~120 cycles of descriptor
       // moves per MMA while an N<=64 MMA executes in 45.  Safe only because there every tile owns
@@ -344,12 +344,18 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
           umma_commit(&s.done[as], leader);
         }
       } else
+      // k-block-ring mode, two issuers: warp 1 takes the even k-blocks (even smem stages), warp 6 the
+      // odd ones, each into its OWN accumulator (columns (2*pair + issuer)*128); the epilogue adds the
+      // two partial tiles.  Every mbarrier is still used by one warp in order (stage count is even),
+      // both wait the same acc_empty phase, and done[pair] collects one commit from each.
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li) {
-        const int as = li % kAccStages, aph = (li / kAccStages) & 1;
-        mbar_wait(&s.acc_empty[as], aph ^ 1);               // epilogue has drained this TMEM stage
+        const int ap = li & 1, aph = (li >> 1) & 1;
+        mbar_wait(&s.acc_empty[ap], aph ^ 1);               // epilogue has drained this accumulator pair
         tc_fence_after();
-        const uint32_t tacc = tmem_base + (uint32_t)(as * kMaxBN);
+        const uint32_t tacc = tmem_base + (uint32_t)((2 * ap + mine) * kMaxBN);
+        uint32_t first = 0;
         for (int kb = 0; kb < nkb; ++kb, ++g) {
+          if ((g & 1) != mine) continue;
           const int st = g % p.stages, ph = (g / p.stages) & 1;
           mbar_wait(&s.full[st], ph);
           tc_fence_after();
@@ -360,11 +366,11 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
             const uint64_t bd = make_desc(smem_u32(s.b(st)) + dyi * wtile, 16, 16 * p.kc, p.kc);
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k)   // +32 bytes along K inside the swizzle row
-              if (k * 16 < p.kc) umma_f16(tacc, ad + 2 * k, bd + 2 * k, idesc, (kb | dyi | k) != 0, leader);
+              if (k * 16 < p.kc) { umma_f16(tacc, ad + 2 * k, bd + 2 * k, idesc, first, leader); first = 1; }
           }
           umma_commit(&s.empty[st], leader);
         }
-        umma_commit(&s.done[as], leader);
+        umma_commit(&s.done[ap], leader);
       }
     }
   } else if (warp >= 2 && warp <= 5) {
@@ -384,13 +390,30 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
       const bool live = b < p.N;
       const long long pix = (long long)b * p.ys_n + (long long)((m0 + mi) * p.os + p.py) * p.ys_h +
                             (long long)((n0 + ni) * p.os + p.px) * p.ys_w;
-      const int as = li % kAccStages, aph = (li / kAccStages) & 1;
+      // resident mode: 4 single accumulators; ring mode: 2 pairs of partial accumulators
+      const bool ring = p.rowshare != 2;
+      const int as = ring ? (li & 1) : li % kAccStages, aph = ring ? (li >> 1) & 1 : (li / kAccStages) & 1;
       mbar_wait(&s.done[as], aph);
       tc_fence_after();
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kMaxBN);
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((ring ? 2 * as : as) * kMaxBN);
+      // which issuers contributed k-blocks to this tile (both unless the tile has a single k-block)
+      const int g0 = li * nkb;
+      const bool has0 = !ring || nkb > 1 || (g0 & 1) == 0, has1 = ring && (nkb > 1 || (g0 & 1) == 1);
       for (int c = 0; c < p.BN; c += 16) {
         uint32_t v[16];
-        tmem_ld16(trow + c, v);
+        if (has0) {
+          tmem_ld16(trow + c, v);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = 0u;
+        }
+        if (has1) {
+          uint32_t v2[16];
+          tmem_ld16(trow + kMaxBN + c, v2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+        }
         tmem_ld_wait();
         const int o = o0 + c;
         if (live && o < p.Cout) {
@@ -827,7 +850,8 @@ extern "C" int lcgan_tapconv_tc(const lcgan_tapconv* d, const void* x, const voi
   } else if (p.rowshare) {
     p.a_bytes = (p.ht + 2) * 16 * p.kc * 2;                 // 20 KiB (kc=64) / 10 KiB (kc=32)
     p.b_bytes = 3 * p.BN * p.kc * 2;
-    p.stages = 3;
+    p.stages = 2;                                           // even: one issuer per stage parity
+    if ((p.a_bytes + p.b_bytes) * 4 <= budget) p.stages = 4;
     if ((p.a_bytes + p.b_bytes) * 6 <= budget) p.stages = 6;
   } else {
     p.a_bytes = kABytes; p.b_bytes = kBBytes; p.stages = kFwdStages;
