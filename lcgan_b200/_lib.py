@@ -78,6 +78,8 @@ _SIGS = {
     "lcgan_warp_fwd": ([_VOIDP, _FP, _VOIDP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _VOIDP], C.c_int),
     "lcgan_warp_bwd": ([_VOIDP, _FP, _VOIDP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                         C.c_float, _VOIDP], C.c_int),
+    "lcgan_warp_bwd_tiled": ([_VOIDP, _FP, _VOIDP, _VOIDP, _FP, _FP, _VOIDP, C.c_int, C.c_int, C.c_int, C.c_int,
+                              C.c_int, C.c_float, _VOIDP], C.c_int),
     "lcgan_cast": ([_VOIDP, _VOIDP, C.c_int, C.c_int, C.c_int64, _VOIDP], C.c_int),
     "lcgan_l2norm_fwd": ([_FP, _FP, _FP, C.c_int, C.c_int, _VOIDP], C.c_int),
     "lcgan_l2norm_bwd": ([_FP, _FP, _FP, _FP, C.c_int, C.c_int, _VOIDP], C.c_int),

@@ -81,6 +81,33 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+
+// ---- shared-memory tile staging (cp.async, zero fill outside the image) ------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool pred) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int sz = pred ? 16 : 0;                          // 0 source bytes: the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+// window pixel (r, q) <- image pixel (wy0 + r, wx0 + q), the 64-byte channel chunk starting at
+// element c0; PITCH bytes per window pixel; NT threads cooperate
+template <typename T, int WW, int WH, int PITCH, int NT>
+__device__ __forceinline__ void load_window(unsigned char* sm, const T* __restrict__ img, int H, int W, int C,
+                                            int c0, int wy0, int wx0) {
+  constexpr int NV = WW * WH * 4;
+  for (int i = threadIdx.x; i < NV; i += NT) {
+    const int v = i & 3, pq = i >> 2;
+    const int q = pq % WW, r = pq / WW;
+    const int y = wy0 + r, x = wx0 + q;
+    const bool ok = y >= 0 && y < H && x >= 0 && x < W;
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(img);
+    if (ok) src = reinterpret_cast<const unsigned char*>(img + ((int64_t)y * W + x) * C + c0) + v * 16;
+    cp_async16(sm + pq * PITCH + v * 16, src, ok);
+  }
+}
+
 // thin.cu: special-shape kernels tried before the generic tiled ones (-1 = not applicable)
 int lcgan_thin_forward(const lcgan_tapconv& d, const void* x, const void* w, void* y, const float* rowscale,
                        const float* bias, const void* residual, cudaStream_t s);

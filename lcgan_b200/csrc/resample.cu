@@ -3,6 +3,7 @@
 // One thread handles one 16-byte channel vector of one pixel (V=1 fallback for odd C), so a warp
 // reads/writes contiguous 512-byte runs along the channel-innermost axis.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -80,7 +81,7 @@ box3_kernel(const T* __restrict__ a, const T* __restrict__ mask, T* __restrict__
 
 // Strip variant: one thread owns a column of R output rows for one channel vector and slides a
 // window of horizontal 3-sums down it, so each input vector is loaded 3(R+2)/R times instead of 9.
-template <typename T, int V, int R>
+template <typename T, int V, int R, bool MASK>
 __global__ void __launch_bounds__(kThreads)
 box3_strip_kernel(const T* __restrict__ a, const T* __restrict__ mask, T* __restrict__ out, int N, int H,
                   int W, int C, float pre_slope, float pre_gain, float post_slope, float post_gain) {
@@ -110,7 +111,7 @@ box3_strip_kernel(const T* __restrict__ a, const T* __restrict__ mask, T* __rest
         const int xc = min(max(xx, 0), W - 1);
         const int64_t off = img + ((int64_t)yc * W + xc) * C + c;
         ldv<T, V>(a + off, f[dx + 1]);
-        if (mask) {
+        if constexpr (MASK) {
           float m[V];
           ldv<T, V>(mask + off, m);
 #pragma unroll
@@ -133,6 +134,60 @@ box3_strip_kernel(const T* __restrict__ a, const T* __restrict__ mask, T* __rest
         o[i] = (v > 0.f ? v : v * post_slope) * post_gain;
       }
       stv<T, V>(out + img + ((int64_t)(y0 + r) * W + x) * C + c, o);
+    }
+  }
+}
+
+
+// Tiled variant (no mask): a CTA stages a 34x18 pixel window of one 64-byte channel chunk in shared
+// memory with cp.async (zero fill = the box filter's zero padding) and each thread slides a window
+// of horizontal 3-sums down 8 rows of one 16-byte channel vector.  The loads need no registers, so
+// enough bytes are in flight regardless of instruction scheduling (the strip kernel's 30 dependent
+// vector loads per thread left it latency-bound at 2.2 TB/s).
+constexpr int kBoxTW = 32, kBoxTH = 16, kBoxWW = kBoxTW + 2, kBoxWH = kBoxTH + 2;
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+box3_tile_kernel(const T* __restrict__ a, T* __restrict__ out, int H, int W, int C, float post_slope,
+                 float post_gain) {
+  constexpr int E = 16 / sizeof(T);
+  __shared__ __align__(16) unsigned char sm[kBoxWW * kBoxWH * 64];
+  const int tiles_x = (W + kBoxTW - 1) / kBoxTW, tiles_y = (H + kBoxTH - 1) / kBoxTH;
+  int t = blockIdx.x;
+  const int tx = t % tiles_x; t /= tiles_x;
+  const int ty = t % tiles_y;
+  const int b = t / tiles_y;
+  const int c0 = blockIdx.y * (64 / (int)sizeof(T));
+  const T* img = a + (int64_t)b * H * W * C;
+  load_window<T, kBoxWW, kBoxWH, 64, kThreads>(sm, img, H, W, C, c0, ty * kBoxTH - 1, tx * kBoxTW - 1);
+  cp_async_wait_all();
+  __syncthreads();
+  const int v = threadIdx.x & 3, xq = (threadIdx.x >> 2) & 31, strip = threadIdx.x >> 7;
+  const int ox = tx * kBoxTW + xq;
+  if (ox >= W) return;
+  float h0[E], h1[E], h2[E];
+#pragma unroll
+  for (int rr = 0; rr < 10; ++rr) {
+    const unsigned char* p = sm + ((strip * 8 + rr) * kBoxWW + xq) * 64 + v * 16;
+    float f0[E], f1[E], f2[E];
+    Vec16<T> u;
+    u.v = *reinterpret_cast<const decltype(u.v)*>(p); u.unpack(f0);
+    u.v = *reinterpret_cast<const decltype(u.v)*>(p + 64); u.unpack(f1);
+    u.v = *reinterpret_cast<const decltype(u.v)*>(p + 128); u.unpack(f2);
+#pragma unroll
+    for (int i = 0; i < E; ++i) { h0[i] = h1[i]; h1[i] = h2[i]; h2[i] = f0[i] + f1[i] + f2[i]; }
+    if (rr >= 2) {
+      const int oy = ty * kBoxTH + strip * 8 + rr - 2;
+      if (oy < H) {
+        float o[E];
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+          const float s = (h0[i] + h1[i] + h2[i]) * (1.f / 9.f);
+          o[i] = (s > 0.f ? s : s * post_slope) * post_gain;
+        }
+        Vec16<T> w;
+        w.pack(o);
+        w.store(out + (((int64_t)b * H + oy) * W + ox) * C + c0 + v * E);
+      }
     }
   }
 }
@@ -350,10 +405,25 @@ extern "C" int lcgan_box3(const void* a, const void* mask, void* out, int dt, in
                           float pre_slope, float pre_gain, float post_slope, float post_gain, void* stream) {
   LCGAN_CHECK(a && out && N > 0 && H > 0 && W > 0 && C > 0, "box3: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
-  if (H % 8 == 0 && (int64_t)N * (H / 8) * W * (C / 8) >= 148LL * 64) {
-#define CALL(T, V)                                                                              \
-  box3_strip_kernel<T, V, 8><<<grid_for((int64_t)N * (H / 8) * W * (C / V)), kThreads, 0, s>>>( \
-      (const T*)a, (const T*)mask, (T*)out, N, H, W, C, pre_slope, pre_gain, post_slope, post_gain)
+  const int cc = dt == LCGAN_BF16 ? 32 : 16;
+  if (!mask && (dt == LCGAN_BF16 || dt == LCGAN_F32) && C % cc == 0 && W >= kBoxTW && H >= kBoxTH &&
+      getenv("LCGAN_BOX_NO_TILE") == nullptr) {
+    const dim3 grid(N * ((H + kBoxTH - 1) / kBoxTH) * ((W + kBoxTW - 1) / kBoxTW), C / cc);
+    if (dt == LCGAN_BF16)
+      box3_tile_kernel<bf16><<<grid, kThreads, 0, s>>>((const bf16*)a, (bf16*)out, H, W, C, post_slope, post_gain);
+    else
+      box3_tile_kernel<float><<<grid, kThreads, 0, s>>>((const float*)a, (float*)out, H, W, C, post_slope, post_gain);
+  } else if (H % 8 == 0 && (int64_t)N * (H / 8) * W * (C / 8) >= 148LL * 64) {
+#define CALL(T, V)                                                                                   \
+  do {                                                                                               \
+    const int g_ = grid_for((int64_t)N * (H / 8) * W * (C / V));                                     \
+    if (mask)                                                                                        \
+      box3_strip_kernel<T, V, 8, true><<<g_, kThreads, 0, s>>>(                                      \
+          (const T*)a, (const T*)mask, (T*)out, N, H, W, C, pre_slope, pre_gain, post_slope, post_gain); \
+    else                                                                                             \
+      box3_strip_kernel<T, V, 8, false><<<g_, kThreads, 0, s>>>(                                     \
+          (const T*)a, (const T*)mask, (T*)out, N, H, W, C, pre_slope, pre_gain, post_slope, post_gain); \
+  } while (0)
     DISPATCH_TV(dt, C, CALL);
 #undef CALL
   } else {

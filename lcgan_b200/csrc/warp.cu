@@ -7,6 +7,8 @@
 // strides over its 16-byte channel vectors, so every gather tap is a contiguous run.
 #include "common.cuh"
 #include <stdlib.h>
+#include <limits.h>
+#include <mutex>
 
 namespace {
 
@@ -29,6 +31,7 @@ struct PixCoord {
   int x0, y0;       // floor of the source index
   float tx, ty;     // fractional parts
   float th0, th1;   // tanh(flow)
+  float ix, iy;     // unrounded source index
 };
 
 __device__ __forceinline__ PixCoord source_index(const float* __restrict__ flow, int64_t pix, int h, int w,
@@ -44,6 +47,7 @@ __device__ __forceinline__ PixCoord source_index(const float* __restrict__ flow,
   const float fx = floorf(ix), fy = floorf(iy);
   pc.x0 = (int)fx; pc.y0 = (int)fy;
   pc.tx = ix - fx; pc.ty = iy - fy;
+  pc.ix = ix; pc.iy = iy;
   return pc;
 }
 
@@ -77,6 +81,38 @@ __device__ __forceinline__ void make_taps(const PixCoord& pc, int H, int W, cons
       t.w[j * 4 + i] = ok ? wy[j] * wx[i] : 0.f;
     }
   }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Tiled kernels.  A CTA owns a 32x16 pixel tile of one image (one thread per pixel, a warp per row)
+// and stages a window of the tile plus a margin in shared memory, one 64-byte channel chunk at a
+// time (32 bf16 / 16 fp32 channels; 80-byte pixel pitch so that 16-byte loads at a one-pixel lane
+// stride are bank-conflict free).  The learned flows are small against the tile (random init:
+// < 2.2 px at 1024^2), so every feature vector is read from HBM/L2 once per neighbouring tile and
+// the 16-tap gathers run out of shared memory.
+//   * forward / dflow: per-pixel fallback to global loads when a footprint leaves the window.
+//   * dx: GATHER formulation - source pixel s collects w(s,p) g[p] from the output pixels p whose
+//     footprint contains s, w = k(|s.x - ix_p|) k(|s.y - iy_p|) with k the cubic convolution kernel.
+//     No atomics, no fp32 accumulator tensor, dx is written once in the activation dtype.  It needs
+//     every contributing p inside the window: a pre-pass reduces the integer displacement range of
+//     the whole field into 4 ints; when the range does not fit, the tiled dx kernel exits and the
+//     atomic kernels above (which otherwise exit) do the work.  Both decisions are taken on the
+//     device, so the sequence is CUDA-graph capturable.
+// ------------------------------------------------------------------------------------------
+constexpr int kTW = 32, kTH = 16, kTileThreads = kTW * kTH;
+constexpr int kPixB = 80;
+constexpr int kRF = 4;                                   // margin of the footprint window (fwd, dflow)
+constexpr int kRB = 5;                                   // margin of the contributor window (dx)
+constexpr int kFW = kTW + 2 * kRF, kFH = kTH + 2 * kRF;  // 40 x 24
+constexpr int kBW = kTW + 2 * kRB, kBH = kTH + 2 * kRB;  // 42 x 26
+constexpr int kFwdSmem = kFW * kFH * kPixB;                          // 76 800 B
+constexpr int kDxSmem = kBW * kBH * (kPixB + 8) + 16;                // 96 112 B
+
+// bounds[0..3] = max(-ex), max(ex), max(-ey), max(ey) over the field, e = floor(source index) - pixel
+// index.  Source pixel s is reached from p in [s - e_max - 2, s - e_min + 1].
+__device__ __forceinline__ bool tiled_ok(const int* __restrict__ b) {
+  return b[1] + 2 <= kRB && b[0] + 1 <= kRB && b[3] + 2 <= kRB && b[2] + 1 <= kRB;
 }
 
 template <typename T, int V>
@@ -118,7 +154,8 @@ template <typename T, int V>
 __global__ void __launch_bounds__(kThreads)
 warp_bwd_kernel(const T* __restrict__ x, const float* __restrict__ flow, const T* __restrict__ dout,
                 float* __restrict__ dx, float* __restrict__ dflow, int N, int H, int W, int C, float scale,
-                int G) {
+                int G, const int* __restrict__ skip_if_tiled) {
+  if (skip_if_tiled && tiled_ok(skip_if_tiled)) return;      // the tiled gather kernels did the work
   const int cv = C / V;
   const int64_t npix = (int64_t)N * H * W;
   const int gl = threadIdx.x % G;
@@ -208,7 +245,8 @@ template <typename T>
 __global__ void __launch_bounds__(128)
 warp_bwd_run_kernel(const T* __restrict__ x, const float* __restrict__ flow, const T* __restrict__ dout,
                     float* __restrict__ dx, float* __restrict__ dflow, int N, int H, int W, int C, float scale,
-                    int G, int run) {
+                    int G, int run, const int* __restrict__ skip_if_tiled) {
+  if (skip_if_tiled && tiled_ok(skip_if_tiled)) return;      // the tiled gather kernels did the work
   constexpr int V = 4;                        // 4 channels per lane: one RED.128 per footprint cell
   const int cv = C / V;                       // == G (one vector per lane, G lanes per run)
   (void)cv;
@@ -320,6 +358,283 @@ warp_bwd_run_kernel(const T* __restrict__ x, const float* __restrict__ flow, con
   }
 }
 
+
+template <typename T> __device__ __forceinline__ void unpack16(const uint4& u, float* f);
+template <> __device__ __forceinline__ void unpack16<bf16>(const uint4& u, float* f) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+template <> __device__ __forceinline__ void unpack16<float>(const uint4& u, float* f) {
+  f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y); f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w);
+}
+
+// acc[0..CC) += w * (64-byte pixel chunk at p)
+template <typename T>
+__device__ __forceinline__ void fma_chunk(const unsigned char* p, float w, float* acc) {
+  constexpr int E = 16 / sizeof(T);
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p + v * 16);
+    float f[E];
+    unpack16<T>(u, f);
+#pragma unroll
+    for (int i = 0; i < E; ++i) acc[v * E + i] = fmaf(f[i], w, acc[v * E + i]);
+  }
+}
+// <chunk at p, chunk g> with g kept packed (4 x uint4)
+template <typename T>
+__device__ __forceinline__ float dot_chunk(const unsigned char* p, const uint4* g) {
+  constexpr int E = 16 / sizeof(T);
+  float dot = 0.f;
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p + v * 16);
+    float f[E], h[E];
+    unpack16<T>(u, f);
+    unpack16<T>(g[v], h);
+#pragma unroll
+    for (int i = 0; i < E; ++i) dot = fmaf(f[i], h[i], dot);
+  }
+  return dot;
+}
+template <typename T>
+__device__ __forceinline__ void store_chunk(T* dst, const float* acc) {
+  constexpr int E = 16 / sizeof(T);
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    Vec16<T> o;
+    o.pack(acc + v * E);
+    o.store(dst + v * E);
+  }
+}
+
+// BWD = false: out[p] = sum_taps w x[tap]          (the forward warp)
+// BWD = true : dflow[p] from <x[tap], g[p]> and the derivative weights
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(kTileThreads, 2)
+warp_tile_gather_kernel(const T* __restrict__ x, const float* __restrict__ flow, const T* __restrict__ g,
+                        T* __restrict__ out, float* __restrict__ dflow, int H, int W, int C, float scale) {
+  constexpr int CC = 64 / sizeof(T);
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int tiles_x = (W + kTW - 1) / kTW, tiles_y = (H + kTH - 1) / kTH;
+  int t = blockIdx.x;
+  const int tx = t % tiles_x; t /= tiles_x;
+  const int ty = t % tiles_y;
+  const int b = t / tiles_y;
+  const int px = tx * kTW + (threadIdx.x & 31), py = ty * kTH + (threadIdx.x >> 5);
+  const bool live = px < W && py < H;
+  const int wx0 = tx * kTW - kRF, wy0 = ty * kTH - kRF;
+  const T* img = x + (int64_t)b * H * W * C;
+  const int64_t pix = ((int64_t)b * H + py) * W + px;
+  PixCoord pc{};
+  float wx[4], wy[4], dwx[4], dwy[4];
+  bool inwin = false;
+  if (live) {
+    pc = source_index(flow, pix, py, px, H, W, scale);
+    cubic_w(pc.tx, wx);
+    cubic_w(pc.ty, wy);
+    if constexpr (BWD) { cubic_dw(pc.tx, dwx); cubic_dw(pc.ty, dwy); }
+    inwin = pc.x0 - 1 >= wx0 && pc.x0 + 2 < wx0 + kFW && pc.y0 - 1 >= wy0 && pc.y0 + 2 < wy0 + kFH;
+  }
+  float gix = 0.f, giy = 0.f;
+  for (int c0 = 0; c0 < C; c0 += CC) {
+    if (c0) __syncthreads();                             // everyone is done with the previous chunk
+    load_window<T, kFW, kFH, kPixB, kTileThreads>(smem, img, H, W, C, c0, wy0, wx0);
+    uint4 gv[4];
+    if (BWD && live) {
+#pragma unroll
+      for (int v = 0; v < 4; ++v) gv[v] = *reinterpret_cast<const uint4*>(g + pix * C + c0 + v * (16 / sizeof(T)));
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    if (!live) continue;
+    float acc[CC];
+#pragma unroll
+    for (int i = 0; i < CC; ++i) acc[i] = 0.f;
+    if (inwin) {
+      const unsigned char* base = smem + ((pc.y0 - 1 - wy0) * kFW + (pc.x0 - 1 - wx0)) * kPixB;
+      // one footprint row at a time (4 taps = 16 vector loads in flight); the row weights rotate
+      // through scalars so the row loop needs no dynamic register indexing
+      float ry0 = wy[0], ry1 = wy[1], ry2 = wy[2], ry3 = wy[3];
+      float dy0 = 0.f, dy1 = 0.f, dy2 = 0.f, dy3 = 0.f;
+      if constexpr (BWD) { dy0 = dwy[0]; dy1 = dwy[1]; dy2 = dwy[2]; dy3 = dwy[3]; }
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const unsigned char* p = base + (j * kFW + i) * kPixB;
+          if constexpr (BWD) {
+            const float dot = dot_chunk<T>(p, gv);
+            gix = fmaf(dot, ry0 * dwx[i], gix);
+            giy = fmaf(dot, dy0 * wx[i], giy);
+          } else {
+            fma_chunk<T>(p, ry0 * wx[i], acc);
+          }
+        }
+        ry0 = ry1; ry1 = ry2; ry2 = ry3;
+        dy0 = dy1; dy1 = dy2; dy2 = dy3;
+      }
+    } else {
+      // footprint leaves the window: same arithmetic from global memory (out-of-image taps weigh 0)
+      float ry0 = wy[0], ry1 = wy[1], ry2 = wy[2], ry3 = wy[3];
+      float dy0 = 0.f, dy1 = 0.f, dy2 = 0.f, dy3 = 0.f;
+      if constexpr (BWD) { dy0 = dwy[0]; dy1 = dwy[1]; dy2 = dwy[2]; dy3 = dwy[3]; }
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        const int yy = pc.y0 - 1 + j;
+        const bool oky = yy >= 0 && yy < H;
+        const T* rowp = img + (int64_t)min(max(yy, 0), H - 1) * W * C + c0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int xx = pc.x0 - 1 + i;
+          const bool ok = oky && xx >= 0 && xx < W;
+          const unsigned char* p = reinterpret_cast<const unsigned char*>(rowp + (int64_t)min(max(xx, 0), W - 1) * C);
+          if constexpr (BWD) {
+            const float dot = ok ? dot_chunk<T>(p, gv) : 0.f;
+            gix = fmaf(dot, ry0 * dwx[i], gix);
+            giy = fmaf(dot, dy0 * wx[i], giy);
+          } else {
+            fma_chunk<T>(p, ok ? ry0 * wx[i] : 0.f, acc);
+          }
+        }
+        ry0 = ry1; ry1 = ry2; ry2 = ry3;
+        dy0 = dy1; dy1 = dy2; dy2 = dy3;
+      }
+    }
+    if constexpr (!BWD) store_chunk<T>(out + pix * C + c0, acc);
+  }
+  if (BWD && live) {
+    const float d0 = gix * (0.5f * (float)W) * scale * (1.f - pc.th0 * pc.th0);
+    const float d1 = giy * (0.5f * (float)H) * scale * (1.f - pc.th1 * pc.th1);
+    *reinterpret_cast<float2*>(dflow + pix * 2) = make_float2(d0, d1);
+  }
+}
+
+// cubic convolution kernel of a distance d >= 0 (0 for d >= 2): the tap weight of source pixel s for a
+// sample at ix is k(|s - ix|) - identical to cubic_w(frac)[s - floor(ix) + 1]
+__device__ __forceinline__ float cubic_k(float d) {
+  const bool nr = d <= 1.f;
+  const float c3 = nr ? (kA + 2.f) : kA;
+  const float c2 = nr ? -(kA + 3.f) : -5.f * kA;
+  const float c1 = nr ? 0.f : 8.f * kA;
+  const float c0 = nr ? 1.f : -4.f * kA;
+  return fmaf(fmaf(fmaf(c3, d, c2), d, c1), d, c0);
+}
+
+// Pre-pass: integer displacement range of the whole field (see tiled_ok).  bounds pre-set to a very
+// negative value (memset 0x80).
+__global__ void __launch_bounds__(256)
+warp_bounds_kernel(const float* __restrict__ flow, int N, int H, int W, float scale, int* __restrict__ bounds) {
+  const int64_t npix = (int64_t)N * H * W;
+  int m0 = INT_MIN, m1 = INT_MIN, m2 = INT_MIN, m3 = INT_MIN;
+  for (int64_t pix = blockIdx.x * 256LL + threadIdx.x; pix < npix; pix += (int64_t)gridDim.x * 256) {
+    const int w = (int)(pix % W);
+    const int h = (int)((pix / W) % H);
+    const PixCoord pc = source_index(flow, pix, h, w, H, W, scale);
+    const int ex = pc.x0 - w, ey = pc.y0 - h;
+    m0 = max(m0, -ex); m1 = max(m1, ex); m2 = max(m2, -ey); m3 = max(m3, ey);
+  }
+  m0 = __reduce_max_sync(0xffffffffu, m0); m1 = __reduce_max_sync(0xffffffffu, m1);
+  m2 = __reduce_max_sync(0xffffffffu, m2); m3 = __reduce_max_sync(0xffffffffu, m3);
+  if ((threadIdx.x & 31) == 0) {
+    if (m0 > INT_MIN) atomicMax(bounds + 0, m0);
+    if (m1 > INT_MIN) atomicMax(bounds + 1, m1);
+    if (m2 > INT_MIN) atomicMax(bounds + 2, m2);
+    if (m3 > INT_MIN) atomicMax(bounds + 3, m3);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kTileThreads, 2)
+warp_tile_dx_kernel(const float* __restrict__ flow, const T* __restrict__ g, T* __restrict__ dx,
+                    const int* __restrict__ bounds, int H, int W, int C, float scale) {
+  if (!tiled_ok(bounds)) return;                         // the atomic kernels take over
+  constexpr int CC = 64 / sizeof(T);
+  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned char* gwin = smem;
+  float2* coord = reinterpret_cast<float2*>(smem + kBW * kBH * kPixB);
+  int* lb = reinterpret_cast<int*>(smem + kBW * kBH * (kPixB + 8));
+  const int tiles_x = (W + kTW - 1) / kTW, tiles_y = (H + kTH - 1) / kTH;
+  int t = blockIdx.x;
+  const int tx = t % tiles_x; t /= tiles_x;
+  const int ty = t % tiles_y;
+  const int b = t / tiles_y;
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int px = tx * kTW + lx, py = ty * kTH + ly;
+  const bool live = px < W && py < H;
+  const int wx0 = tx * kTW - kRB, wy0 = ty * kTH - kRB;
+  const T* gimg = g + (int64_t)b * H * W * C;
+  if (threadIdx.x < 4) lb[threadIdx.x] = INT_MIN;
+  __syncthreads();
+  // sample positions of the window's output pixels + the tile-local displacement range
+  int m0 = INT_MIN, m1 = INT_MIN, m2 = INT_MIN, m3 = INT_MIN;
+  for (int i = threadIdx.x; i < kBW * kBH; i += kTileThreads) {
+    const int q = i % kBW, r = i / kBW;
+    const int yy = wy0 + r, xx = wx0 + q;
+    float2 c = make_float2(-1e8f, -1e8f);
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+      const PixCoord pc = source_index(flow, ((int64_t)b * H + yy) * W + xx, yy, xx, H, W, scale);
+      c = make_float2(pc.ix, pc.iy);
+      const int ex = pc.x0 - xx, ey = pc.y0 - yy;
+      m0 = max(m0, -ex); m1 = max(m1, ex); m2 = max(m2, -ey); m3 = max(m3, ey);
+    }
+    coord[i] = c;
+  }
+  m0 = __reduce_max_sync(0xffffffffu, m0); m1 = __reduce_max_sync(0xffffffffu, m1);
+  m2 = __reduce_max_sync(0xffffffffu, m2); m3 = __reduce_max_sync(0xffffffffu, m3);
+  if (lx == 0) { atomicMax(lb + 0, m0); atomicMax(lb + 1, m1); atomicMax(lb + 2, m2); atomicMax(lb + 3, m3); }
+  __syncthreads();
+  // contributors of s: p = s + o, o in [-e_max - 2, -e_min + 1] (inside the window by tiled_ok)
+  const int ox0 = max(-lb[1] - 2, -kRB), ox1 = min(lb[0] + 1, kRB);
+  const int oy0 = max(-lb[3] - 2, -kRB), oy1 = min(lb[2] + 1, kRB);
+  const float sxf = (float)px, syf = (float)py;
+  const int64_t pix = ((int64_t)b * H + py) * W + px;
+  for (int c0 = 0; c0 < C; c0 += CC) {
+    if (c0) __syncthreads();
+    load_window<T, kBW, kBH, kPixB, kTileThreads>(gwin, gimg, H, W, C, c0, wy0, wx0);
+    cp_async_wait_all();
+    __syncthreads();
+    if (!live) continue;
+    float acc[CC];
+#pragma unroll
+    for (int i = 0; i < CC; ++i) acc[i] = 0.f;
+    for (int oy = oy0; oy <= oy1; ++oy) {
+      const int rowi = (ly + kRB + oy) * kBW + lx + kRB;
+      for (int ox = ox0; ox <= ox1; ++ox) {
+        const float2 c = coord[rowi + ox];
+        const float ddx = fabsf(sxf - c.x), ddy = fabsf(syf - c.y);
+        if (ddx < 2.f && ddy < 2.f) fma_chunk<T>(gwin + (rowi + ox) * kPixB, cubic_k(ddx) * cubic_k(ddy), acc);
+      }
+    }
+    store_chunk<T>(dx + pix * C + c0, acc);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+zero_unless_tiled_kernel(float4* __restrict__ p, int64_t n4, const int* __restrict__ bounds) {
+  if (bounds && tiled_ok(bounds)) return;
+  for (int64_t i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256)
+    p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__global__ void __launch_bounds__(256)
+cast_unless_tiled_kernel(const float4* __restrict__ in, bf16* __restrict__ out, int64_t n4, const int* __restrict__ bounds) {
+  if (bounds && tiled_ok(bounds)) return;
+  for (int64_t i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+    const float4 v = in[i];
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), c = __floats2bfloat162_rn(v.z, v.w);
+    reinterpret_cast<uint2*>(out)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&c));
+  }
+}
+
+inline bool tile_eligible(int dt, int H, int W, int C) {
+  const int cc = dt == LCGAN_BF16 ? 32 : 16;
+  return C % cc == 0 && W >= kTW && H >= kTH && getenv("LCGAN_WARP_NO_TILE") == nullptr;
+}
+
 inline int group_size(int cv) {
   if (cv & (cv - 1)) return 1;   // not a power of two: one lane per pixel
   return cv < 32 ? cv : 32;
@@ -334,11 +649,43 @@ inline int grid_for_groups(int64_t npix, int G) {
 
 }  // namespace
 
+template <typename K>
+static int opt_in_smem(K kernel, int bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess ? 0 : 1;
+}
+
+static int tile_kernels_ready() {
+  static std::once_flag once;
+  static int err = 0;
+  std::call_once(once, [] {
+    err |= opt_in_smem(warp_tile_gather_kernel<bf16, false>, kFwdSmem);
+    err |= opt_in_smem(warp_tile_gather_kernel<bf16, true>, kFwdSmem);
+    err |= opt_in_smem(warp_tile_gather_kernel<float, false>, kFwdSmem);
+    err |= opt_in_smem(warp_tile_gather_kernel<float, true>, kFwdSmem);
+    err |= opt_in_smem(warp_tile_dx_kernel<bf16>, kDxSmem);
+    err |= opt_in_smem(warp_tile_dx_kernel<float>, kDxSmem);
+  });
+  return err;
+}
+
 extern "C" int lcgan_warp_fwd(const void* x, const float* flow, void* out, int dt, int N, int H, int W, int C,
                               float flow_scale, void* stream) {
   LCGAN_CHECK(x && flow && out && N > 0 && H > 1 && W > 1 && C > 0, "warp_fwd: bad arguments");
+  LCGAN_CHECK(dt == LCGAN_F32 || dt == LCGAN_BF16, "warp_fwd: bad dtype %d", dt);
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t npix = (int64_t)N * H * W;
+  if (tile_eligible(dt, H, W, C)) {
+    LCGAN_CHECK(tile_kernels_ready() == 0, "warp_fwd: cannot opt in to %d bytes of shared memory", kDxSmem);
+    const int tiles = N * ((H + kTH - 1) / kTH) * ((W + kTW - 1) / kTW);
+    if (dt == LCGAN_BF16)
+      warp_tile_gather_kernel<bf16, false><<<tiles, kTileThreads, kFwdSmem, s>>>(
+          (const bf16*)x, flow, nullptr, (bf16*)out, nullptr, H, W, C, flow_scale);
+    else
+      warp_tile_gather_kernel<float, false><<<tiles, kTileThreads, kFwdSmem, s>>>(
+          (const float*)x, flow, nullptr, (float*)out, nullptr, H, W, C, flow_scale);
+    LCGAN_LAUNCH_CHECK();
+    return 0;
+  }
 #define CALL(T, V)                                                                         \
   do {                                                                                     \
     const int G = group_size(C / V);                                                       \
@@ -346,17 +693,15 @@ extern "C" int lcgan_warp_fwd(const void* x, const float* flow, void* out, int d
         (const T*)x, flow, (T*)out, N, H, W, C, flow_scale, G);                            \
   } while (0)
   if (dt == LCGAN_F32) { if (C % 4 == 0) CALL(float, 4); else CALL(float, 1); }
-  else if (dt == LCGAN_BF16) { if (C % 8 == 0) CALL(bf16, 8); else CALL(bf16, 1); }
-  else { lcgan_set_error("warp_fwd: bad dtype %d", dt); return 1; }
+  else { if (C % 8 == 0) CALL(bf16, 8); else CALL(bf16, 1); }
 #undef CALL
   LCGAN_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int lcgan_warp_bwd(const void* x, const float* flow, const void* dout, float* dx_acc, float* dflow,
-                              int dt, int N, int H, int W, int C, float flow_scale, void* stream) {
-  LCGAN_CHECK(x && flow && dout && dx_acc && dflow && N > 0 && H > 1 && W > 1 && C > 0, "warp_bwd: bad arguments");
-  cudaStream_t s = (cudaStream_t)stream;
+// the scatter kernels: dx_acc (f32, zeroed) += ..., dflow written; skip = device bounds (or null)
+static void launch_atomic_bwd(const void* x, const float* flow, const void* dout, float* dx_acc, float* dflow, int dt,
+                              int N, int H, int W, int C, float flow_scale, const int* skip, cudaStream_t s) {
   const int64_t npix = (int64_t)N * H * W;
 #define CALL(T, V)                                                                         \
   do {                                                                                     \
@@ -370,16 +715,64 @@ extern "C" int lcgan_warp_bwd(const void* x, const float* flow, const void* dout
       int64_t blocks = (nruns + gpb - 1) / gpb;                                            \
       if (blocks > 148LL * 64) blocks = 148LL * 64;                                        \
       warp_bwd_run_kernel<T><<<(int)blocks, 128, 0, s>>>(                                  \
-          (const T*)x, flow, (const T*)dout, dx_acc, dflow, N, H, W, C, flow_scale, G4, run); \
+          (const T*)x, flow, (const T*)dout, dx_acc, dflow, N, H, W, C, flow_scale, G4, run, skip); \
     } else {                                                                               \
       warp_bwd_kernel<T, V><<<grid_for_groups(npix, G), kThreads, 0, s>>>(                 \
-          (const T*)x, flow, (const T*)dout, dx_acc, dflow, N, H, W, C, flow_scale, G);    \
+          (const T*)x, flow, (const T*)dout, dx_acc, dflow, N, H, W, C, flow_scale, G, skip); \
     }                                                                                      \
   } while (0)
   if (dt == LCGAN_F32) { if (C % 4 == 0) CALL(float, 4); else CALL(float, 1); }
-  else if (dt == LCGAN_BF16) { if (C % 8 == 0) CALL(bf16, 8); else CALL(bf16, 1); }
-  else { lcgan_set_error("warp_bwd: bad dtype %d", dt); return 1; }
+  else { if (C % 8 == 0) CALL(bf16, 8); else CALL(bf16, 1); }
 #undef CALL
+}
+
+extern "C" int lcgan_warp_bwd(const void* x, const float* flow, const void* dout, float* dx_acc, float* dflow,
+                              int dt, int N, int H, int W, int C, float flow_scale, void* stream) {
+  LCGAN_CHECK(x && flow && dout && dx_acc && dflow && N > 0 && H > 1 && W > 1 && C > 0, "warp_bwd: bad arguments");
+  LCGAN_CHECK(dt == LCGAN_F32 || dt == LCGAN_BF16, "warp_bwd: bad dtype %d", dt);
+  launch_atomic_bwd(x, flow, dout, dx_acc, dflow, dt, N, H, W, C, flow_scale, nullptr, (cudaStream_t)stream);
+  LCGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int lcgan_warp_bwd_tiled(const void* x, const float* flow, const void* dout, void* dx, float* dflow,
+                                    float* ws_acc, int* ws_bounds, int dt, int N, int H, int W, int C,
+                                    float flow_scale, void* stream) {
+  LCGAN_CHECK(x && flow && dout && dx && dflow && ws_bounds && N > 0 && H > 1 && W > 1 && C > 0,
+              "warp_bwd_tiled: bad arguments");
+  LCGAN_CHECK(dt == LCGAN_F32 || dt == LCGAN_BF16, "warp_bwd_tiled: bad dtype %d", dt);
+  LCGAN_CHECK(dt == LCGAN_F32 || ws_acc, "warp_bwd_tiled: bf16 needs the f32 scratch accumulator");
+  LCGAN_CHECK(((int64_t)N * H * W * C) % 4 == 0, "warp_bwd_tiled: element count must be a multiple of 4");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t n4 = (int64_t)N * H * W * C / 4;
+  float* acc = dt == LCGAN_F32 ? (float*)dx : ws_acc;     // fp32: the scatter kernels accumulate in place
+  const int egrid = (int)(n4 / 256 + 1 < 148LL * 16 ? n4 / 256 + 1 : 148LL * 16);
+  const int* skip = nullptr;
+  if (tile_eligible(dt, H, W, C)) {
+    LCGAN_CHECK(tile_kernels_ready() == 0, "warp_bwd_tiled: cannot opt in to %d bytes of shared memory", kDxSmem);
+    LCGAN_CUDA(cudaMemsetAsync(ws_bounds, 0x80, 4 * sizeof(int), s));
+    const int64_t npix = (int64_t)N * H * W;
+    const int bgrid = (int)(npix / 256 + 1 < 148LL * 8 ? npix / 256 + 1 : 148LL * 8);
+    warp_bounds_kernel<<<bgrid, 256, 0, s>>>(flow, N, H, W, flow_scale, ws_bounds);
+    const int tiles = N * ((H + kTH - 1) / kTH) * ((W + kTW - 1) / kTW);
+    if (dt == LCGAN_BF16) {
+      warp_tile_gather_kernel<bf16, true><<<tiles, kTileThreads, kFwdSmem, s>>>(
+          (const bf16*)x, flow, (const bf16*)dout, nullptr, dflow, H, W, C, flow_scale);
+      warp_tile_dx_kernel<bf16><<<tiles, kTileThreads, kDxSmem, s>>>(flow, (const bf16*)dout, (bf16*)dx, ws_bounds,
+                                                                    H, W, C, flow_scale);
+    } else {
+      warp_tile_gather_kernel<float, true><<<tiles, kTileThreads, kFwdSmem, s>>>(
+          (const float*)x, flow, (const float*)dout, nullptr, dflow, H, W, C, flow_scale);
+      warp_tile_dx_kernel<float><<<tiles, kTileThreads, kDxSmem, s>>>(flow, (const float*)dout, (float*)dx, ws_bounds,
+                                                                     H, W, C, flow_scale);
+    }
+    LCGAN_LAUNCH_CHECK();
+    skip = ws_bounds;                                     // the rest runs only if the flow is too large
+  }
+  zero_unless_tiled_kernel<<<egrid, 256, 0, s>>>(reinterpret_cast<float4*>(acc), n4, skip);
+  launch_atomic_bwd(x, flow, dout, acc, dflow, dt, N, H, W, C, flow_scale, skip, s);
+  if (dt == LCGAN_BF16)
+    cast_unless_tiled_kernel<<<egrid, 256, 0, s>>>(reinterpret_cast<const float4*>(acc), (bf16*)dx, n4, skip);
   LCGAN_LAUNCH_CHECK();
   return 0;
 }

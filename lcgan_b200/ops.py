@@ -656,17 +656,14 @@ class Warp(torch.autograd.Function):
         x, flow = ctx.saved_tensors
         dout = _cl(dout, x.dtype)
         n, c, h, w = x.shape
-        dx_acc = empty_cl(n, c, h, w, torch.float32, x.device).zero_()
         dflow = torch.empty_like(flow)
-        _lib.call("lcgan_warp_bwd", _ptr(x), _ptr(flow), _ptr(dout), _ptr(dx_acc), _ptr(dflow), _dt(x),
-                  n, h, w, c, C.c_float(ctx.scale), _stream(x),
-                  nbytes=2 * x.numel() * x.element_size() + x.numel() * 4 + 2 * flow.numel() * 4)
-        if x.dtype != torch.float32:
-            dx = torch.empty_like(x)
-            _lib.call("lcgan_cast", _ptr(dx_acc), _ptr(dx), F32, _dt(x), C.c_int64(dx_acc.numel()), _stream(x),
-                      nbytes=dx_acc.numel() * (4 + x.element_size()))
-        else:
-            dx = dx_acc
+        dx = torch.empty_like(x)
+        # scratch for the large-flow (scatter) path only; small flows never touch it
+        ws_acc = None if x.dtype == torch.float32 else torch.empty(x.numel(), dtype=torch.float32, device=x.device)
+        ws_bounds = torch.empty(4, dtype=torch.int32, device=x.device)
+        _lib.call("lcgan_warp_bwd_tiled", _ptr(x), _ptr(flow), _ptr(dout), _ptr(dx), _ptr(dflow), _ptr(ws_acc),
+                  _ptr(ws_bounds), _dt(x), n, h, w, c, C.c_float(ctx.scale), _stream(x), tag="warp_bwd",
+                  nbytes=3 * x.numel() * x.element_size() + 2 * flow.numel() * 4)
         return dx, dflow, None
 
 

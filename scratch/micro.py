@@ -33,9 +33,9 @@ for w in which:
         if w == "box": ms = timeit(lambda: ops.Box3.apply(x)); tr = 2 * nb
         elif w == "actbwd": ms = timeit(lambda: ops._act_bwd_raw(g, x, None, 0.2, 1.4, True, False)); tr = 3 * nb
         elif w == "warpf":
-            flow = cl(torch.randn(N, 2, R, R, device=dev)); ms = timeit(lambda: ops.Warp.apply(x, flow, 0.1)); tr = 2 * nb
+            flow = cl(torch.randn(N, 2, R, R, device=dev) * 0.004); ms = timeit(lambda: ops.Warp.apply(x, flow, 0.1)); tr = 2 * nb
         elif w == "warpb":
-            flow = cl(torch.randn(N, 2, R, R, device=dev)); xr = x.clone().requires_grad_(); fr = flow.clone().requires_grad_()
+            flow = cl(torch.randn(N, 2, R, R, device=dev) * 0.004); xr = x.clone().requires_grad_(); fr = flow.clone().requires_grad_()
             out = ops.Warp.apply(xr, fr, 0.1)
             ms = timeit(lambda: torch.autograd.grad(out, (xr, fr), g, retain_graph=True)); tr = 4 * nb
         print(f"{w:8s} {ms:8.3f} ms  {tr/ms/1e6:8.0f} GB/s (algorithmic)")

@@ -199,6 +199,38 @@ def test_modulate_and_warp(mode, C):
     assert rel_l2(fm.grad, fr.grad) < (1e-3 if mode == "fp32" else 3e-2)
 
 
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", [
+    # (N, C, H, W, flow std, flow scale): eligible for the shared-memory tiled kernels (C % 32, W >= 32, H >= 16)
+    (2, 32, 48, 80, 0.3, 0.1),      # small flow, ragged tiles: gather kernels everywhere
+    (1, 64, 16, 32, 1.5, 0.1),      # two channel chunks, one tile
+    (2, 32, 40, 64, 1.5, 0.6),      # +-19 px: per-pixel global fallback (fwd/dflow), scatter fallback (dx)
+    (1, 32, 32, 64, 0.6, 0.22),     # ~ +-4 px: around the window margins
+])
+def test_warp_tiled(mode, case):
+    ops, _ = _ops()
+    N, C, H, W, fstd, scale = case
+    dt = torch.float32 if mode == "fp32" else torch.bfloat16
+    tol = FP32_TOL * 5 if mode == "fp32" else BF16_TOL
+    torch.manual_seed(5)
+    x = _cl(torch.randn(N, C, H, W, device="cuda").to(dt))
+    g = torch.randn(N, C, H, W, device="cuda").to(dt)
+    flow = _cl(torch.randn(N, 2, H, W, device="cuda") * fstd)
+    xr = x.float().clone().requires_grad_(); fr = flow.clone().requires_grad_()
+    xm = x.clone().requires_grad_(); fm = flow.clone().requires_grad_()
+    ys = 2 * torch.arange(H, device="cuda", dtype=torch.float32) / (H - 1) - 1
+    xs = 2 * torch.arange(W, device="cuda", dtype=torch.float32) / (W - 1) - 1
+    gy, gx = torch.meshgrid(ys, xs, indexing="ij")
+    grid = (torch.stack((gx, gy))[None] + torch.tanh(fr) * scale).permute(0, 2, 3, 1)
+    ref = F.grid_sample(xr, grid, mode="bicubic", padding_mode="zeros", align_corners=False)
+    ref.backward(g.float())
+    out = ops.Warp.apply(xm, fm, scale)
+    out.backward(_cl(g))
+    assert rel_l2(out.float(), ref.detach()) < tol
+    assert rel_l2(xm.grad.float(), xr.grad) < tol * 2
+    assert rel_l2(fm.grad, fr.grad) < (1e-3 if mode == "fp32" else 3e-2)
+
+
 def test_loss_kernels():
     ops, _ = _ops()
     from lcgan_b200 import loss
