@@ -58,6 +58,13 @@ int lcgan_version(void);
 /* 1 if the tcgen05 path can take this descriptor (channels-last bf16, Cin%64==0, ...) */
 int lcgan_tapconv_tc_eligible(const lcgan_tapconv* d);
 
+/* conv_transpose2d(k3, s2, p1, op1) with Cout <= 4 (the flow layers, custom_layers.py:78 with C -> 2):
+ * all four output phases in one pass over X.  d = the descriptor of phase (0,0) of the x2 plan
+ * (N, IH, IW, Cin, Cout, strides, dtypes, w_ld and the epilogue constants are read). */
+int lcgan_tapconv_up2_thin_eligible(const lcgan_tapconv* d);
+int lcgan_tapconv_up2_thin(const lcgan_tapconv* d, const void* x, const void* w2, void* y,
+                           const float* rowscale, const float* bias, void* stream);
+
 /* Forward-type tap conv on CUDA cores (any strides/dtypes; fp32 accumulate).
  * Replaces F.conv2d / F.conv_transpose2d / F.linear call sites (custom_layers.py:25,41,43,78,83)
  * and their autograd data-gradients.  rowscale [N,Cout] f32, bias [Cout] f32, residual like Y;

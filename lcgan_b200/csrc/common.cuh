@@ -75,6 +75,29 @@ template <> struct Vec16<bf16> {
   }
 };
 
+
+// 16-byte read-only global load that the compiler may not sink towards its first use: a batch of
+// these issued back to back keeps that many requests in flight per thread (nvcc otherwise schedules
+// each load of an unrolled streaming loop right before its consumer to save registers).
+__device__ __forceinline__ uint4 ldg_stream16(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+template <typename T> __device__ __forceinline__ void unpack_raw16(const uint4& u, float* f);
+template <> __device__ __forceinline__ void unpack_raw16<bf16>(const uint4& u, float* f) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+template <> __device__ __forceinline__ void unpack_raw16<float>(const uint4& u, float* f) {
+  f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y); f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -87,6 +110,10 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, boo
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   const int sz = pred ? 16 : 0;                          // 0 source bytes: the 16 bytes are zero-filled
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_pending() {   // <= N groups still in flight
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");

@@ -8,6 +8,7 @@
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kStreamStages = 4;     // cp.async depth of the streaming reductions (act_bwd, modulate_bwd)
 
 template <typename T, int V>
 __device__ __forceinline__ void ldv(const T* p, float* f) {
@@ -294,8 +295,7 @@ act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict_
                float slope, float gain, int pix_per_block) {
   const int cv = C / V;
   const int b = blockIdx.y;
-  const int p_begin = blockIdx.x * pix_per_block;
-  const int p_end = min(P, p_begin + pix_per_block);
+  (void)pix_per_block;                       // only sizes the grid: blocks interleave over the pixels
   const float inv_pos = 1.f / gain, inv_neg = 1.f / (gain * slope);
   for (int cg = 0; cg < cv; cg += kThreads) {
     const int ncv = min(kThreads, cv - cg);
@@ -305,11 +305,10 @@ act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict_
     float s0[V], s1[V], dd[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) { s0[i] = 0.f; s1[i] = 0.f; dd[i] = d ? d[(int64_t)b * C + c + i] : 1.f; }
-    for (int p = p_begin + threadIdx.x / ncv; p < p_end; p += lanes) {
-      const int64_t off = ((int64_t)b * P + p) * C + c;
-      float g[V], yy[V];
-      ldv<T, V>(dy + off, g);
-      ldv<T, V>(y + off, yy);
+    const int64_t base = (int64_t)b * P * C + c;
+    int p = blockIdx.x * lanes + threadIdx.x / ncv;
+    const int pstep = gridDim.x * lanes;
+    auto body = [&](float* g, const float* yy, int64_t off) {
 #pragma unroll
       for (int i = 0; i < V; ++i) {
         const bool pos = yy[i] > 0.f;
@@ -319,6 +318,43 @@ act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict_
         g[i] = dz * dd[i];
       }
       stv<T, V>(gout + off, g);
+    };
+    if constexpr (V > 1) {
+      // kStreamStages pixels in flight per thread through cp.async (the loads hold no registers and
+      // cannot be sunk to their consumers by the compiler, which left a plain unrolled loop at
+      // 4.0 TB/s); every thread reads back only the slots it filled itself: no block barrier.
+      __shared__ uint4 stage[kStreamStages][2][kThreads];
+      int pl = p;
+#pragma unroll
+      for (int st = 0; st < kStreamStages; ++st, pl += pstep) {
+        if (pl < P) {
+          cp_async16(&stage[st][0][threadIdx.x], dy + base + (int64_t)pl * C, true);
+          cp_async16(&stage[st][1][threadIdx.x], y + base + (int64_t)pl * C, true);
+        }
+        cp_async_commit();
+      }
+      for (int it = 0; p < P; p += pstep, pl += pstep, ++it) {
+        cp_async_wait_pending<kStreamStages - 1>();
+        const int st = it % kStreamStages;
+        float g[V], yy[V];
+        unpack_raw16<T>(stage[st][0][threadIdx.x], g);
+        unpack_raw16<T>(stage[st][1][threadIdx.x], yy);
+        if (pl < P) {
+          cp_async16(&stage[st][0][threadIdx.x], dy + base + (int64_t)pl * C, true);
+          cp_async16(&stage[st][1][threadIdx.x], y + base + (int64_t)pl * C, true);
+        }
+        cp_async_commit();
+        body(g, yy, base + (int64_t)p * C);
+      }
+      cp_async_wait_pending<0>();
+    } else {
+      for (; p < P; p += pstep) {
+        const int64_t off = base + (int64_t)p * C;
+        float g[V], yy[V];
+        ldv<T, V>(dy + off, g);
+        ldv<T, V>(y + off, yy);
+        body(g, yy, off);
+      }
     }
     if (r0) {
 #pragma unroll
@@ -354,8 +390,7 @@ modulate_bwd_kernel(const T* __restrict__ x, const T* __restrict__ t, const floa
                     T* __restrict__ dx, float* __restrict__ ds, int P, int C, int pix_per_block) {
   const int cv = C / V;
   const int b = blockIdx.y;
-  const int p_begin = blockIdx.x * pix_per_block;
-  const int p_end = min(P, p_begin + pix_per_block);
+  (void)pix_per_block;                       // only sizes the grid: blocks interleave over the pixels
   for (int cg = 0; cg < cv; cg += kThreads) {
     const int ncv = min(kThreads, cv - cg);
     const int lanes = kThreads / ncv;
@@ -364,14 +399,46 @@ modulate_bwd_kernel(const T* __restrict__ x, const T* __restrict__ t, const floa
     float acc[V], ss[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) { acc[i] = 0.f; ss[i] = s[(int64_t)b * C + c + i]; }
-    for (int p = p_begin + threadIdx.x / ncv; p < p_end; p += lanes) {
-      const int64_t off = ((int64_t)b * P + p) * C + c;
-      float xv[V], tv[V];
-      ldv<T, V>(x + off, xv);
-      ldv<T, V>(t + off, tv);
+    const int64_t base = (int64_t)b * P * C + c;
+    int p = blockIdx.x * lanes + threadIdx.x / ncv;
+    const int pstep = gridDim.x * lanes;
+    if constexpr (V > 1) {
+      __shared__ uint4 stage[kStreamStages][2][kThreads];   // cp.async pipeline, see act_bwd_kernel
+      int pl = p;
 #pragma unroll
-      for (int i = 0; i < V; ++i) { acc[i] += xv[i] * tv[i]; tv[i] *= ss[i]; }
-      stv<T, V>(dx + off, tv);
+      for (int st = 0; st < kStreamStages; ++st, pl += pstep) {
+        if (pl < P) {
+          cp_async16(&stage[st][0][threadIdx.x], x + base + (int64_t)pl * C, true);
+          cp_async16(&stage[st][1][threadIdx.x], t + base + (int64_t)pl * C, true);
+        }
+        cp_async_commit();
+      }
+      for (int it = 0; p < P; p += pstep, pl += pstep, ++it) {
+        cp_async_wait_pending<kStreamStages - 1>();
+        const int st = it % kStreamStages;
+        float xv[V], tv[V];
+        unpack_raw16<T>(stage[st][0][threadIdx.x], xv);
+        unpack_raw16<T>(stage[st][1][threadIdx.x], tv);
+        if (pl < P) {
+          cp_async16(&stage[st][0][threadIdx.x], x + base + (int64_t)pl * C, true);
+          cp_async16(&stage[st][1][threadIdx.x], t + base + (int64_t)pl * C, true);
+        }
+        cp_async_commit();
+#pragma unroll
+        for (int i = 0; i < V; ++i) { acc[i] += xv[i] * tv[i]; tv[i] *= ss[i]; }
+        stv<T, V>(dx + base + (int64_t)p * C, tv);
+      }
+      cp_async_wait_pending<0>();
+    } else {
+      for (; p < P; p += pstep) {
+        const int64_t off = base + (int64_t)p * C;
+        float xv[V], tv[V];
+        ldv<T, V>(x + off, xv);
+        ldv<T, V>(t + off, tv);
+#pragma unroll
+        for (int i = 0; i < V; ++i) { acc[i] += xv[i] * tv[i]; tv[i] *= ss[i]; }
+        stv<T, V>(dx + off, tv);
+      }
     }
 #pragma unroll
     for (int i = 0; i < V; ++i) atomicAdd(ds + (int64_t)b * C + c + i, acc[i]);

@@ -119,19 +119,30 @@ template <typename TX, typename TY, int V, int VPT>
 __global__ void __launch_bounds__(kThreads)
 thin_in_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const void* __restrict__ w, TY* __restrict__ y,
                const float* __restrict__ rowscale, const float* __restrict__ bias, const TY* __restrict__ residual) {
-  // one thread = VPT consecutive output channel vectors of one lattice point (index math and the
-  // <= 36 input scalars are amortised over VPT*V outputs; a warp stores a contiguous run)
-  __shared__ __align__(16) float ws[kSmemFloats];          // [t][c][o]
+  // one thread = VPT output channel vectors of one lattice point, INTERLEAVED over the og threads of
+  // the point (thread g owns vectors g, g+og, ...): a warp stores contiguous runs, and the weights
+  // are laid out [t][c][quad][o/4] (V%4==0) so that neighbouring threads read neighbouring 16-byte
+  // quads - the former [t][c][o] layout with 4 consecutive vectors per thread put the threads of a
+  // quarter-warp 128 bytes apart, an 8-way bank conflict on every weight load (measured 0.25 TB/s).
+  __shared__ __align__(16) float ws[kSmemFloats];
   const int tc = d.ntaps * d.Cin;
+  constexpr int Q = V % 4 == 0 ? V / 4 : 1;                 // 16-byte quads per output vector
+  const int nvec = d.Cout / V;                              // output vectors per lattice point
   for (int i = threadIdx.x; i < d.Cout * tc; i += kThreads) {
     const int o = i % d.Cout, r = i / d.Cout, t = r / d.Cin, c = r - t * d.Cin;
-    ws[i] = ldw(w, d.w_dtype, (int64_t)o * d.w_ld + (int64_t)d.wtap[t] * d.Cin + c);
+    const float wv = ldw(w, d.w_dtype, (int64_t)o * d.w_ld + (int64_t)d.wtap[t] * d.Cin + c);
+    if constexpr (V % 4 == 0) {
+      const int vec = o / V, q = (o % V) / 4, e = o % 4;
+      ws[(r * Q + q) * (nvec * 4) + vec * 4 + e] = wv;
+    } else {
+      ws[i] = wv;
+    }
   }
   __syncthreads();
   const int og = d.Cout / (V * VPT);
   const int64_t total = (int64_t)d.N * d.MH * d.MW * og;
   for (int64_t idx = blockIdx.x * (int64_t)kThreads + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * kThreads) {
-    const int o0 = (int)(idx % og) * (V * VPT);
+    const int g = (int)(idx % og);
     int64_t r = idx / og;
     const int n = (int)(r % d.MW); r /= d.MW;
     const int m = (int)(r % d.MH);
@@ -147,19 +158,20 @@ thin_in_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const void* __re
       const TX* xp = x + b * d.xs_n + iy * d.xs_h + ix * d.xs_w;
       for (int c = 0; c < d.Cin; ++c) {
         const float xv = ldf(xp + c * d.xs_c);
-        const float* wp = ws + (t * d.Cin + c) * d.Cout + o0;
+        const float* wp = ws + (t * d.Cin + c) * d.Cout;
 #pragma unroll
         for (int j = 0; j < VPT; ++j) {
+          const int vec = j * og + g;
           if constexpr (V % 4 == 0) {
 #pragma unroll
-            for (int i = 0; i < V; i += 4) {
-              const float4 w4 = *reinterpret_cast<const float4*>(wp + j * V + i);
-              acc[j][i] = fmaf(xv, w4.x, acc[j][i]); acc[j][i + 1] = fmaf(xv, w4.y, acc[j][i + 1]);
-              acc[j][i + 2] = fmaf(xv, w4.z, acc[j][i + 2]); acc[j][i + 3] = fmaf(xv, w4.w, acc[j][i + 3]);
+            for (int q = 0; q < Q; ++q) {
+              const float4 w4 = *reinterpret_cast<const float4*>(wp + q * (nvec * 4) + vec * 4);
+              acc[j][4 * q] = fmaf(xv, w4.x, acc[j][4 * q]); acc[j][4 * q + 1] = fmaf(xv, w4.y, acc[j][4 * q + 1]);
+              acc[j][4 * q + 2] = fmaf(xv, w4.z, acc[j][4 * q + 2]); acc[j][4 * q + 3] = fmaf(xv, w4.w, acc[j][4 * q + 3]);
             }
           } else {
 #pragma unroll
-            for (int i = 0; i < V; ++i) acc[j][i] = fmaf(xv, wp[j * V + i], acc[j][i]);
+            for (int i = 0; i < V; ++i) acc[j][i] = fmaf(xv, wp[vec * V + i], acc[j][i]);
           }
         }
       }
@@ -167,7 +179,7 @@ thin_in_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const void* __re
     const int64_t base = b * d.ys_n + (int64_t)(m * d.os + d.py) * d.ys_h + (int64_t)(n * d.os + d.px) * d.ys_w;
 #pragma unroll
     for (int j = 0; j < VPT; ++j) {
-      const int oj = o0 + j * V;
+      const int oj = (j * og + g) * V;
 #pragma unroll
       for (int i = 0; i < V; ++i) acc[j][i] = epilogue(d, acc[j][i], b, oj + i, rowscale, bias);
       if constexpr (V == 1) {
@@ -181,6 +193,121 @@ thin_in_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const void* __re
           for (int i = 0; i < V; ++i) acc[j][i] += rr[i];
         }
         stv<TY, V>(y + base + oj, acc[j]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// thin-up2: ALL FOUR output phases of conv_transpose2d(k3, s2, p1, op1) with Cout <= 4 (the flow
+// layers, custom_layers.py:78 with C -> 2) in one pass over X: a group of G lanes owns input pixel
+// (m, n), reads the channel vectors of x[m..m+1][n..n+1] once and produces the 2x2 output block
+//   out(2m  , 2n  ) = x[m,n] w11
+//   out(2m  , 2n+1) = x[m,n] w12 + x[m,n+1] w10
+//   out(2m+1, 2n  ) = x[m,n] w21 + x[m+1,n] w01
+//   out(2m+1, 2n+1) = x[m,n] w22 + x[m,n+1] w20 + x[m+1,n] w02 + x[m+1,n+1] w00
+// (the four phase launches of the generic path each re-read X and ran at ~1 TB/s).
+// ------------------------------------------------------------------------------------------
+template <typename TX, typename TY, int V, int CO>
+__global__ void __launch_bounds__(kThreads)
+thin_up2_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const void* __restrict__ w, TY* __restrict__ y,
+                const float* __restrict__ rowscale, const float* __restrict__ bias, int G) {
+  // weights [tap 9][o][quad][vector][4]: lane g reads quad q of its vector at a 16-byte lane stride
+  // (conflict-free; [t][o][c] put the lanes 32 bytes apart, a 2-way conflict on every weight load)
+  __shared__ __align__(16) float ws[kSmemFloats];
+  constexpr int Q = V % 4 == 0 ? V / 4 : 1, E = V % 4 == 0 ? 4 : 1;
+  const int Cin = d.Cin, oc = CO * Cin, cv = Cin / V;
+  for (int i = threadIdx.x; i < 9 * oc; i += kThreads) {
+    const int t = i / oc, r = i - t * oc, o = r / Cin, c = r - o * Cin;
+    const int vec = c / V, q = (c % V) / E, e = c % E;
+    ws[((t * CO + o) * Q + q) * (cv * E) + vec * E + e] = ldw(w, d.w_dtype, (int64_t)o * d.w_ld + (int64_t)t * Cin + c);
+  }
+  __syncthreads();
+  const uint32_t rows = (uint32_t)d.N * d.IH * d.IW;       // < 2^31 (checked on the host)
+  const uint32_t gl = threadIdx.x % G, gpb = kThreads / G;
+  const uint32_t rows_pad = (rows + gpb - 1) / gpb * gpb;
+  const uint32_t IW = d.IW, IH = d.IH;
+  for (uint32_t r = blockIdx.x * gpb + threadIdx.x / G; r < rows_pad; r += gridDim.x * gpb) {
+    const bool live = r < rows;
+    float acc[4][CO];
+#pragma unroll
+    for (int ph = 0; ph < 4; ++ph)
+#pragma unroll
+      for (int o = 0; o < CO; ++o) acc[ph][o] = 0.f;
+    uint32_t b = 0, m = 0, n = 0;
+    if (live) {
+      n = r % IW;
+      const uint32_t q = r / IW;
+      m = q % IH;
+      b = q / IH;
+      const bool okx = n + 1 < IW, oky = m + 1 < IH;
+      const TX* p00 = x + b * d.xs_n + (int64_t)m * d.xs_h + (int64_t)n * d.xs_w;
+      const TX* p01 = okx ? p00 + d.xs_w : p00;
+      const TX* p10 = oky ? p00 + d.xs_h : p00;
+      const TX* p11 = p10 + (okx ? d.xs_w : 0);
+      const float m01 = okx ? 1.f : 0.f, m10 = oky ? 1.f : 0.f, m11 = m01 * m10;
+      for (int v = gl; v < cv; v += G) {
+        float f00[V], f01[V], f10[V], f11[V];
+        ldv<TX, V>(p00 + v * V, f00);
+        ldv<TX, V>(p01 + v * V, f01);
+        ldv<TX, V>(p10 + v * V, f10);
+        ldv<TX, V>(p11 + v * V, f11);
+#pragma unroll
+        for (int o = 0; o < CO; ++o) {
+          auto dot = [&](const float* f, int t) {
+            const float* wp = ws + ((t * CO + o) * Q) * (cv * E) + v * E;
+            float sacc = 0.f;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+              if constexpr (E == 4) {
+                const float4 w4 = *reinterpret_cast<const float4*>(wp + q * (cv * E));
+                sacc = fmaf(f[4 * q], w4.x, sacc); sacc = fmaf(f[4 * q + 1], w4.y, sacc);
+                sacc = fmaf(f[4 * q + 2], w4.z, sacc); sacc = fmaf(f[4 * q + 3], w4.w, sacc);
+              } else {
+                sacc = fmaf(f[q], wp[q * (cv * E)], sacc);
+              }
+            }
+            return sacc;
+          };
+          acc[0][o] += dot(f00, 4);
+          acc[1][o] += dot(f00, 5) + m01 * dot(f01, 3);
+          acc[2][o] += dot(f00, 7) + m10 * dot(f10, 1);
+          acc[3][o] += dot(f00, 8) + m01 * dot(f01, 6) + m10 * dot(f10, 2) + m11 * dot(f11, 0);
+        }
+      }
+    }
+    for (int sft = G >> 1; sft > 0; sft >>= 1) {
+#pragma unroll
+      for (int ph = 0; ph < 4; ++ph)
+#pragma unroll
+        for (int o = 0; o < CO; ++o) acc[ph][o] += __shfl_xor_sync(0xffffffffu, acc[ph][o], sft);
+    }
+    if (live) {
+#pragma unroll
+      for (int ph = 0; ph < 4; ++ph)
+#pragma unroll
+        for (int o = 0; o < CO; ++o) acc[ph][o] = epilogue(d, acc[ph][o], b, o, rowscale, bias);
+      if (CO == 2 && sizeof(TY) == 4 && d.ys_c == 1 && d.ys_w == 2 && (d.ys_h & 3) == 0 && (d.ys_n & 3) == 0) {
+        // dense [.., 2H, 2W, 2] f32: output row 2m+j holds the two phases (j,0),(j,1) of this pixel as
+        // one 16-byte store; lane j of the group writes row j
+        if (gl < 2 || G == 1) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            if ((int)gl == j || G == 1) {
+              float* dst = reinterpret_cast<float*>(y) + b * d.ys_n + (int64_t)(2 * m + j) * d.ys_h + (int64_t)(2 * n) * 2;
+              *reinterpret_cast<float4*>(dst) = make_float4(acc[2 * j][0], acc[2 * j][CO - 1], acc[2 * j + 1][0], acc[2 * j + 1][CO - 1]);
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph) {
+          if ((int)gl == (G >= 4 ? ph : 0)) {
+            const int64_t base = b * d.ys_n + (int64_t)(2 * m + (ph >> 1)) * d.ys_h + (int64_t)(2 * n + (ph & 1)) * d.ys_w;
+#pragma unroll
+            for (int o = 0; o < CO; ++o) stf(y + base + o * d.ys_c, acc[ph][o]);
+          }
+        }
       }
     }
   }
@@ -479,6 +606,42 @@ int lcgan_thin_wgrad(const lcgan_tapconv& d, const void* x, const void* g, float
     else if (xf) TWG(bf16, float, 8, false); else TWG(bf16, bf16, 8, false);
   }
 #undef TWG
+  LCGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+// Fused x2 transposed conv with <= 4 output channels (all phases).  d describes phase (0,0) of the
+// plan: N, IH, IW, Cin, Cout, strides, dtypes, w_ld and the epilogue constants are used.
+extern "C" int lcgan_tapconv_up2_thin_eligible(const lcgan_tapconv* d) {
+  if (!d || d->Cout > kMaxThin || d->os != 2 || d->is != 1) return 0;
+  if (9 * d->Cout * d->Cin > kSmemFloats) return 0;
+  if (d->OH != 2 * d->IH || d->OW != 2 * d->IW) return 0;
+  if ((int64_t)d->N * d->IH * d->IW >= (1LL << 31) - 65536) return 0;   // 32-bit pixel index in the kernel
+  const int vec = d->x_dtype == LCGAN_F32 ? 4 : 8;
+  if (d->x_dtype != LCGAN_F32 && d->x_dtype != LCGAN_BF16) return 0;
+  return dense_inner(d->xs_c, d->xs_w, d->xs_h, d->xs_n, d->Cin, vec) ? 1 : 0;
+}
+
+extern "C" int lcgan_tapconv_up2_thin(const lcgan_tapconv* d, const void* x, const void* w2, void* y,
+                                      const float* rowscale, const float* bias, void* stream) {
+  LCGAN_CHECK(lcgan_tapconv_up2_thin_eligible(d), "tapconv_up2_thin: descriptor not eligible");
+  LCGAN_CHECK(x && w2 && y && (uintptr_t)x % 16 == 0, "tapconv_up2_thin: bad pointers");
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool xf = d->x_dtype == LCGAN_F32, yf = d->y_dtype == LCGAN_F32;
+  const int64_t rows = (int64_t)d->N * d->IH * d->IW;
+#define TU(TXT, TYT, VV)                                                                                     \
+  do {                                                                                                       \
+    const int G = pow2_group(d->Cin / VV);                                                                   \
+    const int grid = grid_cap((rows + kThreads / G - 1) / (kThreads / G), 16);                               \
+    switch (d->Cout) {                                                                                       \
+      case 1: thin_up2_kernel<TXT, TYT, VV, 1><<<grid, kThreads, 0, s>>>(*d, (const TXT*)x, w2, (TYT*)y, rowscale, bias, G); break; \
+      case 2: thin_up2_kernel<TXT, TYT, VV, 2><<<grid, kThreads, 0, s>>>(*d, (const TXT*)x, w2, (TYT*)y, rowscale, bias, G); break; \
+      case 3: thin_up2_kernel<TXT, TYT, VV, 3><<<grid, kThreads, 0, s>>>(*d, (const TXT*)x, w2, (TYT*)y, rowscale, bias, G); break; \
+      default: thin_up2_kernel<TXT, TYT, VV, 4><<<grid, kThreads, 0, s>>>(*d, (const TXT*)x, w2, (TYT*)y, rowscale, bias, G); break; \
+    }                                                                                                        \
+  } while (0)
+  if (xf && yf) TU(float, float, 4); else if (xf) TU(float, bf16, 4); else if (yf) TU(bf16, float, 8); else TU(bf16, bf16, 8);
+#undef TU
   LCGAN_LAUNCH_CHECK();
   return 0;
 }

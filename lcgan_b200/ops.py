@@ -208,6 +208,15 @@ def tapconv(x, w2, y, plan: plans.Plan, rowscale=None, bias=None, residual=None,
     lib = _lib.lib()
     st = _stream(x)
     d = TapConvDesc()
+    if len(plan.launches) == 4 and cout <= 4 and residual is None and plan.launches[0].os == 2:
+        # x2 transposed conv of a flow layer: one fused launch for the four output phases
+        _fill_desc(d, plan.launches[0], x, y, cin, cout, w2, slope, gain, bias_scale, acc_scale)
+        if lib.lcgan_tapconv_up2_thin_eligible(C.byref(d)):
+            _lib.call("lcgan_tapconv_up2_thin", C.byref(d), _ptr(x), _ptr(w2), _ptr(y), _ptr(rowscale), _ptr(bias), st,
+                      tag=_shape_tag("lcgan_tapconv_up2_thin", d),
+                      flops=2.0 * x.shape[0] * plan.IH * plan.IW * 9 * cin * cout,
+                      nbytes=x.numel() * x.element_size() + y.numel() * y.element_size())
+            return y
     for l in plan.launches:
         _fill_desc(d, l, x, y, cin, cout, w2, slope, gain, bias_scale, acc_scale)
         fn = "lcgan_tapconv_tc" if (_USE_TC and lib.lcgan_tapconv_tc_eligible(C.byref(d))) else "lcgan_tapconv_simt"

@@ -26,11 +26,31 @@ for w in which:
         else:
             ms = timeit(lambda: ops.tapconv_wgrad(x, g, plan, C, C))
         print(f"{w:8s} {ms:8.3f} ms  {flops/ms/1e9:8.1f} TF/s  {nbytes/ms/1e6:8.0f} GB/s (algorithmic)")
+    elif w in ("flowf", "flowd", "floww"):
+        C, R = 64, 512
+        x = cl(torch.randn(N, C, R, R, device=dev).bfloat16())
+        wt = torch.randn(2, C, 3, 3, device=dev); plan = plans.conv_transpose_up2(3, R, R)
+        if w == "flowf":
+            w2 = ops.pack_weight(wt, False, torch.bfloat16)
+            y = ops.empty_cl(N, 2, 2 * R, 2 * R, torch.float32, dev)
+            ms = timeit(lambda: ops.tapconv(x, w2, y, plan, None, None, None)); tr = x.numel() * 2 + y.numel() * 4
+        elif w == "flowd":
+            g = cl(torch.randn(N, 2, 2 * R, 2 * R, device=dev)); w2 = ops.pack_weight(wt, True, torch.bfloat16)
+            y = ops.empty_cl(N, C, R, R, torch.bfloat16, dev)
+            ms = timeit(lambda: ops.tapconv(g, w2, y, plans.adjoint(plan))); tr = y.numel() * 2 + g.numel() * 4
+        else:
+            g = cl(torch.randn(N, 2, 2 * R, 2 * R, device=dev))
+            ms = timeit(lambda: ops.tapconv_wgrad(x, g, plan, C, 2)); tr = x.numel() * 2 + g.numel() * 4
+        print(f"{w:8s} {ms:8.3f} ms  {tr/ms/1e6:8.0f} GB/s (algorithmic)")
     else:
         C, R = 32, 1024
         x = cl(torch.randn(N, C, R, R, device=dev).bfloat16()); g = cl(torch.randn(N, C, R, R, device=dev).bfloat16())
         nb = x.numel() * 2
         if w == "box": ms = timeit(lambda: ops.Box3.apply(x)); tr = 2 * nb
+        elif w == "modb":
+            sc = torch.randn(N, C, device=dev); ds = torch.zeros(N, C, device=dev); dx = torch.empty_like(x)
+            from lcgan_b200 import _lib as L
+            ms = timeit(lambda: L.call("lcgan_modulate_bwd", ops._ptr(x), ops._ptr(g), ops._ptr(sc), ops._ptr(dx), ops._ptr(ds), ops._dt(x), N, R * R, C, ops._stream(x))); tr = 3 * nb
         elif w == "actbwd": ms = timeit(lambda: ops._act_bwd_raw(g, x, None, 0.2, 1.4, True, False)); tr = 3 * nb
         elif w == "warpf":
             flow = cl(torch.randn(N, 2, R, R, device=dev) * 0.004); ms = timeit(lambda: ops.Warp.apply(x, flow, 0.1)); tr = 2 * nb

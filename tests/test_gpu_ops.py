@@ -39,6 +39,7 @@ CONV_CASES = [  # (k, stride, up, N, Cin, Cout, H, W)
     (3, 1, 1, 2, 16, 24, 8, 8), (3, 2, 1, 2, 16, 24, 8, 8), (1, 1, 1, 3, 8, 5, 4, 6),
     (3, 1, 2, 2, 16, 24, 8, 8), (3, 1, 1, 1, 513, 64, 4, 4), (1, 1, 1, 2, 3, 32, 16, 16),
     (3, 1, 2, 2, 64, 2, 8, 8), (3, 1, 1, 4, 64, 128, 16, 16), (3, 2, 1, 4, 64, 128, 16, 16),
+    (3, 1, 2, 2, 128, 2, 16, 8), (3, 1, 2, 1, 512, 2, 4, 4), (3, 1, 2, 3, 32, 2, 5, 7),   # flow layers: fused x2 thin path
 ]
 
 
