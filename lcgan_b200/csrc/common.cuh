@@ -120,7 +120,11 @@ __device__ __forceinline__ void cp_async_wait_all() {
 }
 // window pixel (r, q) <- image pixel (wy0 + r, wx0 + q), the 64-byte channel chunk starting at
 // element c0; PITCH bytes per window pixel; NT threads cooperate
-template <typename T, int WW, int WH, int PITCH, int NT>
+// SWZ (PITCH must be 64): the 16-byte slot v of window pixel pq is stored at slot v ^ ((pq >> 1) & 3),
+// which makes 16-byte reads of one slot from 8 consecutive pixels bank-conflict free without padding
+// (read back with swz_slot).
+__device__ __forceinline__ int swz_slot(int pq, int v) { return v ^ ((pq >> 1) & 3); }
+template <typename T, int WW, int WH, int PITCH, int NT, bool SWZ = false>
 __device__ __forceinline__ void load_window(unsigned char* sm, const T* __restrict__ img, int H, int W, int C,
                                             int c0, int wy0, int wx0) {
   constexpr int NV = WW * WH * 4;
@@ -131,7 +135,7 @@ __device__ __forceinline__ void load_window(unsigned char* sm, const T* __restri
     const bool ok = y >= 0 && y < H && x >= 0 && x < W;
     const unsigned char* src = reinterpret_cast<const unsigned char*>(img);
     if (ok) src = reinterpret_cast<const unsigned char*>(img + ((int64_t)y * W + x) * C + c0) + v * 16;
-    cp_async16(sm + pq * PITCH + v * 16, src, ok);
+    cp_async16(sm + pq * PITCH + (SWZ ? swz_slot(pq, v) : v) * 16, src, ok);
   }
 }
 

@@ -30,7 +30,7 @@ constexpr int kMaxBN = 128;
 constexpr int kABytes = kTileM * kBlockK * 2;  // 16 KiB
 constexpr int kBBytes = kMaxBN * kBlockK * 2;  // 16 KiB
 constexpr int kThreads = 192;                  // warp0: TMA, warp1: MMA, warps 2-5: epilogue
-constexpr int kFwdThreads = 224;               // + warp 6: second MMA issuer in the resident-weight mode
+constexpr int kFwdThreads = 352;               // warps: 0 TMA, 1+6 MMA issuers, 2-5 and 7-10 two epilogue groups
 
 struct TcParams {
   int N, Cin, Cout;
@@ -373,13 +373,18 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
         umma_commit(&s.done[ap], leader);
       }
     }
-  } else if (warp >= 2 && warp <= 5) {
-    // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31  (= tile rows)
+  } else if ((warp >= 2 && warp <= 5) || warp >= 7) {
+    // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31  (= tile rows).  TWO groups of four warps
+    // (2-5 and 7-10) alternate tiles: ncu showed the small-channel layers epilogue-bound (one group
+    // busy 100 % of the time, the MMA issuers stalled on acc_empty, tensor pipe 16 % active).  Tile
+    // li uses accumulator (pair) li % 4 (li % 2), so group li & 1 is the only waiter of its barriers.
+    const int eg = warp >= 7 ? 1 : 0;
     const int q = warp % 4;
     const int r = q * 32 + lane;
     const int ni = r % p.wt, mi = (r / p.wt) % p.ht, bi = r / (p.wt * p.ht);
     int li = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li) {
+      if ((li & 1) != eg) continue;
       const int nt_i = tile % p.n_tiles;
       int t = tile / p.n_tiles;
       const int tw = t % p.tiles_w; t /= p.tiles_w;
@@ -399,23 +404,8 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
       // which issuers contributed k-blocks to this tile (both unless the tile has a single k-block)
       const int g0 = li * nkb;
       const bool has0 = !ring || nkb > 1 || (g0 & 1) == 0, has1 = ring && (nkb > 1 || (g0 & 1) == 1);
-      for (int c = 0; c < p.BN; c += 16) {
-        uint32_t v[16];
-        if (has0) {
-          tmem_ld16(trow + c, v);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = 0u;
-        }
-        if (has1) {
-          uint32_t v2[16];
-          tmem_ld16(trow + kMaxBN + c, v2);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
-        }
-        tmem_ld_wait();
-        const int o = o0 + c;
+      // 16 accumulator columns -> scale, bias, activation, residual, store
+      auto finish16 = [&](const uint32_t* v, int o) {
         if (live && o < p.Cout) {
           float f[16];
 #pragma unroll
@@ -468,6 +458,33 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
             o0v.store(yp); o1v.store(yp + 8);
           }
         }
+      };
+      // 32 columns per trip: both TMEM loads (and the partner accumulator's) are in flight together
+      for (int c = 0; c < p.BN; c += 32) {
+        const bool two = c + 16 < p.BN;
+        uint32_t va[16], vb[16];
+        if (has0) {
+          tmem_ld16(trow + c, va);
+          if (two) tmem_ld16(trow + c + 16, vb);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { va[i] = 0u; vb[i] = 0u; }
+        }
+        if (has1) {
+          uint32_t wa[16], wb[16];
+          tmem_ld16(trow + kMaxBN + c, wa);
+          if (two) tmem_ld16(trow + kMaxBN + c + 16, wb);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) va[i] = __float_as_uint(__uint_as_float(va[i]) + __uint_as_float(wa[i]));
+          if (two) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) vb[i] = __float_as_uint(__uint_as_float(vb[i]) + __uint_as_float(wb[i]));
+          }
+        }
+        tmem_ld_wait();
+        finish16(va, o0 + c);
+        if (two) finish16(vb, o0 + c + 16);
       }
       // this warp is done reading the TMEM stage: hand it back to the MMA issuer
       tc_fence_before();

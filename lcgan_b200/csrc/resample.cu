@@ -145,45 +145,60 @@ box3_strip_kernel(const T* __restrict__ a, const T* __restrict__ mask, T* __rest
 // of horizontal 3-sums down 8 rows of one 16-byte channel vector.  The loads need no registers, so
 // enough bytes are in flight regardless of instruction scheduling (the strip kernel's 30 dependent
 // vector loads per thread left it latency-bound at 2.2 TB/s).
-constexpr int kBoxTW = 32, kBoxTH = 16, kBoxWW = kBoxTW + 2, kBoxWH = kBoxTH + 2;
-template <typename T>
+constexpr int kBoxTW = 32, kBoxTH = 16, kBoxWW = kBoxTW + 2;   // tile height: 16 (8 with the mask window, 48 KiB static limit)
+template <typename T, bool MASK, int TH>
 __global__ void __launch_bounds__(kThreads)
-box3_tile_kernel(const T* __restrict__ a, T* __restrict__ out, int H, int W, int C, float post_slope,
-                 float post_gain) {
+box3_tile_kernel(const T* __restrict__ a, const T* __restrict__ mask, T* __restrict__ out, int H, int W, int C,
+                 float pre_slope, float pre_gain, float post_slope, float post_gain) {
   constexpr int E = 16 / sizeof(T);
-  __shared__ __align__(16) unsigned char sm[kBoxWW * kBoxWH * 64];
-  const int tiles_x = (W + kBoxTW - 1) / kBoxTW, tiles_y = (H + kBoxTH - 1) / kBoxTH;
+  constexpr int kBoxWH = TH + 2, SR = TH / 2;               // window height, rows per thread
+  constexpr int kWin = kBoxWW * kBoxWH * 64;
+  __shared__ __align__(16) unsigned char sm[MASK ? 2 * kWin : kWin];
+  const int tiles_x = (W + kBoxTW - 1) / kBoxTW, tiles_y = (H + TH - 1) / TH;
   int t = blockIdx.x;
   const int tx = t % tiles_x; t /= tiles_x;
   const int ty = t % tiles_y;
   const int b = t / tiles_y;
   const int c0 = blockIdx.y * (64 / (int)sizeof(T));
-  const T* img = a + (int64_t)b * H * W * C;
-  load_window<T, kBoxWW, kBoxWH, 64, kThreads>(sm, img, H, W, C, c0, ty * kBoxTH - 1, tx * kBoxTW - 1);
+  load_window<T, kBoxWW, kBoxWH, 64, kThreads>(sm, a + (int64_t)b * H * W * C, H, W, C, c0, ty * TH - 1, tx * kBoxTW - 1);
+  if constexpr (MASK)   // the activation mask of the backward pass: a is scaled by the leaky-relu slope of mask
+    load_window<T, kBoxWW, kBoxWH, 64, kThreads>(sm + kWin, mask + (int64_t)b * H * W * C, H, W, C, c0,
+                                                 ty * TH - 1, tx * kBoxTW - 1);
   cp_async_wait_all();
   __syncthreads();
   const int v = threadIdx.x & 3, xq = (threadIdx.x >> 2) & 31, strip = threadIdx.x >> 7;
   const int ox = tx * kBoxTW + xq;
   if (ox >= W) return;
+  const float neg = pre_gain * pre_slope;
   float h0[E], h1[E], h2[E];
 #pragma unroll
-  for (int rr = 0; rr < 10; ++rr) {
-    const unsigned char* p = sm + ((strip * 8 + rr) * kBoxWW + xq) * 64 + v * 16;
-    float f0[E], f1[E], f2[E];
-    Vec16<T> u;
-    u.v = *reinterpret_cast<const decltype(u.v)*>(p); u.unpack(f0);
-    u.v = *reinterpret_cast<const decltype(u.v)*>(p + 64); u.unpack(f1);
-    u.v = *reinterpret_cast<const decltype(u.v)*>(p + 128); u.unpack(f2);
+  for (int rr = 0; rr < SR + 2; ++rr) {
+    const unsigned char* p = sm + ((strip * SR + rr) * kBoxWW + xq) * 64 + v * 16;
+    float f[3][E];
 #pragma unroll
-    for (int i = 0; i < E; ++i) { h0[i] = h1[i]; h1[i] = h2[i]; h2[i] = f0[i] + f1[i] + f2[i]; }
+    for (int k = 0; k < 3; ++k) {
+      Vec16<T> u;
+      u.v = *reinterpret_cast<const decltype(u.v)*>(p + 64 * k);
+      u.unpack(f[k]);
+      if constexpr (MASK) {
+        Vec16<T> m;
+        float mf[E];
+        m.v = *reinterpret_cast<const decltype(m.v)*>(p + kWin + 64 * k);
+        m.unpack(mf);
+#pragma unroll
+        for (int i = 0; i < E; ++i) f[k][i] *= (mf[i] > 0.f ? pre_gain : neg);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < E; ++i) { h0[i] = h1[i]; h1[i] = h2[i]; h2[i] = f[0][i] + f[1][i] + f[2][i]; }
     if (rr >= 2) {
-      const int oy = ty * kBoxTH + strip * 8 + rr - 2;
+      const int oy = ty * TH + strip * SR + rr - 2;
       if (oy < H) {
         float o[E];
 #pragma unroll
         for (int i = 0; i < E; ++i) {
-          const float s = (h0[i] + h1[i] + h2[i]) * (1.f / 9.f);
-          o[i] = (s > 0.f ? s : s * post_slope) * post_gain;
+          const float sv = (h0[i] + h1[i] + h2[i]) * (1.f / 9.f);
+          o[i] = (sv > 0.f ? sv : sv * post_slope) * post_gain;
         }
         Vec16<T> w;
         w.pack(o);
@@ -473,13 +488,16 @@ extern "C" int lcgan_box3(const void* a, const void* mask, void* out, int dt, in
   LCGAN_CHECK(a && out && N > 0 && H > 0 && W > 0 && C > 0, "box3: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
   const int cc = dt == LCGAN_BF16 ? 32 : 16;
-  if (!mask && (dt == LCGAN_BF16 || dt == LCGAN_F32) && C % cc == 0 && W >= kBoxTW && H >= kBoxTH &&
+  if ((dt == LCGAN_BF16 || dt == LCGAN_F32) && C % cc == 0 && W >= kBoxTW && H >= kBoxTH &&
       getenv("LCGAN_BOX_NO_TILE") == nullptr) {
-    const dim3 grid(N * ((H + kBoxTH - 1) / kBoxTH) * ((W + kBoxTW - 1) / kBoxTW), C / cc);
-    if (dt == LCGAN_BF16)
-      box3_tile_kernel<bf16><<<grid, kThreads, 0, s>>>((const bf16*)a, (bf16*)out, H, W, C, post_slope, post_gain);
-    else
-      box3_tile_kernel<float><<<grid, kThreads, 0, s>>>((const float*)a, (float*)out, H, W, C, post_slope, post_gain);
+    const int th = mask ? 8 : kBoxTH;
+    const dim3 grid(N * ((H + th - 1) / th) * ((W + kBoxTW - 1) / kBoxTW), C / cc);
+#define BT(T, M, THH)                                                                                     \
+  box3_tile_kernel<T, M, THH><<<grid, kThreads, 0, s>>>((const T*)a, (const T*)mask, (T*)out, H, W, C,       \
+                                                        pre_slope, pre_gain, post_slope, post_gain)
+    if (dt == LCGAN_BF16) { if (mask) BT(bf16, true, 8); else BT(bf16, false, 16); }
+    else { if (mask) BT(float, true, 8); else BT(float, false, 16); }
+#undef BT
   } else if (H % 8 == 0 && (int64_t)N * (H / 8) * W * (C / 8) >= 148LL * 64) {
 #define CALL(T, V)                                                                                   \
   do {                                                                                               \

@@ -87,8 +87,8 @@ __device__ __forceinline__ void make_taps(const PixCoord& pc, int H, int W, cons
 // ------------------------------------------------------------------------------------------
 // Tiled kernels.  A CTA owns a 32x16 pixel tile of one image (one thread per pixel, a warp per row)
 // and stages a window of the tile plus a margin in shared memory, one 64-byte channel chunk at a
-// time (32 bf16 / 16 fp32 channels; 80-byte pixel pitch so that 16-byte loads at a one-pixel lane
-// stride are bank-conflict free).  The learned flows are small against the tile (random init:
+// time (32 bf16 / 16 fp32 channels; the four 16-byte slots of a pixel are XOR-swizzled so that 16-byte
+// loads at a one-pixel lane stride are bank-conflict free).  The learned flows are small against the tile (random init:
 // < 2.2 px at 1024^2), so every feature vector is read from HBM/L2 once per neighbouring tile and
 // the 16-tap gathers run out of shared memory.
 //   * forward / dflow: per-pixel fallback to global loads when a footprint leaves the window.
@@ -101,13 +101,13 @@ __device__ __forceinline__ void make_taps(const PixCoord& pc, int H, int W, cons
 //     device, so the sequence is CUDA-graph capturable.
 // ------------------------------------------------------------------------------------------
 constexpr int kTW = 32, kTH = 16, kTileThreads = kTW * kTH;
-constexpr int kPixB = 80;
-constexpr int kRF = 4;                                   // margin of the footprint window (fwd, dflow)
-constexpr int kRB = 5;                                   // margin of the contributor window (dx)
-constexpr int kFW = kTW + 2 * kRF, kFH = kTH + 2 * kRF;  // 40 x 24
-constexpr int kBW = kTW + 2 * kRB, kBH = kTH + 2 * kRB;  // 42 x 26
-constexpr int kFwdSmem = kFW * kFH * kPixB;                          // 76 800 B
-constexpr int kDxSmem = kBW * kBH * (kPixB + 8) + 16;                // 96 112 B
+constexpr int kPixB = 64;                                // XOR-swizzled 16-byte slots (swz_slot), no padding
+constexpr int kRF = 6;                                   // margin of the footprint window (fwd, dflow)
+constexpr int kRB = 8;                                   // margin of the contributor window (dx)
+constexpr int kFW = kTW + 2 * kRF, kFH = kTH + 2 * kRF;  // 44 x 28
+constexpr int kBW = kTW + 2 * kRB, kBH = kTH + 2 * kRB;  // 48 x 32
+constexpr int kFwdSmem = kFW * kFH * kPixB;                          //  78 848 B (2 CTAs / SM)
+constexpr int kDxSmem = kBW * kBH * (kPixB + 8) + 16;                // 110 608 B (2 CTAs / SM)
 
 // bounds[0..3] = max(-ex), max(ex), max(-ey), max(ey) over the field, e = floor(source index) - pixel
 // index.  Source pixel s is reached from p in [s - e_max - 2, s - e_min + 1].
@@ -401,6 +401,38 @@ __device__ __forceinline__ float dot_chunk(const unsigned char* p, const uint4* 
   }
   return dot;
 }
+// the same on a swizzled window pixel (win = window base, pq = pixel index in the window)
+template <typename T>
+__device__ __forceinline__ void fma_chunk_win(const unsigned char* win, int pq, float w, float* acc) {
+  constexpr int E = 16 / sizeof(T);
+  const unsigned char* p = win + pq * kPixB;
+  const int x = (pq >> 1) & 3;
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p + ((v ^ x) << 4));
+    float f[E];
+    unpack16<T>(u, f);
+#pragma unroll
+    for (int i = 0; i < E; ++i) acc[v * E + i] = fmaf(f[i], w, acc[v * E + i]);
+  }
+}
+template <typename T>
+__device__ __forceinline__ float dot_chunk_win(const unsigned char* win, int pq, const uint4* g) {
+  constexpr int E = 16 / sizeof(T);
+  const unsigned char* p = win + pq * kPixB;
+  const int x = (pq >> 1) & 3;
+  float dot = 0.f;
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p + ((v ^ x) << 4));
+    float f[E], h[E];
+    unpack16<T>(u, f);
+    unpack16<T>(g[v], h);
+#pragma unroll
+    for (int i = 0; i < E; ++i) dot = fmaf(f[i], h[i], dot);
+  }
+  return dot;
+}
 template <typename T>
 __device__ __forceinline__ void store_chunk(T* dst, const float* acc) {
   constexpr int E = 16 / sizeof(T);
@@ -443,7 +475,7 @@ warp_tile_gather_kernel(const T* __restrict__ x, const float* __restrict__ flow,
   float gix = 0.f, giy = 0.f;
   for (int c0 = 0; c0 < C; c0 += CC) {
     if (c0) __syncthreads();                             // everyone is done with the previous chunk
-    load_window<T, kFW, kFH, kPixB, kTileThreads>(smem, img, H, W, C, c0, wy0, wx0);
+    load_window<T, kFW, kFH, kPixB, kTileThreads, true>(smem, img, H, W, C, c0, wy0, wx0);
     uint4 gv[4];
     if (BWD && live) {
 #pragma unroll
@@ -456,7 +488,7 @@ warp_tile_gather_kernel(const T* __restrict__ x, const float* __restrict__ flow,
 #pragma unroll
     for (int i = 0; i < CC; ++i) acc[i] = 0.f;
     if (inwin) {
-      const unsigned char* base = smem + ((pc.y0 - 1 - wy0) * kFW + (pc.x0 - 1 - wx0)) * kPixB;
+      const int pq0 = (pc.y0 - 1 - wy0) * kFW + (pc.x0 - 1 - wx0);
       // one footprint row at a time (4 taps = 16 vector loads in flight); the row weights rotate
       // through scalars so the row loop needs no dynamic register indexing
       float ry0 = wy[0], ry1 = wy[1], ry2 = wy[2], ry3 = wy[3];
@@ -466,13 +498,13 @@ warp_tile_gather_kernel(const T* __restrict__ x, const float* __restrict__ flow,
       for (int j = 0; j < 4; ++j) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const unsigned char* p = base + (j * kFW + i) * kPixB;
+          const int pq = pq0 + j * kFW + i;
           if constexpr (BWD) {
-            const float dot = dot_chunk<T>(p, gv);
+            const float dot = dot_chunk_win<T>(smem, pq, gv);
             gix = fmaf(dot, ry0 * dwx[i], gix);
             giy = fmaf(dot, dy0 * wx[i], giy);
           } else {
-            fma_chunk<T>(p, ry0 * wx[i], acc);
+            fma_chunk_win<T>(smem, pq, ry0 * wx[i], acc);
           }
         }
         ry0 = ry1; ry1 = ry2; ry2 = ry3;
@@ -595,7 +627,7 @@ warp_tile_dx_kernel(const float* __restrict__ flow, const T* __restrict__ g, T* 
   const int64_t pix = ((int64_t)b * H + py) * W + px;
   for (int c0 = 0; c0 < C; c0 += CC) {
     if (c0) __syncthreads();
-    load_window<T, kBW, kBH, kPixB, kTileThreads>(gwin, gimg, H, W, C, c0, wy0, wx0);
+    load_window<T, kBW, kBH, kPixB, kTileThreads, true>(gwin, gimg, H, W, C, c0, wy0, wx0);
     cp_async_wait_all();
     __syncthreads();
     if (!live) continue;
@@ -607,7 +639,7 @@ warp_tile_dx_kernel(const float* __restrict__ flow, const T* __restrict__ g, T* 
       for (int ox = ox0; ox <= ox1; ++ox) {
         const float2 c = coord[rowi + ox];
         const float ddx = fabsf(sxf - c.x), ddy = fabsf(syf - c.y);
-        if (ddx < 2.f && ddy < 2.f) fma_chunk<T>(gwin + (rowi + ox) * kPixB, cubic_k(ddx) * cubic_k(ddy), acc);
+        if (ddx < 2.f && ddy < 2.f) fma_chunk_win<T>(gwin, rowi + ox, cubic_k(ddx) * cubic_k(ddy), acc);
       }
     }
     store_chunk<T>(dx + pix * C + c0, acc);

@@ -148,16 +148,18 @@ def test_resample_ops(mode, C):
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
-def test_box_filter_strip_kernel(mode):
-    """Large enough for the row-reusing strip kernel (H % 8 == 0, many threads)."""
+@pytest.mark.parametrize("shape", [(4, 64, 64, 48), (2, 32, 44, 72), (2, 24, 64, 48)])
+def test_box_filter_strip_kernel(mode, shape):
+    """Shapes of the shared-memory tiled kernel (C % 32 == 0 in bf16 / C % 16 in fp32, W >= 32, H >= 16;
+    ragged tiles included) and of the row-reusing strip kernel (H % 8 == 0, many threads)."""
     ops, _ = _ops()
     dt = torch.float32 if mode == "fp32" else torch.bfloat16
     tol = FP32_TOL if mode == "fp32" else BF16_TOL
-    x = _cl(torch.randn(4, 64, 64, 48, device="cuda").to(dt))
+    x = _cl(torch.randn(*shape, device="cuda").to(dt))
     xf = x.float().contiguous()
     assert rel_l2(ops.Box3.apply(x).float(), F.avg_pool2d(xf, 3, 1, 1)) < tol
     xr = xf.clone().requires_grad_(); xm = x.clone().requires_grad_()
-    g = torch.randn(4, 64, 64, 48, device="cuda").to(dt)
+    g = torch.randn(*shape, device="cuda").to(dt)
     ref = F.leaky_relu(F.avg_pool2d(xr, 3, 1, 1), 0.2) * 1.4
     ref.backward(g.float())
     y = ops.Box3Act.apply(xm, 0.2, 1.4)
@@ -206,7 +208,9 @@ def test_modulate_and_warp(mode, C):
     (2, 32, 48, 80, 0.3, 0.1),      # small flow, ragged tiles: gather kernels everywhere
     (1, 64, 16, 32, 1.5, 0.1),      # two channel chunks, one tile
     (2, 32, 40, 64, 1.5, 0.6),      # +-19 px: per-pixel global fallback (fwd/dflow), scatter fallback (dx)
-    (1, 32, 32, 64, 0.6, 0.22),     # ~ +-4 px: around the window margins
+    (1, 32, 32, 64, 0.6, 0.22),     # ~ +-4 px
+    (1, 32, 32, 64, 1.5, 0.2),      # ~ +-6 px: around the window margins
+    (1, 32, 32, 64, 1.5, 0.26),     # ~ +-7.5 px: mixed
 ])
 def test_warp_tiled(mode, case):
     ops, _ = _ops()
