@@ -30,7 +30,7 @@ constexpr int kMaxBN = 128;
 constexpr int kABytes = kTileM * kBlockK * 2;  // 16 KiB
 constexpr int kBBytes = kMaxBN * kBlockK * 2;  // 16 KiB
 constexpr int kThreads = 192;                  // warp0: TMA, warp1: MMA, warps 2-5: epilogue
-constexpr int kFwdThreads = 352;               // warps: 0 TMA, 1+6 MMA issuers, 2-5 and 7-10 two epilogue groups
+constexpr int kFwdThreads = 608;               // warps: 0 TMA, 1+6 MMA issuers, 2-5 / 7-10 / 11-14 / 15-18 epilogue groups
 
 struct TcParams {
   int N, Cin, Cout;
@@ -226,7 +226,7 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
     tma_prefetch_desc(&tmw);
     for (int i = 0; i < p.stages; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
     mbar_init(s.wfull, 1);
-    for (int i = 0; i < kAccStages; ++i) { mbar_init(&s.done[i], p.rowshare == 2 ? 1 : 2); mbar_init(&s.acc_empty[i], 4); }
+    for (int i = 0; i < kAccStages; ++i) { mbar_init(&s.done[i], p.rowshare == 2 ? 1 : 2); mbar_init(&s.acc_empty[i], 8); }
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<kAccStages * kMaxBN>(s.tmem_slot);
@@ -374,11 +374,14 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
       }
     }
   } else if ((warp >= 2 && warp <= 5) || warp >= 7) {
-    // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31  (= tile rows).  TWO groups of four warps
-    // (2-5 and 7-10) alternate tiles: ncu showed the small-channel layers epilogue-bound (one group
-    // busy 100 % of the time, the MMA issuers stalled on acc_empty, tensor pipe 16 % active).  Tile
-    // li uses accumulator (pair) li % 4 (li % 2), so group li & 1 is the only waiter of its barriers.
-    const int eg = warp >= 7 ? 1 : 0;
+    // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31  (= tile rows).  FOUR groups of four warps
+    // (2-5, 7-10, 11-14, 15-18): groups alternate tiles (li & 1) and split a tile's 16-column chunks
+    // (even / odd chunks).  ncu showed the small-channel layers epilogue-bound - a single group busy
+    // 100 % of the time at one dependent instruction per ~4 cycles, the MMA issuers stalled on
+    // acc_empty, tensor pipe 16 % active.  Tile li uses accumulator (pair) li % 4 (li % 2), so the two
+    // groups with parity li & 1 are the only waiters of its barriers (8 arrivals free an accumulator).
+    const int grp = warp <= 5 ? 0 : (warp - 7) / 4 + 1;
+    const int eg = grp & 1, half = grp >> 1;
     const int q = warp % 4;
     const int r = q * 32 + lane;
     const int ni = r % p.wt, mi = (r / p.wt) % p.ht, bi = r / (p.wt * p.ht);
@@ -459,32 +462,23 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
           }
         }
       };
-      // 32 columns per trip: both TMEM loads (and the partner accumulator's) are in flight together
-      for (int c = 0; c < p.BN; c += 32) {
-        const bool two = c + 16 < p.BN;
-        uint32_t va[16], vb[16];
+      for (int c = half * 16; c < p.BN; c += 32) {
+        uint32_t va[16];
         if (has0) {
           tmem_ld16(trow + c, va);
-          if (two) tmem_ld16(trow + c + 16, vb);
         } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) { va[i] = 0u; vb[i] = 0u; }
+          for (int i = 0; i < 16; ++i) va[i] = 0u;
         }
         if (has1) {
-          uint32_t wa[16], wb[16];
+          uint32_t wa[16];
           tmem_ld16(trow + kMaxBN + c, wa);
-          if (two) tmem_ld16(trow + kMaxBN + c + 16, wb);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; ++i) va[i] = __float_as_uint(__uint_as_float(va[i]) + __uint_as_float(wa[i]));
-          if (two) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) vb[i] = __float_as_uint(__uint_as_float(vb[i]) + __uint_as_float(wb[i]));
-          }
         }
         tmem_ld_wait();
         finish16(va, o0 + c);
-        if (two) finish16(vb, o0 + c + 16);
       }
       // this warp is done reading the TMEM stage: hand it back to the MMA issuer
       tc_fence_before();

@@ -8,13 +8,18 @@ def cl(x): return x.contiguous(memory_format=torch.channels_last)
 which = sys.argv[1:] or ["fwd32", "box", "warpf", "warpb"]
 N, C, R = 32, 32, 1024
 x = cl(torch.randn(N, C, R, R, device=dev).bfloat16()); g = cl(torch.randn(N, C, R, R, device=dev).bfloat16())
-reps = 2
+reps = 1
 for w in which:
     for _ in range(reps):
         if w == "fwd32":
             w2 = torch.randn(C, 9 * C, device=dev).bfloat16(); plan = plans.conv(3, 1, R, R)
             y = ops.empty_cl(N, C, R, R, torch.bfloat16, dev); bias = torch.randn(C, device=dev)
             ops.tapconv(x, w2, y, plan, None, bias, None, slope=0.2, gain=1.4)
+        elif w in ("wg32", "wg64"):
+            Cw = int(w[2:]); Rw = {32: 1024, 64: 512}[Cw]
+            xw = cl(torch.randn(N, Cw, Rw, Rw, device=dev).bfloat16()); gw = cl(torch.randn(N, Cw, Rw, Rw, device=dev).bfloat16())
+            ops.tapconv_wgrad(xw, gw, plans.conv(3, 1, Rw, Rw), Cw, Cw)
+            del xw, gw
         elif w == "box":
             ops.Box3.apply(x)
         elif w == "actbwd":
