@@ -65,6 +65,11 @@ int lcgan_tapconv_up2_thin_eligible(const lcgan_tapconv* d);
 int lcgan_tapconv_up2_thin(const lcgan_tapconv* d, const void* x, const void* w2, void* y,
                            const float* rowscale, const float* bias, void* stream);
 
+/* weight gradient of the same layer, all 9 taps in one pass over X (Cout <= 2, Cin % 4 == 0, Cin/4 a
+ * divisor of 256): dw2 [Cout][9*Cin] f32 += scale * sum g x; d->y_* describe G [N, 2H, 2W, Cout]. */
+int lcgan_tapconv_up2_thin_wgrad(const lcgan_tapconv* d, const void* x, const void* g, float* dw2,
+                                 float scale, void* stream);
+
 /* Forward-type tap conv on CUDA cores (any strides/dtypes; fp32 accumulate).
  * Replaces F.conv2d / F.conv_transpose2d / F.linear call sites (custom_layers.py:25,41,43,78,83)
  * and their autograd data-gradients.  rowscale [N,Cout] f32, bias [Cout] f32, residual like Y;

@@ -272,30 +272,29 @@ up2box_add_kernel(const T* __restrict__ s, const T* __restrict__ t, T* __restric
     const int ox = (int)(p % OW); p /= OW;
     const int oy = (int)(p % OH);
     const int b = (int)(p / OH);
-    // the 3x3 window on the x2 grid covers at most 2 low-res rows/cols with weights (2,1) or (1,2)
+    // the 3x3 window on the x2 grid covers at most 2 low-res rows/cols with weights (2,1) or (1,2);
+    // branch-free: out-of-range rows/cols are clamped and weigh 0, so the five loads issue together
     const int y0 = (oy - 1) >> 1, y1 = (oy + 1) >> 1;   // oy-1 may be -1 -> y0 = -1 (arith shift)
     const int x0 = (ox - 1) >> 1, x1 = (ox + 1) >> 1;
-    const float wy0 = (oy & 1) ? 2.f : 1.f, wy1 = (oy & 1) ? 1.f : 2.f;
-    const float wx0 = (ox & 1) ? 2.f : 1.f, wx1 = (ox & 1) ? 1.f : 2.f;
-    float acc[V];
+    const float wy[2] = {y0 >= 0 ? ((oy & 1) ? 2.f : 1.f) : 0.f, y1 < H ? ((oy & 1) ? 1.f : 2.f) : 0.f};
+    const float wx[2] = {x0 >= 0 ? ((ox & 1) ? 2.f : 1.f) : 0.f, x1 < W ? ((ox & 1) ? 1.f : 2.f) : 0.f};
+    const int ys[2] = {max(y0, 0), min(y1, H - 1)};
+    const int xs[2] = {max(x0, 0), min(x1, W - 1)};
+    float acc[V], f[4][V];
     ldv<T, V>(t + idx * V, acc);
-    const int ys[2] = {y0, y1};
-    const int xs[2] = {x0, x1};
-    const float wys[2] = {wy0, wy1};
-    const float wxs[2] = {wx0, wx1};
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      if (ys[j] < 0 || ys[j] >= H) continue;
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        ldv<T, V>(s + (((int64_t)b * H + ys[j]) * W + xs[i]) * C + c, f[j * 2 + i]);
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        if (xs[i] < 0 || xs[i] >= W) continue;
-        float f[V];
-        ldv<T, V>(s + (((int64_t)b * H + ys[j]) * W + xs[i]) * C + c, f);
-        const float wgt = wys[j] * wxs[i] * (1.f / 9.f);
+        const float wgt = wy[j] * wx[i] * (1.f / 9.f);
 #pragma unroll
-        for (int k = 0; k < V; ++k) acc[k] += f[k] * wgt;
+        for (int k = 0; k < V; ++k) acc[k] += f[j * 2 + i][k] * wgt;
       }
-    }
     stv<T, V>(out + idx * V, acc);
   }
 }

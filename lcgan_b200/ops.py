@@ -238,6 +238,18 @@ def tapconv_wgrad(x, g, plan: plans.Plan, cin, cout, scale=1.0):
     lib = _lib.lib()
     st = _stream(x)
     d = TapConvDesc()
+    cv4 = cin // 4
+    if (len(plan.launches) == 4 and cout <= 2 and plan.launches[0].os == 2 and cin % 4 == 0 and cv4 <= 256
+            and 256 % cv4 == 0):
+        # x2 transposed conv of a flow layer: one fused pass for all 9 taps
+        _fill_desc(d, plan.launches[0], x, g, cin, cout, None, 1.0, 1.0, 1.0)
+        d.w_ld = plan.k * plan.k * cin
+        if lib.lcgan_tapconv_up2_thin_eligible(C.byref(d)):
+            _lib.call("lcgan_tapconv_up2_thin_wgrad", C.byref(d), _ptr(x), _ptr(g), _ptr(dw2), C.c_float(scale), st,
+                      tag=_shape_tag("lcgan_tapconv_up2_thin_wgrad", d),
+                      flops=2.0 * x.shape[0] * plan.IH * plan.IW * 9 * cin * cout,
+                      nbytes=x.numel() * x.element_size() + g.numel() * g.element_size())
+            return dw2
     for l in plan.launches:
         _fill_desc(d, l, x, g, cin, cout, None, 1.0, 1.0, 1.0)
         d.w_ld = plan.k * plan.k * cin
