@@ -130,11 +130,12 @@ int lcgan_warp_bwd(const void* x, const float* flow, const void* dout, float* dx
                    int dt, int N, int H, int W, int C, float flow_scale, void* stream);
 
 /* Backward of the flow warp with dx written once in the activation dtype: dx [N,H,W,C] dt and
- * dflow [N,H,W,2] f32.  Small flows (every contributing output pixel within 3.5 px of the source
- * pixel - decided on the device from the field itself) run as shared-memory tiled gathers without
- * atomics; otherwise the scatter kernels of lcgan_warp_bwd accumulate into ws_acc and the result is
- * cast.  ws_acc: f32 scratch of N*H*W*C elements (bf16 only, fp32 accumulates in dx); ws_bounds:
- * 4 ints of scratch.  No host synchronisation: CUDA-graph capturable. */
+ * dflow [N,H,W,2] f32.  Smooth flows (the output pixels that reach a 32x16 source tile fit a few
+ * 48x32 windows - decided per tile on the device from the field itself) run as shared-memory tiled
+ * gathers without atomics; otherwise the scatter kernels of lcgan_warp_bwd accumulate into ws_acc
+ * and the result is cast.  ws_acc: f32 scratch of N*H*W*C elements (bf16 only, fp32 accumulates in
+ * dx); ws_bounds: 4 * N * ceil(H/16) * ceil(W/32) + 4 ints of scratch.  No host synchronisation:
+ * CUDA-graph capturable. */
 int lcgan_warp_bwd_tiled(const void* x, const float* flow, const void* dout, void* dx, float* dflow,
                          float* ws_acc, int* ws_bounds, int dt, int N, int H, int W, int C,
                          float flow_scale, void* stream);

@@ -86,34 +86,33 @@ __device__ __forceinline__ void make_taps(const PixCoord& pc, int H, int W, cons
 
 // ------------------------------------------------------------------------------------------
 // Tiled kernels.  A CTA owns a 32x16 pixel tile of one image (one thread per pixel, a warp per row)
-// and stages a window of the tile plus a margin in shared memory, one 64-byte channel chunk at a
-// time (32 bf16 / 16 fp32 channels; the four 16-byte slots of a pixel are XOR-swizzled so that 16-byte
-// loads at a one-pixel lane stride are bank-conflict free).  The learned flows are small against the tile (random init:
-// < 2.2 px at 1024^2), so every feature vector is read from HBM/L2 once per neighbouring tile and
-// the 16-tap gathers run out of shared memory.
-//   * forward / dflow: per-pixel fallback to global loads when a footprint leaves the window.
+// and stages a window of the other tensor in shared memory, one 64-byte channel chunk at a time
+// (32 bf16 / 16 fp32 channels; the four 16-byte slots of a pixel are XOR-swizzled so that 16-byte
+// loads at a one-pixel lane stride are bank-conflict free).  The learned flows are smooth: a tile's
+// samples land in a patch of about the tile's size, displaced by up to tens of pixels once training
+// is under way (measured at 1024^2: < 3 px at init, mean 3 px / max 18 px after 56 iterations).  So
+// the window is PLACED per tile and every feature vector is read from HBM/L2 about once.
+//   * forward / dflow: window = bounding box of the tile's footprints (block reduction); a pixel
+//     whose footprint leaves the 44x28 window falls back to global loads on its own.
 //   * dx: GATHER formulation - source pixel s collects w(s,p) g[p] from the output pixels p whose
 //     footprint contains s, w = k(|s.x - ix_p|) k(|s.y - iy_p|) with k the cubic convolution kernel.
-//     No atomics, no fp32 accumulator tensor, dx is written once in the activation dtype.  It needs
-//     every contributing p inside the window: a pre-pass reduces the integer displacement range of
-//     the whole field into 4 ints; when the range does not fit, the tiled dx kernel exits and the
-//     atomic kernels above (which otherwise exit) do the work.  Both decisions are taken on the
-//     device, so the sequence is CUDA-graph capturable.
+//     No atomics, no fp32 accumulator tensor, dx is written once in the activation dtype.  A pre-pass
+//     over the flow records, per SOURCE tile, the bounding box of the output pixels that reach it;
+//     the dx kernel walks that box in 48x32 windows (one window when the flow is smooth).  A box
+//     needing more than kMaxWindows windows raises a device flag: the tiled result is then
+//     discarded and the atomic scatter kernels above (which otherwise exit at once) redo the
+//     tensor.  Every decision is taken on the device, so the sequence is CUDA-graph capturable.
 // ------------------------------------------------------------------------------------------
 constexpr int kTW = 32, kTH = 16, kTileThreads = kTW * kTH;
 constexpr int kPixB = 64;                                // XOR-swizzled 16-byte slots (swz_slot), no padding
-constexpr int kRF = 6;                                   // margin of the footprint window (fwd, dflow)
-constexpr int kRB = 8;                                   // margin of the contributor window (dx)
-constexpr int kFW = kTW + 2 * kRF, kFH = kTH + 2 * kRF;  // 44 x 28
-constexpr int kBW = kTW + 2 * kRB, kBH = kTH + 2 * kRB;  // 48 x 32
-constexpr int kFwdSmem = kFW * kFH * kPixB;                          //  78 848 B (2 CTAs / SM)
-constexpr int kDxSmem = kBW * kBH * (kPixB + 8) + 16;                // 110 608 B (2 CTAs / SM)
+constexpr int kFW = 44, kFH = 28;                        // footprint window (fwd, dflow): tile + 12
+constexpr int kBW = 48, kBH = 32;                        // contributor window (dx): tile + 16
+constexpr int kMaxWindows = 6;                           // dx: windows per source tile before giving up
+constexpr int kFwdSmem = kFW * kFH * kPixB + 16;                     //  78 864 B (2 CTAs / SM)
+constexpr int kDxSmem = kBW * kBH * (kPixB + 8) + 32;                // 110 624 B (2 CTAs / SM)
 
-// bounds[0..3] = max(-ex), max(ex), max(-ey), max(ey) over the field, e = floor(source index) - pixel
-// index.  Source pixel s is reached from p in [s - e_max - 2, s - e_min + 1].
-__device__ __forceinline__ bool tiled_ok(const int* __restrict__ b) {
-  return b[1] + 2 <= kRB && b[0] + 1 <= kRB && b[3] + 2 <= kRB && b[2] + 1 <= kRB;
-}
+// the scatter (atomic) kernels run only when the tiled dx kernel raised the flag
+__device__ __forceinline__ bool tiled_ok(const int* __restrict__ flag) { return *flag == 0; }
 
 template <typename T, int V>
 __global__ void __launch_bounds__(kThreads)
@@ -459,19 +458,28 @@ warp_tile_gather_kernel(const T* __restrict__ x, const float* __restrict__ flow,
   const int b = t / tiles_y;
   const int px = tx * kTW + (threadIdx.x & 31), py = ty * kTH + (threadIdx.x >> 5);
   const bool live = px < W && py < H;
-  const int wx0 = tx * kTW - kRF, wy0 = ty * kTH - kRF;
   const T* img = x + (int64_t)b * H * W * C;
   const int64_t pix = ((int64_t)b * H + py) * W + px;
+  int* org = reinterpret_cast<int*>(smem + kFW * kFH * kPixB);   // window origin (min x0, min y0 of the tile)
+  if (threadIdx.x < 2) org[threadIdx.x] = INT_MAX;
+  __syncthreads();
   PixCoord pc{};
   float wx[4], wy[4], dwx[4], dwy[4];
-  bool inwin = false;
+  int mx = INT_MAX, my = INT_MAX;
   if (live) {
     pc = source_index(flow, pix, py, px, H, W, scale);
     cubic_w(pc.tx, wx);
     cubic_w(pc.ty, wy);
     if constexpr (BWD) { cubic_dw(pc.tx, dwx); cubic_dw(pc.ty, dwy); }
-    inwin = pc.x0 - 1 >= wx0 && pc.x0 + 2 < wx0 + kFW && pc.y0 - 1 >= wy0 && pc.y0 + 2 < wy0 + kFH;
+    // footprints entirely outside the image contribute nothing and must not drag the window away
+    if (pc.x0 + 2 >= 0 && pc.x0 - 1 < W && pc.y0 + 2 >= 0 && pc.y0 - 1 < H) { mx = pc.x0; my = pc.y0; }
   }
+  mx = __reduce_min_sync(0xffffffffu, mx);
+  my = __reduce_min_sync(0xffffffffu, my);
+  if ((threadIdx.x & 31) == 0) { atomicMin(org + 0, mx); atomicMin(org + 1, my); }
+  __syncthreads();
+  const int wx0 = min(max(org[0] - 1, -4), W), wy0 = min(max(org[1] - 1, -4), H);
+  const bool inwin = live && pc.x0 - 1 >= wx0 && pc.x0 + 2 < wx0 + kFW && pc.y0 - 1 >= wy0 && pc.y0 + 2 < wy0 + kFH;
   float gix = 0.f, giy = 0.f;
   for (int c0 = 0; c0 < C; c0 += CC) {
     if (c0) __syncthreads();                             // everyone is done with the previous chunk
@@ -557,34 +565,45 @@ __device__ __forceinline__ float cubic_k(float d) {
   return fmaf(fmaf(fmaf(c3, d, c2), d, c1), d, c0);
 }
 
-// Pre-pass: integer displacement range of the whole field (see tiled_ok).  bounds pre-set to a very
-// negative value (memset 0x80).
+// Pre-pass: per SOURCE tile, the bounding box of the output pixels whose 4x4 footprint touches it.
+// bbox[tile] = {max(-p.x), max(p.x), max(-p.y), max(p.y)}, pre-set very negative (memset 0x80).  A warp
+// (32 pixels of a row) aggregates by source tile before the atomics.
 __global__ void __launch_bounds__(256)
-warp_bounds_kernel(const float* __restrict__ flow, int N, int H, int W, float scale, int* __restrict__ bounds) {
+warp_bbox_kernel(const float* __restrict__ flow, int N, int H, int W, float scale, int* __restrict__ bbox) {
+  const int tiles_x = (W + kTW - 1) / kTW, tiles_y = (H + kTH - 1) / kTH;
   const int64_t npix = (int64_t)N * H * W;
-  int m0 = INT_MIN, m1 = INT_MIN, m2 = INT_MIN, m3 = INT_MIN;
-  for (int64_t pix = blockIdx.x * 256LL + threadIdx.x; pix < npix; pix += (int64_t)gridDim.x * 256) {
-    const int w = (int)(pix % W);
-    const int h = (int)((pix / W) % H);
-    const PixCoord pc = source_index(flow, pix, h, w, H, W, scale);
-    const int ex = pc.x0 - w, ey = pc.y0 - h;
-    m0 = max(m0, -ex); m1 = max(m1, ex); m2 = max(m2, -ey); m3 = max(m3, ey);
-  }
-  m0 = __reduce_max_sync(0xffffffffu, m0); m1 = __reduce_max_sync(0xffffffffu, m1);
-  m2 = __reduce_max_sync(0xffffffffu, m2); m3 = __reduce_max_sync(0xffffffffu, m3);
-  if ((threadIdx.x & 31) == 0) {
-    if (m0 > INT_MIN) atomicMax(bounds + 0, m0);
-    if (m1 > INT_MIN) atomicMax(bounds + 1, m1);
-    if (m2 > INT_MIN) atomicMax(bounds + 2, m2);
-    if (m3 > INT_MIN) atomicMax(bounds + 3, m3);
+  const int64_t npix_pad = (npix + 31) / 32 * 32;
+  for (int64_t pix = blockIdx.x * 256LL + threadIdx.x; pix < npix_pad; pix += (int64_t)gridDim.x * 256) {
+    const bool live = pix < npix;
+    int w = 0, h = 0, b = 0, fx0 = 1, fx1 = 0, fy0 = 1, fy1 = 0;      // empty footprint
+    if (live) {
+      w = (int)(pix % W); h = (int)((pix / W) % H); b = (int)(pix / ((int64_t)W * H));
+      const PixCoord pc = source_index(flow, pix, h, w, H, W, scale);
+      fx0 = max(pc.x0 - 1, 0); fx1 = min(pc.x0 + 2, W - 1);
+      fy0 = max(pc.y0 - 1, 0); fy1 = min(pc.y0 + 2, H - 1);
+    }
+    const bool any = fx0 <= fx1 && fy0 <= fy1;
+    const int tx0 = fx0 / kTW, tx1 = fx1 / kTW, ty0 = fy0 / kTH, ty1 = fy1 / kTH;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int tx = (k & 1) ? tx1 : tx0, ty = (k & 2) ? ty1 : ty0;
+      const bool dup = ((k & 1) && tx1 == tx0) || ((k & 2) && ty1 == ty0);
+      const int id = (any && !dup) ? (b * tiles_y + ty) * tiles_x + tx : -1;
+      const unsigned grp = __match_any_sync(0xffffffffu, id);
+      const int a0 = __reduce_max_sync(grp, -w), a1 = __reduce_max_sync(grp, w);
+      const int a2 = __reduce_max_sync(grp, -h), a3 = __reduce_max_sync(grp, h);
+      if (id >= 0 && (int)(threadIdx.x & 31) == __ffs(grp) - 1) {
+        int* bb = bbox + (int64_t)id * 4;
+        atomicMax(bb + 0, a0); atomicMax(bb + 1, a1); atomicMax(bb + 2, a2); atomicMax(bb + 3, a3);
+      }
+    }
   }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(kTileThreads, 2)
 warp_tile_dx_kernel(const float* __restrict__ flow, const T* __restrict__ g, T* __restrict__ dx,
-                    const int* __restrict__ bounds, int H, int W, int C, float scale) {
-  if (!tiled_ok(bounds)) return;                         // the atomic kernels take over
+                    const int* __restrict__ bbox, int* __restrict__ flag, int H, int W, int C, float scale) {
   constexpr int CC = 64 / sizeof(T);
   extern __shared__ __align__(16) unsigned char smem[];
   unsigned char* gwin = smem;
@@ -592,69 +611,85 @@ warp_tile_dx_kernel(const float* __restrict__ flow, const T* __restrict__ g, T* 
   int* lb = reinterpret_cast<int*>(smem + kBW * kBH * (kPixB + 8));
   const int tiles_x = (W + kTW - 1) / kTW, tiles_y = (H + kTH - 1) / kTH;
   int t = blockIdx.x;
+  const int* bb = bbox + (int64_t)t * 4;
   const int tx = t % tiles_x; t /= tiles_x;
   const int ty = t % tiles_y;
   const int b = t / tiles_y;
   const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
   const int px = tx * kTW + lx, py = ty * kTH + ly;
   const bool live = px < W && py < H;
-  const int wx0 = tx * kTW - kRB, wy0 = ty * kTH - kRB;
-  const T* gimg = g + (int64_t)b * H * W * C;
-  if (threadIdx.x < 4) lb[threadIdx.x] = INT_MIN;
-  __syncthreads();
-  // sample positions of the window's output pixels + the tile-local displacement range
-  int m0 = INT_MIN, m1 = INT_MIN, m2 = INT_MIN, m3 = INT_MIN;
-  for (int i = threadIdx.x; i < kBW * kBH; i += kTileThreads) {
-    const int q = i % kBW, r = i / kBW;
-    const int yy = wy0 + r, xx = wx0 + q;
-    float2 c = make_float2(-1e8f, -1e8f);
-    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-      const PixCoord pc = source_index(flow, ((int64_t)b * H + yy) * W + xx, yy, xx, H, W, scale);
-      c = make_float2(pc.ix, pc.iy);
-      const int ex = pc.x0 - xx, ey = pc.y0 - yy;
-      m0 = max(m0, -ex); m1 = max(m1, ex); m2 = max(m2, -ey); m3 = max(m3, ey);
-    }
-    coord[i] = c;
-  }
-  m0 = __reduce_max_sync(0xffffffffu, m0); m1 = __reduce_max_sync(0xffffffffu, m1);
-  m2 = __reduce_max_sync(0xffffffffu, m2); m3 = __reduce_max_sync(0xffffffffu, m3);
-  if (lx == 0) { atomicMax(lb + 0, m0); atomicMax(lb + 1, m1); atomicMax(lb + 2, m2); atomicMax(lb + 3, m3); }
-  __syncthreads();
-  // contributors of s: p = s + o, o in [-e_max - 2, -e_min + 1] (inside the window by tiled_ok)
-  const int ox0 = max(-lb[1] - 2, -kRB), ox1 = min(lb[0] + 1, kRB);
-  const int oy0 = max(-lb[3] - 2, -kRB), oy1 = min(lb[2] + 1, kRB);
-  const float sxf = (float)px, syf = (float)py;
   const int64_t pix = ((int64_t)b * H + py) * W + px;
+  const T* gimg = g + (int64_t)b * H * W * C;
+  // bounding box of the contributing output pixels
+  const int bx0 = -bb[0], bx1 = bb[1], by0 = -bb[2], by1 = bb[3];
+  const bool empty = bb[1] < 0 || bb[3] < 0;                 // still at the memset value: nothing reaches the tile
+  const int nwx = empty ? 0 : (bx1 - bx0 + kBW) / kBW, nwy = empty ? 0 : (by1 - by0 + kBH) / kBH;
+  if (nwx * nwy > kMaxWindows) {                             // rough flow: the scatter kernels redo the tensor
+    if (threadIdx.x == 0) atomicExch(flag, 1);
+    return;
+  }
+  const float sxf = (float)px, syf = (float)py;
   for (int c0 = 0; c0 < C; c0 += CC) {
-    if (c0) __syncthreads();
-    load_window<T, kBW, kBH, kPixB, kTileThreads, true>(gwin, gimg, H, W, C, c0, wy0, wx0);
-    cp_async_wait_all();
-    __syncthreads();
-    if (!live) continue;
     float acc[CC];
 #pragma unroll
     for (int i = 0; i < CC; ++i) acc[i] = 0.f;
-    for (int oy = oy0; oy <= oy1; ++oy) {
-      const int rowi = (ly + kRB + oy) * kBW + lx + kRB;
-      for (int ox = ox0; ox <= ox1; ++ox) {
-        const float2 c = coord[rowi + ox];
-        const float ddx = fabsf(sxf - c.x), ddy = fabsf(syf - c.y);
-        if (ddx < 2.f && ddy < 2.f) fma_chunk_win<T>(gwin, rowi + ox, cubic_k(ddx) * cubic_k(ddy), acc);
+    for (int wi = 0; wi < nwx * nwy; ++wi) {
+      const int wx0 = bx0 + (wi % nwx) * kBW, wy0 = by0 + (wi / nwx) * kBH;
+      __syncthreads();                                       // previous window fully consumed
+      load_window<T, kBW, kBH, kPixB, kTileThreads, true>(gwin, gimg, H, W, C, c0, wy0, wx0);
+      if (c0 == 0 || nwx * nwy > 1) {
+        // sample positions of the window's output pixels + their integer displacement range
+        if (threadIdx.x < 4) lb[threadIdx.x] = INT_MIN;
+        __syncthreads();
+        int m0 = INT_MIN, m1 = INT_MIN, m2 = INT_MIN, m3 = INT_MIN;
+        for (int i = threadIdx.x; i < kBW * kBH; i += kTileThreads) {
+          const int q = i % kBW, r = i / kBW;
+          const int yy = wy0 + r, xx = wx0 + q;
+          float2 c = make_float2(-1e8f, -1e8f);
+          if (yy >= 0 && yy < H && xx >= 0 && xx < W && xx <= bx1 && yy <= by1) {
+            const PixCoord pc = source_index(flow, ((int64_t)b * H + yy) * W + xx, yy, xx, H, W, scale);
+            // only samples that can reach this tile take part in the candidate range
+            if (pc.ix > (float)(tx * kTW - 2) && pc.ix < (float)(tx * kTW + kTW + 1) &&
+                pc.iy > (float)(ty * kTH - 2) && pc.iy < (float)(ty * kTH + kTH + 1)) {
+              c = make_float2(pc.ix, pc.iy);
+              const int ex = pc.x0 - xx, ey = pc.y0 - yy;
+              m0 = max(m0, -ex); m1 = max(m1, ex); m2 = max(m2, -ey); m3 = max(m3, ey);
+            }
+          }
+          coord[i] = c;
+        }
+        m0 = __reduce_max_sync(0xffffffffu, m0); m1 = __reduce_max_sync(0xffffffffu, m1);
+        m2 = __reduce_max_sync(0xffffffffu, m2); m3 = __reduce_max_sync(0xffffffffu, m3);
+        if (lx == 0) { atomicMax(lb + 0, m0); atomicMax(lb + 1, m1); atomicMax(lb + 2, m2); atomicMax(lb + 3, m3); }
+      }
+      cp_async_wait_all();
+      __syncthreads();
+      if (!live || lb[1] == INT_MIN) continue;               // no sample of this window reaches the tile
+      // contributors of s: p in [s - e_max - 2, s - e_min + 1], clipped to the window
+      const int qx0 = max(px - lb[1] - 2 - wx0, 0), qx1 = min(px + lb[0] + 1 - wx0, kBW - 1);
+      const int qy0 = max(py - lb[3] - 2 - wy0, 0), qy1 = min(py + lb[2] + 1 - wy0, kBH - 1);
+      for (int qy = qy0; qy <= qy1; ++qy) {
+        for (int qx = qx0; qx <= qx1; ++qx) {
+          const int qi = qy * kBW + qx;
+          const float2 c = coord[qi];
+          const float ddx = fabsf(sxf - c.x), ddy = fabsf(syf - c.y);
+          if (ddx < 2.f && ddy < 2.f) fma_chunk_win<T>(gwin, qi, cubic_k(ddx) * cubic_k(ddy), acc);
+        }
       }
     }
-    store_chunk<T>(dx + pix * C + c0, acc);
+    if (live) store_chunk<T>(dx + pix * C + c0, acc);
   }
 }
 
 __global__ void __launch_bounds__(256)
-zero_unless_tiled_kernel(float4* __restrict__ p, int64_t n4, const int* __restrict__ bounds) {
-  if (bounds && tiled_ok(bounds)) return;
+zero_unless_tiled_kernel(float4* __restrict__ p, int64_t n4, const int* __restrict__ flag) {
+  if (flag && tiled_ok(flag)) return;
   for (int64_t i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256)
     p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 __global__ void __launch_bounds__(256)
-cast_unless_tiled_kernel(const float4* __restrict__ in, bf16* __restrict__ out, int64_t n4, const int* __restrict__ bounds) {
-  if (bounds && tiled_ok(bounds)) return;
+cast_unless_tiled_kernel(const float4* __restrict__ in, bf16* __restrict__ out, int64_t n4, const int* __restrict__ flag) {
+  if (flag && tiled_ok(flag)) return;
   for (int64_t i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
     const float4 v = in[i];
     __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), c = __floats2bfloat162_rn(v.z, v.w);
@@ -782,24 +817,27 @@ extern "C" int lcgan_warp_bwd_tiled(const void* x, const float* flow, const void
   const int* skip = nullptr;
   if (tile_eligible(dt, H, W, C)) {
     LCGAN_CHECK(tile_kernels_ready() == 0, "warp_bwd_tiled: cannot opt in to %d bytes of shared memory", kDxSmem);
-    LCGAN_CUDA(cudaMemsetAsync(ws_bounds, 0x80, 4 * sizeof(int), s));
+    const int tiles = N * ((H + kTH - 1) / kTH) * ((W + kTW - 1) / kTW);
+    int* bbox = ws_bounds;                                // [tiles][4]
+    int* flag = ws_bounds + (size_t)tiles * 4;            // raised by the dx kernel when a tile's box is too large
+    LCGAN_CUDA(cudaMemsetAsync(bbox, 0x80, (size_t)tiles * 4 * sizeof(int), s));
+    LCGAN_CUDA(cudaMemsetAsync(flag, 0, 4 * sizeof(int), s));
     const int64_t npix = (int64_t)N * H * W;
     const int bgrid = (int)(npix / 256 + 1 < 148LL * 8 ? npix / 256 + 1 : 148LL * 8);
-    warp_bounds_kernel<<<bgrid, 256, 0, s>>>(flow, N, H, W, flow_scale, ws_bounds);
-    const int tiles = N * ((H + kTH - 1) / kTH) * ((W + kTW - 1) / kTW);
+    warp_bbox_kernel<<<bgrid, 256, 0, s>>>(flow, N, H, W, flow_scale, bbox);
     if (dt == LCGAN_BF16) {
       warp_tile_gather_kernel<bf16, true><<<tiles, kTileThreads, kFwdSmem, s>>>(
           (const bf16*)x, flow, (const bf16*)dout, nullptr, dflow, H, W, C, flow_scale);
-      warp_tile_dx_kernel<bf16><<<tiles, kTileThreads, kDxSmem, s>>>(flow, (const bf16*)dout, (bf16*)dx, ws_bounds,
+      warp_tile_dx_kernel<bf16><<<tiles, kTileThreads, kDxSmem, s>>>(flow, (const bf16*)dout, (bf16*)dx, bbox, flag,
                                                                     H, W, C, flow_scale);
     } else {
       warp_tile_gather_kernel<float, true><<<tiles, kTileThreads, kFwdSmem, s>>>(
           (const float*)x, flow, (const float*)dout, nullptr, dflow, H, W, C, flow_scale);
-      warp_tile_dx_kernel<float><<<tiles, kTileThreads, kDxSmem, s>>>(flow, (const float*)dout, (float*)dx, ws_bounds,
+      warp_tile_dx_kernel<float><<<tiles, kTileThreads, kDxSmem, s>>>(flow, (const float*)dout, (float*)dx, bbox, flag,
                                                                      H, W, C, flow_scale);
     }
     LCGAN_LAUNCH_CHECK();
-    skip = ws_bounds;                                     // the rest runs only if the flow is too large
+    skip = flag;                                          // the rest runs only if a tile gave up
   }
   zero_unless_tiled_kernel<<<egrid, 256, 0, s>>>(reinterpret_cast<float4*>(acc), n4, skip);
   launch_atomic_bwd(x, flow, dout, acc, dflow, dt, N, H, W, C, flow_scale, skip, s);

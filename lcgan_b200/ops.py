@@ -681,7 +681,7 @@ class Warp(torch.autograd.Function):
         dx = torch.empty_like(x)
         # scratch for the large-flow (scatter) path only; small flows never touch it
         ws_acc = None if x.dtype == torch.float32 else torch.empty(x.numel(), dtype=torch.float32, device=x.device)
-        ws_bounds = torch.empty(4, dtype=torch.int32, device=x.device)
+        ws_bounds = torch.empty(4 * n * ((h + 15) // 16) * ((w + 31) // 32) + 4, dtype=torch.int32, device=x.device)
         _lib.call("lcgan_warp_bwd_tiled", _ptr(x), _ptr(flow), _ptr(dout), _ptr(dx), _ptr(dflow), _ptr(ws_acc),
                   _ptr(ws_bounds), _dt(x), n, h, w, c, C.c_float(ctx.scale), _stream(x), tag="warp_bwd",
                   nbytes=3 * x.numel() * x.element_size() + 2 * flow.numel() * 4)

@@ -14,6 +14,8 @@ def timeit(fn, n=5):
     return e0.elapsed_time(e1) / n
 which = sys.argv[1:] or ["fwd32", "wg32", "fwd64", "wg64", "fwd128", "box", "actbwd", "warpf", "warpb"]
 N = 32
+import os
+FS = float(os.environ.get('FLOW_STD', '0.1'))   # tanh(0.1)*0.1*512 = 5 px std, smooth (64-px correlation)
 for w in which:
     if w.startswith("fwd") or w.startswith("wg"):
         C = int(w[3:] if w.startswith("fwd") else w[2:]); R = {32: 1024, 64: 512, 128: 256, 256: 128}[C]
@@ -53,9 +55,9 @@ for w in which:
             ms = timeit(lambda: L.call("lcgan_modulate_bwd", ops._ptr(x), ops._ptr(g), ops._ptr(sc), ops._ptr(dx), ops._ptr(ds), ops._dt(x), N, R * R, C, ops._stream(x))); tr = 3 * nb
         elif w == "actbwd": ms = timeit(lambda: ops._act_bwd_raw(g, x, None, 0.2, 1.4, True, False)); tr = 3 * nb
         elif w == "warpf":
-            flow = cl(torch.randn(N, 2, R, R, device=dev) * 0.004); ms = timeit(lambda: ops.Warp.apply(x, flow, 0.1)); tr = 2 * nb
+            flow = cl(torch.nn.functional.interpolate(torch.randn(N, 2, R // 64, R // 64, device=dev) * FS, size=(R, R), mode='bilinear')); ms = timeit(lambda: ops.Warp.apply(x, flow, 0.1)); tr = 2 * nb
         elif w == "warpb":
-            flow = cl(torch.randn(N, 2, R, R, device=dev) * 0.004); xr = x.clone().requires_grad_(); fr = flow.clone().requires_grad_()
+            flow = cl(torch.nn.functional.interpolate(torch.randn(N, 2, R // 64, R // 64, device=dev) * FS, size=(R, R), mode='bilinear')); xr = x.clone().requires_grad_(); fr = flow.clone().requires_grad_()
             out = ops.Warp.apply(xr, fr, 0.1)
             ms = timeit(lambda: torch.autograd.grad(out, (xr, fr), g, retain_graph=True)); tr = 4 * nb
         print(f"{w:8s} {ms:8.3f} ms  {tr/ms/1e6:8.0f} GB/s (algorithmic)")

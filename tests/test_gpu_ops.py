@@ -204,23 +204,25 @@ def test_modulate_and_warp(mode, C):
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
 @pytest.mark.parametrize("case", [
-    # (N, C, H, W, flow std, flow scale): eligible for the shared-memory tiled kernels (C % 32, W >= 32, H >= 16)
-    (2, 32, 48, 80, 0.3, 0.1),      # small flow, ragged tiles: gather kernels everywhere
-    (1, 64, 16, 32, 1.5, 0.1),      # two channel chunks, one tile
-    (2, 32, 40, 64, 1.5, 0.6),      # +-19 px: per-pixel global fallback (fwd/dflow), scatter fallback (dx)
-    (1, 32, 32, 64, 0.6, 0.22),     # ~ +-4 px
-    (1, 32, 32, 64, 1.5, 0.2),      # ~ +-6 px: around the window margins
-    (1, 32, 32, 64, 1.5, 0.26),     # ~ +-7.5 px: mixed
+    # (N, C, H, W, flow std, flow scale, flow mean): eligible for the shared-memory tiled kernels
+    # (C % 32, W >= 32, H >= 16); displacement = tanh(flow) * scale * W/2 pixels
+    (2, 32, 48, 80, 0.3, 0.1, 0.0),      # small flow, ragged tiles: one window per tile
+    (1, 64, 16, 32, 1.5, 0.1, 0.0),      # two channel chunks, one tile
+    (1, 32, 48, 96, 0.05, 0.5, 0.8),     # large SMOOTH flow (~16 px / 8 px): displaced single windows
+    (1, 32, 48, 96, 0.05, 0.9, -1.5),    # ~ -39 px: most samples leave the image
+    (2, 32, 40, 64, 1.5, 0.6, 0.0),      # rough +-19 px: several windows per source tile, per-pixel global fallback
+    (1, 32, 32, 64, 1.5, 0.2, 0.0),      # rough +-6 px
+    (1, 32, 64, 128, 1.5, 0.9, 0.0),     # rough +-57 px: the dx kernel gives up, scatter kernels take over
 ])
 def test_warp_tiled(mode, case):
     ops, _ = _ops()
-    N, C, H, W, fstd, scale = case
+    N, C, H, W, fstd, scale, fmean = case
     dt = torch.float32 if mode == "fp32" else torch.bfloat16
     tol = FP32_TOL * 5 if mode == "fp32" else BF16_TOL
     torch.manual_seed(5)
     x = _cl(torch.randn(N, C, H, W, device="cuda").to(dt))
     g = torch.randn(N, C, H, W, device="cuda").to(dt)
-    flow = _cl(torch.randn(N, 2, H, W, device="cuda") * fstd)
+    flow = _cl(torch.randn(N, 2, H, W, device="cuda") * fstd + fmean)
     xr = x.float().clone().requires_grad_(); fr = flow.clone().requires_grad_()
     xm = x.clone().requires_grad_(); fm = flow.clone().requires_grad_()
     ys = 2 * torch.arange(H, device="cuda", dtype=torch.float32) / (H - 1) - 1
