@@ -155,11 +155,14 @@ box3_tile_kernel(const T* __restrict__ a, const T* __restrict__ mask, T* __restr
   constexpr int kWin = kBoxWW * kBoxWH * 64;
   __shared__ __align__(16) unsigned char sm[MASK ? 2 * kWin : kWin];
   const int tiles_x = (W + kBoxTW - 1) / kBoxTW, tiles_y = (H + TH - 1) / TH;
-  int t = blockIdx.x;
+  // the channel chunks of a tile are neighbouring CTAs (chunk fastest): they run together and read
+  // whole DRAM pages; chunk-major order swept the tensor once per chunk, 64 bytes of every pixel
+  const int nchunk = C / (64 / (int)sizeof(T));
+  int t = blockIdx.x / nchunk;
+  const int c0 = (blockIdx.x % nchunk) * (64 / (int)sizeof(T));
   const int tx = t % tiles_x; t /= tiles_x;
   const int ty = t % tiles_y;
   const int b = t / tiles_y;
-  const int c0 = blockIdx.y * (64 / (int)sizeof(T));
   load_window<T, kBoxWW, kBoxWH, 64, kThreads>(sm, a + (int64_t)b * H * W * C, H, W, C, c0, ty * TH - 1, tx * kBoxTW - 1);
   if constexpr (MASK)   // the activation mask of the backward pass: a is scaled by the leaky-relu slope of mask
     load_window<T, kBoxWW, kBoxWH, 64, kThreads>(sm + kWin, mask + (int64_t)b * H * W * C, H, W, C, c0,
@@ -490,7 +493,7 @@ extern "C" int lcgan_box3(const void* a, const void* mask, void* out, int dt, in
   if ((dt == LCGAN_BF16 || dt == LCGAN_F32) && C % cc == 0 && W >= kBoxTW && H >= kBoxTH &&
       getenv("LCGAN_BOX_NO_TILE") == nullptr) {
     const int th = mask ? 8 : kBoxTH;
-    const dim3 grid(N * ((H + th - 1) / th) * ((W + kBoxTW - 1) / kBoxTW), C / cc);
+    const dim3 grid(N * ((H + th - 1) / th) * ((W + kBoxTW - 1) / kBoxTW) * (C / cc));
 #define BT(T, M, THH)                                                                                     \
   box3_tile_kernel<T, M, THH><<<grid, kThreads, 0, s>>>((const T*)a, (const T*)mask, (T*)out, H, W, C,       \
                                                         pre_slope, pre_gain, post_slope, post_gain)

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(kThreads)
 thin_out_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const void* __restrict__ w, TY* __restrict__ y,
                 const float* __restrict__ rowscale, const float* __restrict__ bias, const TY* __restrict__ residual,
                 int G) {
-  __shared__ __align__(16) float ws[kSmemFloats];          // [o][t][c]
+  extern __shared__ __align__(16) float ws[];               // [o][t][c], sized by the launch (<= kSmemFloats)
   const int tc = d.ntaps * d.Cin;
   for (int i = threadIdx.x; i < d.Cout * tc; i += kThreads) {
     const int o = i / tc, r = i - o * tc, t = r / d.Cin, c = r - t * d.Cin;
@@ -127,7 +127,7 @@ thin_in_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const void* __re
   // are laid out [t][c][quad][o/4] (V%4==0) so that neighbouring threads read neighbouring 16-byte
   // quads - the former [t][c][o] layout with 4 consecutive vectors per thread put the threads of a
   // quarter-warp 128 bytes apart, an 8-way bank conflict on every weight load (measured 0.25 TB/s).
-  __shared__ __align__(16) float ws[kSmemFloats];
+  extern __shared__ __align__(16) float ws[];               // sized by the launch (<= kSmemFloats)
   const int tc = d.ntaps * d.Cin;
   constexpr int Q = V % 4 == 0 ? V / 4 : 1;                 // 16-byte quads per output vector
   const int nvec = d.Cout / V;                              // output vectors per lattice point
@@ -218,7 +218,7 @@ thin_up2_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const void* __r
                 const float* __restrict__ rowscale, const float* __restrict__ bias, int G) {
   // weights [tap 9][o][quad][vector][4]: lane g reads quad q of its vector at a 16-byte lane stride
   // (conflict-free; [t][o][c] put the lanes 32 bytes apart, a 2-way conflict on every weight load)
-  __shared__ __align__(16) float ws[kSmemFloats];
+  extern __shared__ __align__(16) float ws[];               // sized by the launch (<= kSmemFloats)
   constexpr int Q = V % 4 == 0 ? V / 4 : 1, E = V % 4 == 0 ? 4 : 1;
   const int Cin = d.Cin, oc = CO * Cin, cv = Cin / V;
   for (int i = threadIdx.x; i < 9 * oc; i += kThreads) {
@@ -621,6 +621,7 @@ int lcgan_thin_forward(const lcgan_tapconv& d, const void* x, const void* w, voi
   }
   if (rows * (d.Cin <= kMaxThin ? d.Cout : 1) >= (1LL << 31) - (1 << 20)) return -1;   // 32-bit indices below
   // ---- thin-out --------------------------------------------------------------------------
+  const size_t wbytes = (size_t)d.Cout * d.ntaps * d.Cin * sizeof(float);   // weight staging (dynamic smem)
   if (d.Cout <= kMaxThin && d.Cout * d.ntaps * d.Cin <= kSmemFloats) {
     const int vec = xf ? 4 : 8;
     const bool v_ok = dense_inner(d.xs_c, d.xs_w, d.xs_h, d.xs_n, d.Cin, vec) && ((uintptr_t)x % 16 == 0);
@@ -628,7 +629,7 @@ int lcgan_thin_forward(const lcgan_tapconv& d, const void* x, const void* w, voi
     do {                                                                                                    \
       const int G = pow2_group(d.Cin / VV);                                                                 \
       const int grid = grid_cap((rows + kThreads / G - 1) / (kThreads / G), 16);                            \
-      thin_out_kernel<TXT, TYT, VV><<<grid, kThreads, 0, s>>>(d, (const TXT*)x, w, (TYT*)y, rowscale, bias, \
+      thin_out_kernel<TXT, TYT, VV><<<grid, kThreads, wbytes, s>>>(d, (const TXT*)x, w, (TYT*)y, rowscale, bias, \
                                                               (const TYT*)residual, G);                     \
     } while (0)
     if (xf && yf) { if (v_ok) TO(float, float, 4); else TO(float, float, 1); }
@@ -648,11 +649,11 @@ int lcgan_thin_forward(const lcgan_tapconv& d, const void* x, const void* w, voi
     do {                                                                                                    \
       if (VV > 1 && d.Cout % (VV * 4) == 0) {                                                               \
         const int grid = grid_cap((rows * (d.Cout / (VV * 4)) + kThreads - 1) / kThreads, 32);              \
-        thin_in_kernel<TXT, TYT, VV, 4><<<grid, kThreads, 0, s>>>(d, (const TXT*)x, w, (TYT*)y, rowscale,   \
+        thin_in_kernel<TXT, TYT, VV, 4><<<grid, kThreads, wbytes, s>>>(d, (const TXT*)x, w, (TYT*)y, rowscale,   \
                                                                   bias, (const TYT*)residual);              \
       } else {                                                                                              \
         const int grid = grid_cap((rows * (d.Cout / VV) + kThreads - 1) / kThreads, 32);                    \
-        thin_in_kernel<TXT, TYT, VV, 1><<<grid, kThreads, 0, s>>>(d, (const TXT*)x, w, (TYT*)y, rowscale,   \
+        thin_in_kernel<TXT, TYT, VV, 1><<<grid, kThreads, wbytes, s>>>(d, (const TXT*)x, w, (TYT*)y, rowscale,   \
                                                                   bias, (const TYT*)residual);              \
       }                                                                                                     \
     } while (0)
@@ -732,15 +733,16 @@ extern "C" int lcgan_tapconv_up2_thin(const lcgan_tapconv* d, const void* x, con
   cudaStream_t s = (cudaStream_t)stream;
   const bool xf = d->x_dtype == LCGAN_F32, yf = d->y_dtype == LCGAN_F32;
   const int64_t rows = (int64_t)d->N * d->IH * d->IW;
+  const size_t wbytes = (size_t)9 * d->Cout * d->Cin * sizeof(float);
 #define TU(TXT, TYT, VV)                                                                                     \
   do {                                                                                                       \
     const int G = pow2_group(d->Cin / VV);                                                                   \
     const int grid = grid_cap((rows + kThreads / G - 1) / (kThreads / G), 16);                               \
     switch (d->Cout) {                                                                                       \
-      case 1: thin_up2_kernel<TXT, TYT, VV, 1><<<grid, kThreads, 0, s>>>(*d, (const TXT*)x, w2, (TYT*)y, rowscale, bias, G); break; \
-      case 2: thin_up2_kernel<TXT, TYT, VV, 2><<<grid, kThreads, 0, s>>>(*d, (const TXT*)x, w2, (TYT*)y, rowscale, bias, G); break; \
-      case 3: thin_up2_kernel<TXT, TYT, VV, 3><<<grid, kThreads, 0, s>>>(*d, (const TXT*)x, w2, (TYT*)y, rowscale, bias, G); break; \
-      default: thin_up2_kernel<TXT, TYT, VV, 4><<<grid, kThreads, 0, s>>>(*d, (const TXT*)x, w2, (TYT*)y, rowscale, bias, G); break; \
+      case 1: thin_up2_kernel<TXT, TYT, VV, 1><<<grid, kThreads, wbytes, s>>>(*d, (const TXT*)x, w2, (TYT*)y, rowscale, bias, G); break; \
+      case 2: thin_up2_kernel<TXT, TYT, VV, 2><<<grid, kThreads, wbytes, s>>>(*d, (const TXT*)x, w2, (TYT*)y, rowscale, bias, G); break; \
+      case 3: thin_up2_kernel<TXT, TYT, VV, 3><<<grid, kThreads, wbytes, s>>>(*d, (const TXT*)x, w2, (TYT*)y, rowscale, bias, G); break; \
+      default: thin_up2_kernel<TXT, TYT, VV, 4><<<grid, kThreads, wbytes, s>>>(*d, (const TXT*)x, w2, (TYT*)y, rowscale, bias, G); break; \
     }                                                                                                        \
   } while (0)
   if (xf && yf) TU(float, float, 4); else if (xf) TU(float, bf16, 4); else if (yf) TU(bf16, float, 8); else TU(bf16, bf16, 8);
