@@ -29,7 +29,8 @@ __device__ __forceinline__ void stv(T* p, const float* f) {
 
 inline int grid_for(int64_t n) {
   int64_t b = (n + kThreads - 1) / kThreads;
-  const int64_t cap = 148LL * 64;   // grid-stride beyond 64 CTAs per SM
+  static const int per_sm = getenv("LCGAN_GRID_CAP") ? atoi(getenv("LCGAN_GRID_CAP")) : 64;
+  const int64_t cap = 148LL * per_sm;   // grid-stride beyond 64 CTAs per SM
   return (int)(b < cap ? (b > 0 ? b : 1) : cap);
 }
 
@@ -305,7 +306,7 @@ up2box_add_kernel(const T* __restrict__ s, const T* __restrict__ t, T* __restric
 // Epilogue backward with per-(b,c) reductions.  Block = (pixel chunk, b); threads along channels
 // first so loads coalesce; each thread owns one channel vector, keeps V partial sums over its
 // pixels and finishes with one atomic per (b,c).
-template <typename T, int V>
+template <typename T, int V, int STAGES>
 __global__ void __launch_bounds__(kThreads)
 act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ gout,
                const float* __restrict__ d, float* __restrict__ r0, float* __restrict__ r1, int P, int C,
@@ -337,13 +338,13 @@ act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict_
       stv<T, V>(gout + off, g);
     };
     if constexpr (V > 1) {
-      // kStreamStages pixels in flight per thread through cp.async (the loads hold no registers and
+      // STAGES pixels in flight per thread through cp.async (the loads hold no registers and
       // cannot be sunk to their consumers by the compiler, which left a plain unrolled loop at
       // 4.0 TB/s); every thread reads back only the slots it filled itself: no block barrier.
-      __shared__ uint4 stage[kStreamStages][2][kThreads];
+      __shared__ uint4 stage[STAGES][2][kThreads];
       int pl = p;
 #pragma unroll
-      for (int st = 0; st < kStreamStages; ++st, pl += pstep) {
+      for (int st = 0; st < STAGES; ++st, pl += pstep) {
         if (pl < P) {
           cp_async16(&stage[st][0][threadIdx.x], dy + base + (int64_t)pl * C, true);
           cp_async16(&stage[st][1][threadIdx.x], y + base + (int64_t)pl * C, true);
@@ -351,8 +352,8 @@ act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict_
         cp_async_commit();
       }
       for (int it = 0; p < P; p += pstep, pl += pstep, ++it) {
-        cp_async_wait_pending<kStreamStages - 1>();
-        const int st = it % kStreamStages;
+        cp_async_wait_pending<STAGES - 1>();
+        const int st = it % STAGES;
         float g[V], yy[V];
         unpack_raw16<T>(stage[st][0][threadIdx.x], g);
         unpack_raw16<T>(stage[st][1][threadIdx.x], yy);
@@ -561,9 +562,9 @@ extern "C" int lcgan_up2box_add(const void* sk, const void* t, void* out, int dt
   return 0;
 }
 
-static inline int pix_per_block_for(int N, int P) {
+static inline int pix_per_block_for(int N, int P, int blocks_per_sm = 8) {
   // aim for ~8 CTAs per SM overall, at least 64 pixels per block
-  int64_t want_blocks = 148LL * 8;
+  int64_t want_blocks = 148LL * blocks_per_sm;
   int64_t per_b = (want_blocks + N - 1) / N;
   int ppb = (int)((P + per_b - 1) / per_b);
   if (ppb < 64) ppb = 64;
@@ -576,11 +577,20 @@ extern "C" int lcgan_act_bwd(const void* dy, const void* y, void* gout, const fl
   LCGAN_CHECK(slope > 0.f && gain > 0.f, "act_bwd: slope and gain must be positive");
   LCGAN_CHECK(N <= 65535, "act_bwd: batch too large");
   cudaStream_t s = (cudaStream_t)stream;
-  const int ppb = pix_per_block_for(N, P);
+  const char* e_bps = getenv("LCGAN_ACT_BPS");          // tuning knobs (experiments only)
+  const char* e_st = getenv("LCGAN_ACT_STAGES");
+  const int ppb = pix_per_block_for(N, P, e_bps ? atoi(e_bps) : 4);   // one resident wave (measured best: 3-6)
+  const bool deep = e_st && atoi(e_st) == 6;
   dim3 grid(ceil_div(P, ppb), N);
 #define CALL(T, V)                                                                              \
-  act_bwd_kernel<T, V><<<grid, kThreads, 0, s>>>((const T*)dy, (const T*)y, (T*)gout, d, r0, r1, P, C, \
-                                                 slope, gain, ppb)
+  do {                                                                                          \
+    if (deep)                                                                                   \
+      act_bwd_kernel<T, V, 6><<<grid, kThreads, 0, s>>>((const T*)dy, (const T*)y, (T*)gout, d, r0, r1, P, C, \
+                                                        slope, gain, ppb);                      \
+    else                                                                                        \
+      act_bwd_kernel<T, V, kStreamStages><<<grid, kThreads, 0, s>>>((const T*)dy, (const T*)y, (T*)gout, d, r0, \
+                                                                    r1, P, C, slope, gain, ppb); \
+  } while (0)
   DISPATCH_TV(dt, C, CALL);
 #undef CALL
   LCGAN_LAUNCH_CHECK();
@@ -603,7 +613,8 @@ extern "C" int lcgan_modulate_bwd(const void* x, const void* t, const float* sc,
   LCGAN_CHECK(x && t && sc && dx && ds && N > 0 && P > 0 && C > 0, "modulate_bwd: bad arguments");
   LCGAN_CHECK(N <= 65535, "modulate_bwd: batch too large");
   cudaStream_t s = (cudaStream_t)stream;
-  const int ppb = pix_per_block_for(N, P);
+  const char* e_bps = getenv("LCGAN_ACT_BPS");          // tuning knob (experiments only)
+  const int ppb = pix_per_block_for(N, P, e_bps ? atoi(e_bps) : 3);   // measured best: 1-3 (6.0 vs 5.2 TB/s at 8)
   dim3 grid(ceil_div(P, ppb), N);
 #define CALL(T, V)                                                                              \
   modulate_bwd_kernel<T, V><<<grid, kThreads, 0, s>>>((const T*)x, (const T*)t, sc, (T*)dx, ds, P, C, ppb)
