@@ -1,0 +1,63 @@
+"""CPU-side contract checks of bench.py and of the host-side dispatch predicates (no GPU)."""
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    """`bench.py --impl reference` = the oracle port of the reference's CPU path, bounded sample."""
+    env = dict(os.environ, LCGAN_BENCH_RES="32")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1",
+                          "--steps", "2", "--warmup", "1"], capture_output=True, text=True, env=env, timeout=600,
+                         cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "img/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["n_gpus"] == 1 and d["gpu_launches"] == 0
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "oracle" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_reference_arm_is_silent_on_non_zero_ranks():
+    env = dict(os.environ, LCGAN_BENCH_RES="32", RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                         capture_output=True, text=True, env=env, timeout=300, cwd=ROOT)
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_fused_flow_layer_path_is_selected_for_the_x2_thin_layers_only():
+    """Host-side predicate of the all-phase x2 thin kernels (the flow layers, C -> 2)."""
+    import torch
+    from lcgan_b200 import _lib, ops, plans
+
+    class T:                                  # stride/shape carrier (no device memory needed)
+        def __init__(self, shape, strides, dt):
+            self.shape, self._st, self.dtype = shape, strides, dt
+
+        def stride(self):
+            return self._st
+
+    lib = _lib.lib()
+    N, Cin, R = 4, 64, 32
+    x = T((N, Cin, R, R), (Cin * R * R, 1, R * Cin, Cin), torch.bfloat16)             # channels-last
+    w2 = T((2, 9 * Cin), (9 * Cin, 1), torch.bfloat16)
+    plan = plans.conv_transpose_up2(3, R, R)
+    d = ops.TapConvDesc()
+    y = T((N, 2, 2 * R, 2 * R), (8 * R * R, 1, 4 * R, 2), torch.float32)
+    ops._fill_desc(d, plan.launches[0], x, y, Cin, 2, w2, 1.0, 1.0, 1.0, 1.0)
+    assert lib.lcgan_tapconv_up2_thin_eligible(C.byref(d)) == 1
+    y8 = T((N, 8, 2 * R, 2 * R), (32 * R * R, 1, 16 * R, 8), torch.float32)         # 8 output channels: not thin
+    ops._fill_desc(d, plan.launches[0], x, y8, Cin, 8, w2, 1.0, 1.0, 1.0, 1.0)
+    assert lib.lcgan_tapconv_up2_thin_eligible(C.byref(d)) == 0
+    p1 = plans.conv(3, 1, R, R)                                                      # stride-1 conv: not an x2 layer
+    y1 = T((N, 2, R, R), (2 * R * R, 1, 2 * R, 2), torch.float32)
+    ops._fill_desc(d, p1.launches[0], x, y1, Cin, 2, w2, 1.0, 1.0, 1.0, 1.0)
+    assert lib.lcgan_tapconv_up2_thin_eligible(C.byref(d)) == 0
