@@ -58,6 +58,14 @@ int lcgan_version(void);
 /* 1 if the tcgen05 path can take this descriptor (channels-last bf16, Cin%64==0, ...) */
 int lcgan_tapconv_tc_eligible(const lcgan_tapconv* d);
 
+/* lcgan_tapconv_tc with BLOCKED output channels: channel o is stored at element offset
+ * (o / cblk) * ys_blk + o % cblk of its lattice point's output pixel and takes rowscale[b, o % cperiod],
+ * bias[o % cperiod].  Used to run conv_transpose2d(k3, s2, p1, op1) (custom_layers.py:78) as one launch
+ * over the input lattice (4 taps, Cout' = 4 Cout, cblk = 2 Cout, ys_blk = one output row). */
+int lcgan_tapconv_tc_blocked(const lcgan_tapconv* d, const void* x, const void* w2, void* y,
+                             const float* rowscale, const float* bias, int cblk, int64_t ys_blk,
+                             int cperiod, void* stream);
+
 /* conv_transpose2d(k3, s2, p1, op1) with Cout <= 4 (the flow layers, custom_layers.py:78 with C -> 2):
  * all four output phases in one pass over X.  d = the descriptor of phase (0,0) of the x2 plan
  * (N, IH, IW, Cin, Cout, strides, dtypes, w_ld and the epilogue constants are read). */

@@ -65,6 +65,8 @@ _SIGS = {
     "lcgan_tapconv_up2_thin_eligible": ([C.POINTER(TapConvDesc)], C.c_int),
     "lcgan_tapconv_up2_thin": ([C.POINTER(TapConvDesc), _VOIDP, _VOIDP, _VOIDP, _FP, _FP, _VOIDP], C.c_int),
     "lcgan_tapconv_up2_thin_wgrad": ([C.POINTER(TapConvDesc), _VOIDP, _VOIDP, _FP, C.c_float, _VOIDP], C.c_int),
+    "lcgan_tapconv_tc_blocked": ([C.POINTER(TapConvDesc), _VOIDP, _VOIDP, _VOIDP, _FP, _FP, C.c_int, C.c_int64, C.c_int,
+                                  _VOIDP], C.c_int),
     "lcgan_tapconv_simt": ([C.POINTER(TapConvDesc), _VOIDP, _VOIDP, _VOIDP, _FP, _FP, _VOIDP, _VOIDP], C.c_int),
     "lcgan_tapconv_tc": ([C.POINTER(TapConvDesc), _VOIDP, _VOIDP, _VOIDP, _FP, _FP, _VOIDP, _VOIDP], C.c_int),
     "lcgan_tapconv_wgrad_simt": ([C.POINTER(TapConvDesc), _VOIDP, _VOIDP, _FP, C.c_float, _VOIDP], C.c_int),

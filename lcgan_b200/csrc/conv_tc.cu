@@ -45,6 +45,10 @@ struct TcParams {
   long long ys_n, ys_h, ys_w;
   int y_f32;
   float acc_scale, bias_scale, slope, gain;
+  // blocked output channels (lcgan_tapconv_tc_blocked): channel o lands at (o / cblk) * ys_blk + o % cblk
+  // and takes rowscale / bias of channel o % cperiod; cblk == 0: plain channel-innermost output
+  int cblk, cperiod;
+  long long ys_blk;
 };
 
 struct WgParams {
@@ -408,13 +412,17 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
       const int g0 = li * nkb;
       const bool has0 = !ring || nkb > 1 || (g0 & 1) == 0, has1 = ring && (nkb > 1 || (g0 & 1) == 1);
       // 16 accumulator columns -> scale, bias, activation, residual, store
-      auto finish16 = [&](const uint32_t* v, int o) {
-        if (live && o < p.Cout) {
+      auto finish16 = [&](const uint32_t* v, int oc) {
+        if (live && oc < p.Cout) {
+          // o: channel whose rowscale / bias apply; yo: element offset of the chunk inside the pixel
+          const int o = p.cblk ? oc % p.cperiod : oc;
+          const long long yo = p.cblk ? (long long)(oc / p.cblk) * p.ys_blk + oc % p.cblk : oc;
+          const int crow = p.cblk ? p.cperiod : p.Cout;
           float f[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * p.acc_scale;
           if (rowscale) {
-            const float4* rs = reinterpret_cast<const float4*>(rowscale + (long long)b * p.Cout + o);
+            const float4* rs = reinterpret_cast<const float4*>(rowscale + (long long)b * crow + o);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float4 sc = rs[i];
@@ -433,9 +441,9 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = (f[i] > 0.f ? f[i] : f[i] * p.slope) * p.gain;
           if (p.y_f32) {
-            float* yp = reinterpret_cast<float*>(y) + pix + o;
+            float* yp = reinterpret_cast<float*>(y) + pix + yo;
             if (residual) {
-              const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(residual) + pix + o);
+              const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(residual) + pix + yo);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const float4 rr = rp[i];
@@ -446,9 +454,9 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
             for (int i = 0; i < 4; ++i)
               reinterpret_cast<float4*>(yp)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
           } else {
-            bf16* yp = reinterpret_cast<bf16*>(y) + pix + o;
+            bf16* yp = reinterpret_cast<bf16*>(y) + pix + yo;
             if (residual) {
-              const bf16* rp = reinterpret_cast<const bf16*>(residual) + pix + o;
+              const bf16* rp = reinterpret_cast<const bf16*>(residual) + pix + yo;
               Vec16<bf16> r0, r1;
               r0.load(rp); r1.load(rp + 8);
               float g[16];
@@ -810,8 +818,32 @@ extern "C" int lcgan_tapconv_tc_eligible(const lcgan_tapconv* d) {
   return 1;
 }
 
+static int tapconv_tc_launch(const lcgan_tapconv* d, const void* x, const void* w2, void* y, const float* rowscale,
+                             const float* bias, const void* residual, void* stream, int cblk, long long ys_blk,
+                             int cperiod);
+
 extern "C" int lcgan_tapconv_tc(const lcgan_tapconv* d, const void* x, const void* w2, void* y,
                                 const float* rowscale, const float* bias, const void* residual, void* stream) {
+  return tapconv_tc_launch(d, x, w2, y, rowscale, bias, residual, stream, 0, 0, 0);
+}
+
+// Blocked output channels: channel o of the contraction is stored at element offset
+// (o / cblk) * ys_blk + o % cblk of its lattice point's output pixel and uses rowscale / bias of channel
+// o % cperiod (rowscale is [N, cperiod]).  This runs conv_transpose2d(k3, s2, p1, op1) as ONE launch over
+// the input lattice: 4 taps (the 2x2 input neighbourhood), Cout' = 4 Cout with the unused (phase, tap)
+// weight blocks zero, cblk = 2 Cout (the two horizontally adjacent output pixels), ys_blk = one output row.
+extern "C" int lcgan_tapconv_tc_blocked(const lcgan_tapconv* d, const void* x, const void* w2, void* y,
+                                        const float* rowscale, const float* bias, int cblk, int64_t ys_blk,
+                                        int cperiod, void* stream) {
+  LCGAN_CHECK(d && cblk > 0 && cblk % 16 == 0 && cperiod > 0 && cperiod % 16 == 0 && d->Cout % cblk == 0 &&
+              cblk % cperiod == 0 && ys_blk % 8 == 0,
+              "tapconv_tc_blocked: need cblk %% 16 == 0, cperiod %% 16 == 0, cperiod | cblk | Cout, ys_blk %% 8 == 0");
+  return tapconv_tc_launch(d, x, w2, y, rowscale, bias, nullptr, stream, cblk, ys_blk, cperiod);
+}
+
+static int tapconv_tc_launch(const lcgan_tapconv* d, const void* x, const void* w2, void* y, const float* rowscale,
+                             const float* bias, const void* residual, void* stream, int cblk, long long ys_blk,
+                             int cperiod) {
   LCGAN_CHECK(lcgan_tapconv_tc_eligible(d), "tapconv_tc: descriptor not eligible for the tensor-core path");
   LCGAN_CHECK(d->w_dtype == LCGAN_BF16, "tapconv_tc: weights must be bf16");
   LCGAN_CHECK(x && w2 && y, "tapconv_tc: null tensor pointer");
@@ -830,6 +862,7 @@ extern "C" int lcgan_tapconv_tc(const lcgan_tapconv* d, const void* x, const voi
   p.ys_n = d->ys_n; p.ys_h = d->ys_h; p.ys_w = d->ys_w;
   p.y_f32 = d->y_dtype == LCGAN_F32;
   p.acc_scale = d->acc_scale; p.bias_scale = d->bias_scale; p.slope = d->slope; p.gain = d->gain;
+  p.cblk = cblk; p.cperiod = cperiod; p.ys_blk = ys_blk;
 
   // row-shared mode: full 3x3 stride-1 tap set on a 16-wide, 8-tall, single-image tile
   p.rowshare = 0;

@@ -195,6 +195,61 @@ def _shape_tag(fn, d):
             f"x{d.x_dtype}y{d.y_dtype}")
 
 
+# Experimental (off by default, LCGAN_UP2_FUSED=1 or set_up2_fused): memory-bound x2 transposed convs
+# (Cin <= 128) as ONE tensor-core launch over the input lattice instead of four phase launches.
+_UP2_FUSED = os.environ.get("LCGAN_UP2_FUSED", "0") == "1"
+# measured (scratch/up2fused.py, batch 32): 64->32 @512->1024 1.84 -> 1.37 ms; 128->64 @256->512 0.88 -> 0.87 ms
+# (the zero weight blocks cost 16/9 of the MMA work, which only the HBM-bound layers can absorb)
+_UP2_FUSED_MAX_CIN = 64
+
+
+def set_up2_fused(flag: bool):
+    global _UP2_FUSED
+    _UP2_FUSED = bool(flag)
+
+
+def _is_cl_dense(t):
+    n, c, h, w = t.shape
+    return t.stride() == (c * h * w, 1, w * c, c)
+
+
+def _tapconv_up2_fused(lib, d, x, w2, y, plan, rowscale, bias, slope, gain, bias_scale, acc_scale, st):
+    """conv_transpose2d(k3, s2, p1, op1) as a 4-tap conv over the input lattice with 4*Cout output channels
+    (phase-major): out(2m+py, 2n+px) = sum_{dy,dx in {0,1}} x[m+dy, n+dx] w[py+1-2dy, px+1-2dx]; the
+    (phase, tap) blocks with a kernel index outside 0..2 are zero.  The epilogue scatters channel block
+    (py, px) to output pixel (2m+py, 2n+px) (lcgan_tapconv_tc_blocked)."""
+    cout, cin = w2.shape[0], x.shape[1]
+    n, _, h, w = x.shape
+    w3 = w2.view(cout, 9, cin)
+    wf = torch.zeros((4 * cout, 4 * cin), dtype=w2.dtype, device=w2.device)
+    for py in (0, 1):
+        for px in (0, 1):
+            for dy in (0, 1):
+                for dx in (0, 1):
+                    ki, kj = py + 1 - 2 * dy, px + 1 - 2 * dx
+                    if 0 <= ki <= 2 and 0 <= kj <= 2:
+                        ph, tap = py * 2 + px, dy * 2 + dx
+                        wf[ph * cout:(ph + 1) * cout, tap * cin:(tap + 1) * cin] = w3[:, ki * 3 + kj, :]
+    d.N, d.IH, d.IW, d.Cin = n, h, w, cin
+    d.OH, d.OW, d.Cout = h, w, 4 * cout
+    d.xs_n, d.xs_h, d.xs_w, d.xs_c = _strides_nhwc(x)
+    ysn, ysh, ysw, ysc = _strides_nhwc(y)
+    d.ys_n, d.ys_h, d.ys_w, d.ys_c = ysn, 2 * ysh, 2 * ysw, 1
+    d.x_dtype, d.y_dtype, d.w_dtype = _dt(x), _dt(y), _dt(wf)
+    d.MH, d.MW, d.os, d.py, d.px, d.is_ = h, w, 1, 0, 0, 1
+    d.ntaps = 4
+    for t, (dy, dx) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
+        d.dy[t], d.dx[t], d.wtap[t] = dy, dx, t
+    d.w_ld = 4 * cin
+    d.acc_scale, d.bias_scale, d.slope, d.gain = acc_scale, bias_scale, slope, gain
+    if not lib.lcgan_tapconv_tc_eligible(C.byref(d)):
+        raise RuntimeError("fused x2 transposed conv: descriptor not eligible for the tensor-core path")
+    _lib.call("lcgan_tapconv_tc_blocked", C.byref(d), _ptr(x), _ptr(wf), _ptr(y), _ptr(rowscale), _ptr(bias),
+              2 * cout, C.c_int64(ysh), cout, st, tag=_shape_tag("lcgan_tapconv_tc_up2fused", d),
+              flops=2.0 * n * h * w * 9 * cin * cout,
+              nbytes=x.numel() * x.element_size() + y.numel() * y.element_size())
+
+
 def tapconv(x, w2, y, plan: plans.Plan, rowscale=None, bias=None, residual=None, slope=1.0, gain=1.0,
             bias_scale=1.0, acc_scale=1.0):
     """y = epilogue(tapconv(x, w2)) for every launch of the plan; x, y logical NCHW."""
@@ -208,6 +263,11 @@ def tapconv(x, w2, y, plan: plans.Plan, rowscale=None, bias=None, residual=None,
     lib = _lib.lib()
     st = _stream(x)
     d = TapConvDesc()
+    if (_UP2_FUSED and _USE_TC and len(plan.launches) == 4 and plan.launches[0].os == 2 and residual is None
+            and cout % 16 == 0 and cin % 32 == 0 and cin <= _UP2_FUSED_MAX_CIN and x.dtype == torch.bfloat16
+            and w2.dtype == torch.bfloat16 and _is_cl_dense(x) and _is_cl_dense(y)):
+        _tapconv_up2_fused(lib, d, x, w2, y, plan, rowscale, bias, slope, gain, bias_scale, acc_scale, st)
+        return y
     if len(plan.launches) == 4 and cout <= 4 and residual is None and plan.launches[0].os == 2:
         # x2 transposed conv of a flow layer: one fused launch for the four output phases
         _fill_desc(d, plan.launches[0], x, y, cin, cout, w2, slope, gain, bias_scale, acc_scale)

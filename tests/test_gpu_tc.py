@@ -20,6 +20,8 @@ def _setup():
     yield
     ops.set_tensor_cores(True)
     ops.set_wgrad_tensor_cores(True)
+    ops.set_up2_fused(False)
+    ops._UP2_FUSED_MAX_CIN = 64
 
 
 def _cl(x):
@@ -95,3 +97,33 @@ def test_tc_wgrad_matches_simt(case):
     out = ops.tapconv_wgrad(x, g, plan, Cin, Cout)
     torch.cuda.synchronize()
     assert rel_l2(out, ref) < 1e-5, f"{case}: {rel_l2(out, ref)}"
+
+
+@pytest.mark.parametrize("case", [  # N, Cin, Cout, H, W
+    (2, 64, 32, 16, 16), (1, 128, 64, 8, 16), (3, 32, 16, 16, 8), (2, 64, 32, 64, 64), (5, 32, 32, 4, 4),
+])
+@pytest.mark.parametrize("out_f32", [False, True])
+def test_fused_up2_matches_four_phase_path(case, out_f32):
+    """Experimental single-launch x2 transposed conv (blocked output channels) against the four phase
+    launches on identical bf16 operands, with every epilogue feature."""
+    from lcgan_b200 import ops, plans, _lib
+    N, Cin, Cout, H, W = case
+    plan = plans.conv_transpose_up2(3, H, W)
+    x = _cl(torch.randn(N, Cin, H, W, device="cuda").bfloat16())
+    w2 = (torch.randn(Cout, 9 * Cin, device="cuda") / (9 * Cin) ** 0.5).bfloat16()
+    rs = torch.rand(N, Cout, device="cuda") + 0.5
+    bias = torch.randn(Cout, device="cuda")
+    dt = torch.float32 if out_f32 else torch.bfloat16
+    outs = []
+    for fused in (False, True):
+        ops.set_up2_fused(fused)
+        ops._UP2_FUSED_MAX_CIN = 128          # exercise the two-n-tile case as well
+        before = _lib.launches
+        y = ops.empty_cl(N, Cout, 2 * H, 2 * W, dt, "cuda").fill_(float("nan"))
+        ops.tapconv(x, w2, y, plan, rs, bias, None, slope=0.2, gain=1.4, bias_scale=0.5)
+        assert _lib.launches - before == (1 if fused else 4)
+        outs.append(y.float())
+    torch.cuda.synchronize()
+    a, b = outs
+    assert torch.isfinite(b).all()
+    assert rel_l2(b, a) < (1e-5 if out_f32 else 4e-3), f"{case}: {rel_l2(b, a)}"
