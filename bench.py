@@ -380,32 +380,51 @@ def roofline_pass(step_fn, it0, _lib, pk):
         step_fn(it0 + i)
     torch.cuda.synchronize()
     stats = _lib.profile_end()
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp))
+    return summarise_kernels(stats, pk, traffic)
+
+
+def summarise_kernels(stats, pk, traffic_table):
+    """stats: {kernel: {n, ms, flops, bytes}} from the instrumented cycle -> (roofline object of the
+    dominant kernel, the 12 heaviest kernels).  A tap-conv kernel is held against the tensor peak, every
+    other kernel against the HBM peak; `hbm_top` adds the heaviest memory-bound kernel when the dominant
+    one is a tensor-core kernel."""
     rows = []
     for name, s in stats.items():
         rows.append({"kernel": name, "launches": s["n"], "ms": s["ms"], "tflops": (s["flops"] / (s["ms"] / 1e3) / 1e12)
                      if s["flops"] and s["ms"] > 0 else None,
                      "gbs": (s["bytes"] / (s["ms"] / 1e3) / 1e9) if s["bytes"] and s["ms"] > 0 else None})
+    if not rows:
+        return None, []
     rows.sort(key=lambda r: -r["ms"])
     total = sum(r["ms"] for r in rows) or 1.0
     for r in rows:
         r["share"] = r["ms"] / total
+
+    def hbm_obj(r):
+        s = stats[r["kernel"]]
+        return {"kernel": r["kernel"], "bound": "hbm", "achieved": r["gbs"], "peak": pk["hbm"], "unit": "GB/s",
+                "frac": (r["gbs"] or 0) / pk["hbm"], "traffic": traffic_table.get(r["kernel"]),
+                "peak_source": pk["src"], "avg_launch_ms": s["ms"] / max(s["n"], 1), "share_of_step": r["share"],
+                "bytes_per_launch": s["bytes"] / max(s["n"], 1)}
+
     top = rows[0]
     s = stats[top["kernel"]]
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(top["kernel"])
     if top["tflops"] is not None and "tapconv" in top["kernel"]:
         roof = {"kernel": top["kernel"], "bound": "tensor", "achieved": top["tflops"], "peak": pk["tensor_sustained"],
-                "unit": "TFLOP/s", "frac": top["tflops"] / pk["tensor_sustained"], "traffic": traffic,
+                "unit": "TFLOP/s", "frac": top["tflops"] / pk["tensor_sustained"],
+                "traffic": traffic_table.get(top["kernel"]),
                 "peak_source": pk["src"] + " (sustained: kernel timed inside a long step)",
-                "avg_launch_ms": s["ms"] / s["n"], "share_of_step": top["share"],
-                "flop_per_launch": s["flops"] / s["n"]}
+                "avg_launch_ms": s["ms"] / max(s["n"], 1), "share_of_step": top["share"],
+                "flop_per_launch": s["flops"] / max(s["n"], 1)}
+        mem = [r for r in rows if r["tflops"] is None and r["gbs"] is not None]
+        if mem:
+            roof["hbm_top"] = hbm_obj(mem[0])
     else:
-        roof = {"kernel": top["kernel"], "bound": "hbm", "achieved": top["gbs"], "peak": pk["hbm"], "unit": "GB/s",
-                "frac": (top["gbs"] or 0) / pk["hbm"], "traffic": traffic, "peak_source": pk["src"],
-                "avg_launch_ms": s["ms"] / s["n"], "share_of_step": top["share"],
-                "bytes_per_launch": s["bytes"] / s["n"]}
+        roof = hbm_obj(top)
     return roof, rows[:12]
 
 

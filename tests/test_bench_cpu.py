@@ -61,3 +61,24 @@ def test_fused_flow_layer_path_is_selected_for_the_x2_thin_layers_only():
     y1 = T((N, 2, R, R), (2 * R * R, 1, 2 * R, 2), torch.float32)
     ops._fill_desc(d, p1.launches[0], x, y1, Cin, 2, w2, 1.0, 1.0, 1.0, 1.0)
     assert lib.lcgan_tapconv_up2_thin_eligible(C.byref(d)) == 0
+
+
+def test_roofline_summary_of_an_instrumented_cycle():
+    sys.path.insert(0, ROOT)
+    import bench
+    pk = {"hbm": 6500.0, "tensor_burst": 1600.0, "tensor_sustained": 1400.0, "src": "measured"}
+    stats = {"tapconv_tc": {"n": 10, "ms": 20.0, "flops": 1.0e13, "bytes": 4.0e10},
+             "act_bwd": {"n": 5, "ms": 10.0, "flops": 0, "bytes": 5.0e10},
+             "skinny": {"n": 3, "ms": 0.0, "flops": 0, "bytes": 0}}
+    roof, rows = bench.summarise_kernels(stats, pk, {"tapconv_tc": 4.2e9})
+    assert roof["kernel"] == "tapconv_tc" and roof["bound"] == "tensor" and roof["traffic"] == 4.2e9
+    assert abs(roof["achieved"] - 500.0) < 1e-6 and abs(roof["frac"] - 500.0 / 1400.0) < 1e-9
+    assert roof["hbm_top"]["kernel"] == "act_bwd" and abs(roof["hbm_top"]["achieved"] - 5000.0) < 1e-6
+    assert [r["kernel"] for r in rows] == ["tapconv_tc", "act_bwd", "skinny"]
+    assert abs(sum(r["share"] for r in rows) - 1.0) < 1e-9
+    # a memory-bound kernel on top
+    stats["act_bwd"]["ms"] = 40.0
+    roof, _ = bench.summarise_kernels(stats, pk, {})
+    assert roof["kernel"] == "act_bwd" and roof["bound"] == "hbm" and roof["traffic"] is None
+    assert bench.summarise_kernels({}, pk, {}) == (None, [])
+    json.dumps(roof)
