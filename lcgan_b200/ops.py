@@ -213,13 +213,10 @@ def _is_cl_dense(t):
     return t.stride() == (c * h * w, 1, w * c, c)
 
 
-def _tapconv_up2_fused(lib, d, x, w2, y, plan, rowscale, bias, slope, gain, bias_scale, acc_scale, st):
-    """conv_transpose2d(k3, s2, p1, op1) as a 4-tap conv over the input lattice with 4*Cout output channels
-    (phase-major): out(2m+py, 2n+px) = sum_{dy,dx in {0,1}} x[m+dy, n+dx] w[py+1-2dy, px+1-2dx]; the
-    (phase, tap) blocks with a kernel index outside 0..2 are zero.  The epilogue scatters channel block
-    (py, px) to output pixel (2m+py, 2n+px) (lcgan_tapconv_tc_blocked)."""
-    cout, cin = w2.shape[0], x.shape[1]
-    n, _, h, w = x.shape
+def fused_up2_weights(w2: torch.Tensor, cin: int) -> torch.Tensor:
+    """W2 [Cout][9*Cin] of a 3x3 x2 transposed conv -> W' [4*Cout][4*Cin]: row (py*2+px)*Cout + o, column
+    (dy*2+dx)*Cin + c holds w[o, c, py+1-2dy, px+1-2dx] (zero when that kernel index is outside 0..2)."""
+    cout = w2.shape[0]
     w3 = w2.view(cout, 9, cin)
     wf = torch.zeros((4 * cout, 4 * cin), dtype=w2.dtype, device=w2.device)
     for py in (0, 1):
@@ -230,6 +227,17 @@ def _tapconv_up2_fused(lib, d, x, w2, y, plan, rowscale, bias, slope, gain, bias
                     if 0 <= ki <= 2 and 0 <= kj <= 2:
                         ph, tap = py * 2 + px, dy * 2 + dx
                         wf[ph * cout:(ph + 1) * cout, tap * cin:(tap + 1) * cin] = w3[:, ki * 3 + kj, :]
+    return wf
+
+
+def _tapconv_up2_fused(lib, d, x, w2, y, plan, rowscale, bias, slope, gain, bias_scale, acc_scale, st):
+    """conv_transpose2d(k3, s2, p1, op1) as a 4-tap conv over the input lattice with 4*Cout output channels
+    (phase-major): out(2m+py, 2n+px) = sum_{dy,dx in {0,1}} x[m+dy, n+dx] w[py+1-2dy, px+1-2dx]; the
+    (phase, tap) blocks with a kernel index outside 0..2 are zero.  The epilogue scatters channel block
+    (py, px) to output pixel (2m+py, 2n+px) (lcgan_tapconv_tc_blocked)."""
+    cout, cin = w2.shape[0], x.shape[1]
+    n, _, h, w = x.shape
+    wf = fused_up2_weights(w2, cin)
     d.N, d.IH, d.IW, d.Cin = n, h, w, cin
     d.OH, d.OW, d.Cout = h, w, 4 * cout
     d.xs_n, d.xs_h, d.xs_w, d.xs_c = _strides_nhwc(x)

@@ -74,3 +74,27 @@ def test_macs_model_counts_transposed_conv_without_zero_insert():
     # 2.25 * Cin * Cout MAC per output pixel
     p = plans.conv_transpose_up2(3, 16, 16)
     assert plans.macs(p, 1, 1, 1) == int(2.25 * 32 * 32)
+
+
+def test_fused_up2_weight_layout_reproduces_conv_transpose():
+    """The single-launch form of the x2 transposed conv (ops.fused_up2_weights + blocked output channels):
+    a 4-tap conv over the input lattice with 4*Cout phase-major channels equals F.conv_transpose2d."""
+    import torch.nn.functional as F
+    from lcgan_b200 import ops
+    torch.manual_seed(0)
+    N, Cin, Cout, H, W = 2, 5, 3, 4, 6
+    x = torch.randn(N, Cin, H, W, dtype=torch.float64)
+    w = torch.randn(Cout, Cin, 3, 3, dtype=torch.float64)
+    ref = F.conv_transpose2d(x, w.transpose(0, 1), stride=2, padding=1, output_padding=1)
+    w2 = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin)                       # pack_weight layout [o][t*Cin + c]
+    wf = ops.fused_up2_weights(w2, Cin).view(4, Cout, 4, Cin)               # [phase][o][tap][c]
+    xp = F.pad(x, (0, 1, 0, 1))                                             # taps read x[m+dy, n+dx], zero beyond
+    out = torch.zeros(N, Cout, 2 * H, 2 * W, dtype=torch.float64)
+    for py in (0, 1):
+        for px in (0, 1):
+            acc = torch.zeros(N, Cout, H, W, dtype=torch.float64)
+            for dy in (0, 1):
+                for dx in (0, 1):
+                    acc += torch.einsum("nchw,oc->nohw", xp[:, :, dy:dy + H, dx:dx + W], wf[py * 2 + px, :, dy * 2 + dx, :])
+            out[:, :, py::2, px::2] = acc
+    assert torch.allclose(out, ref, atol=1e-12)
