@@ -187,7 +187,7 @@ def main():
     import torch.distributed as dist
     import __graft_entry__ as entry
     from lcgan_b200 import _lib, cnn, ops, train_step as T
-    from oracle.lcgan_oracle import Config, Hyper   # configuration containers only (no compute)
+    from lcgan_b200.config import Config, Hyper
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -31,7 +31,8 @@ extern "C" {
  *   for a lattice point (b, m, n), m < MH, n < MW:
  *     out pixel (oy, ox) = (m*os + py, n*os + px)
  *     acc[o] = sum_t sum_c  X[b, m*is + dy[t], n*is + dx[t], c] * W2[o][wtap[t]*Cin + c]
- *     Y[b, oy, ox, o] = lrelu(acc[o]*acc_scale*rowscale[b,o] + bias[o]*bias_scale, slope) * gain + R[b,oy,ox,o]
+ *     Y[b, oy, ox, o] = lrelu(acc[o]*acc_scale*rowscale[b,o] + bias[o]*bias_scale + noise[oy,ox]*noise_scale, slope) * gain
+ *                       + R[b,oy,ox,o]
  *   out-of-range input pixels read as zero.
  *
  * X and Y are addressed with explicit element strides, so NCHW fp32 images and channels-last bf16
@@ -51,6 +52,10 @@ typedef struct lcgan_tapconv {
   int64_t w_ld;                    /* row stride (elements) of W2[Cout][w_ld] */
   float acc_scale;                 /* equalized-lr constant c (weights are packed unscaled) */
   float bias_scale, slope, gain;   /* slope = 1 -> no activation */
+  const float* noise;              /* optional f32 plane [OH][OW] (device) added before the activation:
+                                      + noise[oy][ox] * noise_scale - the noise injection of
+                                      custom_layers.py:108-110; NULL = none */
+  float noise_scale;
 } lcgan_tapconv;
 
 const char* lcgan_last_error(void);
@@ -166,9 +171,44 @@ int lcgan_sumsq(const float* x, float* out, int B, int64_t L, void* stream);
 /* y[b,i] = x[b,i] * s[b]  (backward of sumsq) */
 int lcgan_rowscale(const float* x, const float* s, float* y, int B, int64_t L, void* stream);
 
-/* multi-tensor EMA (ema.py:26-32): dst = src + decay*(dst - src) over n contiguous f32 spans */
+/* multi-tensor EMA (ema.py:26-32): dst = src + decay*(dst - src) over n contiguous f32 spans.
+ * decay_dev (device scalar, may be NULL) overrides `decay`: a captured CUDA graph can then follow the
+ * ema.py:19-23 start_iter schedule without re-capture. */
 int lcgan_ema_lerp(float* const* dst, const float* const* src, const int64_t* numel, int n,
-                   float decay, void* stream); /* dst/src/numel are DEVICE arrays of length n */
+                   float decay, const float* decay_dev, void* stream); /* dst/src/numel: DEVICE arrays of length n */
+
+/* ---- multi-tensor optimizer step and weight packing (optim.cu) ------------------------------- */
+#define LCGAN_MT_MAX 48
+/* Up to LCGAN_MT_MAX f32 tensors; the struct itself is a HOST object passed by value to the kernel. */
+typedef struct lcgan_adam_chunk {
+  float* p[LCGAN_MT_MAX];          /* parameters (updated in place) */
+  const float* g[LCGAN_MT_MAX];    /* gradients */
+  float* m[LCGAN_MT_MAX];          /* exp_avg (may be NULL when beta1 == 0: m = g) */
+  float* v[LCGAN_MT_MAX];          /* exp_avg_sq */
+  float* step[LCGAN_MT_MAX];       /* per-tensor completed-step counters (device f32 scalars; incremented) */
+  int64_t numel[LCGAN_MT_MAX];
+  int32_t count;
+} lcgan_adam_chunk;
+/* torch.optim.Adam(betas, eps, weight_decay=0, amsgrad=False) step (worker.py:98-110) for every tensor
+ * of the chunk in one launch; bias corrections use each tensor's own step counter, like torch. */
+int lcgan_adam_step(const lcgan_adam_chunk* chunk, float lr, float beta1, float beta2, float eps, void* stream);
+
+typedef struct lcgan_pack_chunk {
+  const float* src[LCGAN_MT_MAX];  /* w [O][I][K] f32 (K = kh*kw) */
+  void* dst[LCGAN_MT_MAX];
+  int32_t O[LCGAN_MT_MAX], I[LCGAN_MT_MAX], K[LCGAN_MT_MAX];
+  int32_t mode[LCGAN_MT_MAX];      /* 0: [O][K*I] (forward), 1: [I][K*O] (data gradient), 2: Wsq [O][I] f32 */
+  float scale[LCGAN_MT_MAX];       /* mode 2: sum_k (round(w)*scale)^2 */
+  int32_t count;
+} lcgan_pack_chunk;
+/* Tap-conv weight packs (W2 layouts of lcgan_tapconv) and demodulation tables (custom_layers.py:65-67)
+ * for up to LCGAN_MT_MAX weights in one launch; dt = dtype code of the packs. */
+int lcgan_pack_weights(const lcgan_pack_chunk* chunk, int dt, void* stream);
+
+/* Deterministic mode: reductions that finish with fp32 atomics (split-K weight gradients, per-(b,c)
+ * sums) take ordered turns instead, so repeated runs are bit-identical.  Returns the previous setting.
+ * Kernels launched in this mode must not run concurrently on two streams. */
+int lcgan_set_deterministic(int on);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "liblcgan_b200.so")
-_SRCS = ["api.cu", "conv_simt.cu", "conv_tc.cu", "thin.cu", "resample.cu", "warp.cu", "loss.cu"]
+_SRCS = ["api.cu", "conv_simt.cu", "conv_tc.cu", "thin.cu", "resample.cu", "warp.cu", "loss.cu", "optim.cu"]
 _lock = threading.Lock()
 _lib = None
 
@@ -36,24 +36,58 @@ class TapConvDesc(C.Structure):
         ("dy", C.c_int32 * MAX_TAPS), ("dx", C.c_int32 * MAX_TAPS), ("wtap", C.c_int32 * MAX_TAPS),
         ("w_ld", C.c_int64),
         ("acc_scale", C.c_float), ("bias_scale", C.c_float), ("slope", C.c_float), ("gain", C.c_float),
+        ("noise", C.c_void_p), ("noise_scale", C.c_float),
     ]
+
+
+MT_MAX = 48
+
+
+class AdamChunk(C.Structure):
+    """Mirror of `struct lcgan_adam_chunk`."""
+    _fields_ = [("p", C.c_void_p * MT_MAX), ("g", C.c_void_p * MT_MAX), ("m", C.c_void_p * MT_MAX),
+                ("v", C.c_void_p * MT_MAX), ("step", C.c_void_p * MT_MAX), ("numel", C.c_int64 * MT_MAX),
+                ("count", C.c_int32)]
+
+
+class PackChunk(C.Structure):
+    """Mirror of `struct lcgan_pack_chunk`."""
+    _fields_ = [("src", C.c_void_p * MT_MAX), ("dst", C.c_void_p * MT_MAX), ("O", C.c_int32 * MT_MAX),
+                ("I", C.c_int32 * MT_MAX), ("K", C.c_int32 * MT_MAX), ("mode", C.c_int32 * MT_MAX),
+                ("scale", C.c_float * MT_MAX), ("count", C.c_int32)]
 
 
 def build(verbose: bool = False) -> str:
     """Compile csrc/*.cu for sm_100a into lcgan_b200/liblcgan_b200.so (nvcc cross-compiles
-    without a GPU)."""
+    without a GPU).  One object per source (compiled in parallel, rebuilt only when the source or a
+    header is newer), then one link."""
+    from concurrent.futures import ThreadPoolExecutor
     src_dir = os.path.join(_HERE, "csrc")
-    srcs = [os.path.join(src_dir, s) for s in _SRCS]
-    deps = srcs + [os.path.join(src_dir, f) for f in os.listdir(src_dir) if f.endswith(".cuh")]
-    deps.append(os.path.join(os.path.dirname(_HERE), "include", "lcgan_b200.h"))
-    if os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps):
-        return _SO
+    obj_dir = os.path.join(src_dir, "_build")
+    os.makedirs(obj_dir, exist_ok=True)
+    hdrs = [os.path.join(src_dir, f) for f in os.listdir(src_dir) if f.endswith(".cuh")]
+    hdrs.append(os.path.join(os.path.dirname(_HERE), "include", "lcgan_b200.h"))
+    hdr_time = max(os.path.getmtime(h) for h in hdrs)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-o", _SO] + srcs
-    if verbose:
-        print(" ".join(cmd))
-    subprocess.run(cmd, check=True)
+    flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+    srcs = [os.path.join(src_dir, n) for n in _SRCS]
+    if os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in srcs + hdrs):
+        return _SO
+    jobs, objs = [], []
+    for name in _SRCS:
+        src, obj = os.path.join(src_dir, name), os.path.join(obj_dir, name[:-3] + ".o")
+        objs.append(obj)
+        if not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_time):
+            jobs.append([nvcc] + flags + ["-c", src, "-o", obj])
+
+    def run(cmd):
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.run(cmd, check=True)
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        list(ex.map(run, jobs))
+    run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", _SO] + objs)
     return _SO
 
 
@@ -92,7 +126,10 @@ _SIGS = {
     "lcgan_contrastive_bwd": ([_FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_float, _VOIDP], C.c_int),
     "lcgan_sumsq": ([_FP, _FP, C.c_int, C.c_int64, _VOIDP], C.c_int),
     "lcgan_rowscale": ([_FP, _FP, _FP, C.c_int, C.c_int64, _VOIDP], C.c_int),
-    "lcgan_ema_lerp": ([_VOIDP, _VOIDP, _VOIDP, C.c_int, C.c_float, _VOIDP], C.c_int),
+    "lcgan_ema_lerp": ([_VOIDP, _VOIDP, _VOIDP, C.c_int, C.c_float, _FP, _VOIDP], C.c_int),
+    "lcgan_adam_step": ([C.POINTER(AdamChunk), C.c_float, C.c_float, C.c_float, C.c_float, _VOIDP], C.c_int),
+    "lcgan_pack_weights": ([C.POINTER(PackChunk), C.c_int, _VOIDP], C.c_int),
+    "lcgan_set_deterministic": ([C.c_int], C.c_int),
 }
 EXPORTS = tuple(_SIGS) + ("lcgan_last_error",)
 

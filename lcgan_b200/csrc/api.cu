@@ -12,4 +12,13 @@ void lcgan_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* lcgan_last_error(void) { return g_err; }
-extern "C" int lcgan_version(void) { return 1; }
+extern "C" int lcgan_version(void) { return 2; }
+
+// Deterministic mode: ordered (turn-taking) reductions instead of fp32 atomics - see common.cuh.
+static int g_det = 0;
+bool lcgan_det_enabled() { return g_det != 0; }
+extern "C" int lcgan_set_deterministic(int on) {
+  const int old = g_det;
+  g_det = on ? 1 : 0;
+  return old;
+}

@@ -145,3 +145,43 @@ int lcgan_thin_forward(const lcgan_tapconv& d, const void* x, const void* w, voi
 int lcgan_thin_wgrad(const lcgan_tapconv& d, const void* x, const void* g, float* dw, float scale, cudaStream_t s);
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- deterministic mode (lcgan_set_deterministic) ------------------------------------------------
+// Reductions that normally finish with fp32 atomics (split-K weight gradients, per-(b,c) sums) take
+// TURNS instead: the contributors of one output region own a semaphore and add their partial sums with
+// plain loads/stores in a fixed order (contributor k waits until k-1 has published), so two runs are
+// bit-identical.  Contributors are ordered by their linear block index, and blocks are dispatched in
+// that order, so a waiting block only ever waits on blocks that are already resident or finished (the
+// serial split-K argument).  The last contributor resets the semaphore to 0: the pool needs no memset,
+// but kernels using it must not run concurrently on two streams.
+bool lcgan_det_enabled();
+constexpr int kDetSems = 32768;
+
+__device__ __forceinline__ void det_wait_turn(int* sem, int turn) {
+  int v;
+  do {
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(sem) : "memory");
+    if (v != turn) __nanosleep(32);
+  } while (v != turn);
+}
+__device__ __forceinline__ void det_pass_turn(int* sem, int turn, int nturns) {
+  const int next = turn + 1 == nturns ? 0 : turn + 1;
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(sem), "r"(next) : "memory");
+}
+// dst += v inside a turn (L2-coherent read: other blocks wrote the previous value)
+__device__ __forceinline__ void det_add(float* dst, float v) { __stcg(dst, __ldcg(dst) + v); }
+__device__ __forceinline__ void det_add4(float* dst, float4 v) {
+  float4 o = __ldcg(reinterpret_cast<const float4*>(dst));
+  o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+  __stcg(reinterpret_cast<float4*>(dst), o);
+}
+// whole-block turn: call with all threads of the block
+__device__ __forceinline__ void det_block_begin(int* sem, int turn) {
+  if (threadIdx.x == 0) det_wait_turn(sem, turn);
+  __syncthreads();
+}
+__device__ __forceinline__ void det_block_end(int* sem, int turn, int nturns) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) det_pass_turn(sem, turn, nturns);
+}

@@ -97,6 +97,7 @@ tapconv_simt_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const TW* _
       float v = acc[i][j] * d.acc_scale;
       if (rowscale) v *= rowscale[(int64_t)b * d.Cout + o];
       if (bias) v += bias[o] * d.bias_scale;
+      if (d.noise) v += d.noise[(int64_t)oy * d.OW + ox] * d.noise_scale;
       v = (v > 0.f ? v : v * d.slope) * d.gain;
       if (residual) v += ldf(residual + base + o * d.ys_c);
       stf(y + base + o * d.ys_c, v);
@@ -104,10 +105,12 @@ tapconv_simt_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const TW* _
   }
 }
 
+__device__ int g_sems[kDetSems];   // deterministic-mode turn semaphores (self-resetting)
+
 template <typename TX, typename TG>
 __global__ void __launch_bounds__(kThreads)
 tapconv_wgrad_simt_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const TG* __restrict__ g,
-                          float* __restrict__ dw, float scale, int64_t rows_per_split, int ctiles) {
+                          float* __restrict__ dw, float scale, int64_t rows_per_split, int ctiles, int* sems) {
   constexpr int BO = 64, BC = 64;
   __shared__ float Gs[BK][BO + 1];
   __shared__ float Xs[BK][BC + 1];
@@ -176,6 +179,9 @@ tapconv_wgrad_simt_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const
     __syncthreads();
   }
   const int64_t wcol0 = (int64_t)d.wtap[t] * d.Cin;
+  // deterministic mode: the K-splits of this (tile, tap) add in split order (common.cuh)
+  int* sem = sems ? sems + blockIdx.y * gridDim.x + blockIdx.x : nullptr;
+  if (sem) det_block_begin(sem, blockIdx.z);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int o = o0 + ty + i * 16;
@@ -184,9 +190,12 @@ tapconv_wgrad_simt_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const
     for (int j = 0; j < 4; ++j) {
       const int c = c0 + tx + j * 16;
       if (c >= d.Cin) continue;
-      atomicAdd(dw + (int64_t)o * d.w_ld + wcol0 + c, acc[i][j] * scale);
+      float* dst = dw + (int64_t)o * d.w_ld + wcol0 + c;
+      if (sem) det_add(dst, acc[i][j] * scale);
+      else atomicAdd(dst, acc[i][j] * scale);
     }
   }
+  if (sem) det_block_end(sem, blockIdx.z, gridDim.z);
 }
 
 template <typename TX, typename TW, typename TY>
@@ -240,7 +249,7 @@ extern "C" int lcgan_tapconv_simt(const lcgan_tapconv* d, const void* x, const v
   if (int e = check_desc(d)) return e;
   LCGAN_CHECK(x && w2 && y, "tapconv_simt: null tensor pointer");
   cudaStream_t s = (cudaStream_t)stream;
-  {
+  if (!d->noise) {                               // the special-shape kernels have no noise term
     const int e = lcgan_thin_forward(*d, x, w2, y, rowscale, bias, residual, s);
     if (e >= 0) return e;
   }
@@ -269,9 +278,14 @@ extern "C" int lcgan_tapconv_wgrad_simt(const lcgan_tapconv* d, const void* x, c
   rps = (rps + BK - 1) / BK * BK;
   splits = (int)((rows + rps - 1) / rps);
   dim3 grid(otiles * ctiles, d->ntaps, splits);
+  int* sems = nullptr;
+  if (lcgan_det_enabled()) {
+    LCGAN_CHECK(otiles * ctiles * d->ntaps <= kDetSems, "tapconv_wgrad_simt: too many tiles for deterministic mode");
+    LCGAN_CUDA(cudaGetSymbolAddress((void**)&sems, g_sems));
+  }
 #define WG(TXT, TGT)                                                                     \
   tapconv_wgrad_simt_kernel<TXT, TGT><<<grid, kThreads, 0, s>>>(*d, (const TXT*)x, (const TGT*)g, \
-                                                                dw2, scale, rps, ctiles)
+                                                                dw2, scale, rps, ctiles, sems)
   if (d->x_dtype == LCGAN_F32 && d->y_dtype == LCGAN_F32) WG(float, float);
   else if (d->x_dtype == LCGAN_F32) WG(float, bf16);
   else if (d->y_dtype == LCGAN_F32) WG(bf16, float);

@@ -49,6 +49,9 @@ struct TcParams {
   // and takes rowscale / bias of channel o % cperiod; cblk == 0: plain channel-innermost output
   int cblk, cperiod;
   long long ys_blk;
+  const float* noise;                           // [OH][OW] f32 plane added before the activation (or null)
+  float noise_scale;
+  int OW;
 };
 
 struct WgParams {
@@ -61,7 +64,10 @@ struct WgParams {
   int tiles_per_split;
   long long w_ld;
   float scale;
+  int* sems;                                    // deterministic mode: ordered K-split accumulation (common.cuh)
 };
+
+__device__ int g_sems[kDetSems];
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -402,6 +408,8 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
       const bool live = b < p.N;
       const long long pix = (long long)b * p.ys_n + (long long)((m0 + mi) * p.os + p.py) * p.ys_h +
                             (long long)((n0 + ni) * p.os + p.px) * p.ys_w;
+      const float nz = (p.noise && live) ? p.noise[(long long)((m0 + mi) * p.os + p.py) * p.OW + (n0 + ni) * p.os + p.px] *
+                                           p.noise_scale : 0.f;
       // resident mode: 4 single accumulators; ring mode: 2 pairs of partial accumulators
       const bool ring = p.rowshare != 2;
       const int as = ring ? (li & 1) : li % kAccStages, aph = ring ? (li >> 1) & 1 : (li / kAccStages) & 1;
@@ -439,7 +447,7 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
             }
           }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = (f[i] > 0.f ? f[i] : f[i] * p.slope) * p.gain;
+          for (int i = 0; i < 16; ++i) f[i] = (f[i] + nz > 0.f ? f[i] + nz : (f[i] + nz) * p.slope) * p.gain;
           if (p.y_f32) {
             float* yp = reinterpret_cast<float*>(y) + pix + yo;
             if (residual) {
@@ -581,6 +589,12 @@ tapconv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmg, const __grid_co
     tc_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     float* row = dw + (long long)o * p.w_ld + (long long)p.wtap[tap] * p.Cin + c0;
+    // deterministic mode: each epilogue warp owns 32 rows of the tile; the K-splits (blockIdx.z) add in order
+    int* sem = p.sems ? p.sems + ((blockIdx.y * gridDim.x + blockIdx.x) * 4 + q) : nullptr;
+    if (sem) {
+      if (lane == 0) det_wait_turn(sem, blockIdx.z);
+      __syncwarp();
+    }
     for (int c = 0; c < p.BN; c += 16) {
       uint32_t v[16];
       tmem_ld16(trow + c, v);
@@ -588,12 +602,19 @@ tapconv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmg, const __grid_co
       if (o < p.Cout && nkb > 0) {
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
-          if (c0 + c + i < p.Cin)
-            atomicAdd(reinterpret_cast<float4*>(row + c + i),
-                      make_float4(__uint_as_float(v[i]) * p.scale, __uint_as_float(v[i + 1]) * p.scale,
-                                  __uint_as_float(v[i + 2]) * p.scale, __uint_as_float(v[i + 3]) * p.scale));
+          if (c0 + c + i < p.Cin) {
+            const float4 add = make_float4(__uint_as_float(v[i]) * p.scale, __uint_as_float(v[i + 1]) * p.scale,
+                                           __uint_as_float(v[i + 2]) * p.scale, __uint_as_float(v[i + 3]) * p.scale);
+            if (sem) det_add4(row + c + i, add);
+            else atomicAdd(reinterpret_cast<float4*>(row + c + i), add);
+          }
         }
       }
+    }
+    if (sem) {
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) det_pass_turn(sem, blockIdx.z, gridDim.z);
     }
     tc_fence_before();
   }
@@ -693,6 +714,11 @@ tapconv_wgrad_tn_kernel(const __grid_constant__ CUtensorMap tmg, const __grid_co
     mbar_wait(&s.done[0], 0);
     tc_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    int* sem = p.sems ? p.sems + (blockIdx.x * 4 + q) : nullptr;      // K-splits (blockIdx.y) add in order
+    if (sem) {
+      if (lane == 0) det_wait_turn(sem, blockIdx.y);
+      __syncwarp();
+    }
     for (int c = 0; c < ntot; c += 16) {
       uint32_t v[16];
       tmem_ld16(trow + c, v);
@@ -701,11 +727,18 @@ tapconv_wgrad_tn_kernel(const __grid_constant__ CUtensorMap tmg, const __grid_co
         const int tap = c / p.Cin, ci = c - tap * p.Cin;      // 16 | Cin, so a 16-column group stays in one tap
         float* row = dw + (long long)o * p.w_ld + (long long)p.wtap[tap] * p.Cin + ci;
 #pragma unroll
-        for (int i = 0; i < 16; i += 4)
-          atomicAdd(reinterpret_cast<float4*>(row + i),
-                    make_float4(__uint_as_float(v[i]) * p.scale, __uint_as_float(v[i + 1]) * p.scale,
-                                __uint_as_float(v[i + 2]) * p.scale, __uint_as_float(v[i + 3]) * p.scale));
+        for (int i = 0; i < 16; i += 4) {
+          const float4 add = make_float4(__uint_as_float(v[i]) * p.scale, __uint_as_float(v[i + 1]) * p.scale,
+                                         __uint_as_float(v[i + 2]) * p.scale, __uint_as_float(v[i + 3]) * p.scale);
+          if (sem) det_add4(row + i, add);
+          else atomicAdd(reinterpret_cast<float4*>(row + i), add);
+        }
       }
+    }
+    if (sem) {
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) det_pass_turn(sem, blockIdx.y, gridDim.y);
     }
     tc_fence_before();
   }
@@ -863,6 +896,8 @@ static int tapconv_tc_launch(const lcgan_tapconv* d, const void* x, const void* 
   p.y_f32 = d->y_dtype == LCGAN_F32;
   p.acc_scale = d->acc_scale; p.bias_scale = d->bias_scale; p.slope = d->slope; p.gain = d->gain;
   p.cblk = cblk; p.cperiod = cperiod; p.ys_blk = ys_blk;
+  p.noise = d->noise; p.noise_scale = d->noise_scale; p.OW = d->OW;
+  LCGAN_CHECK(!(d->noise && cblk), "tapconv_tc_blocked: no noise term in the blocked-output form");
 
   // row-shared mode: full 3x3 stride-1 tap set on a 16-wide, 8-tall, single-image tile
   p.rowshare = 0;
@@ -948,6 +983,11 @@ extern "C" int lcgan_tapconv_wgrad_tc(const lcgan_tapconv* d, const void* x, con
   p.tiles_per_split = (p.tiles_total + splits - 1) / splits;
   splits = (p.tiles_total + p.tiles_per_split - 1) / p.tiles_per_split;
   p.w_ld = d->w_ld; p.scale = scale;
+  p.sems = nullptr;
+  if (lcgan_det_enabled()) {
+    LCGAN_CHECK(base * 4 <= kDetSems, "tapconv_wgrad_tc: too many tiles for deterministic mode");
+    LCGAN_CUDA(cudaGetSymbolAddress((void**)&p.sems, g_sems));
+  }
 
   if (d->ntaps * d->Cin <= kTnMaxN && d->Cin % 16 == 0 && getenv("LCGAN_NO_WGRAD_TN") == nullptr) {
     // small-channel layers: all taps along N, persistent-ish K split (one CTA per SM)

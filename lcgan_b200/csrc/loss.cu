@@ -6,6 +6,7 @@
 namespace {
 
 constexpr int kThreads = 256;
+__device__ int g_sems[kDetSems];     // deterministic-mode turn semaphores (common.cuh)
 
 __global__ void __launch_bounds__(kThreads)
 l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ inv_norm, int B, int D) {
@@ -70,7 +71,7 @@ contrastive_bwd_kernel(const float* __restrict__ a, const float* __restrict__ p,
 }
 
 __global__ void __launch_bounds__(kThreads)
-sumsq_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t L) {
+sumsq_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t L, int* sems) {
   const int b = blockIdx.y;
   const float* xr = x + (int64_t)b * L;
   float acc = 0.f;
@@ -88,7 +89,16 @@ sumsq_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t L) {
   if (threadIdx.x < 32) {
     float v = threadIdx.x < kThreads / 32 ? part[threadIdx.x] : 0.f;
     v = warp_sum(v);
-    if (threadIdx.x == 0) atomicAdd(out + b, v);
+    if (threadIdx.x == 0) {
+      if (sems) {                                   // deterministic mode: blocks of a row add in order
+        det_wait_turn(sems + b, blockIdx.x);
+        det_add(out + b, v);
+        __threadfence();
+        det_pass_turn(sems + b, blockIdx.x, gridDim.x);
+      } else {
+        atomicAdd(out + b, v);
+      }
+    }
   }
 }
 
@@ -104,7 +114,8 @@ rowscale_kernel(const float* __restrict__ x, const float* __restrict__ s, float*
 
 __global__ void __launch_bounds__(kThreads)
 ema_lerp_kernel(float* const* __restrict__ dst, const float* const* __restrict__ src,
-                const int64_t* __restrict__ numel, float decay) {
+                const int64_t* __restrict__ numel, float decay, const float* __restrict__ decay_dev) {
+  if (decay_dev) decay = *decay_dev;
   float* d = dst[blockIdx.y];
   const float* s = src[blockIdx.y];
   const int64_t n = numel[blockIdx.y];
@@ -157,7 +168,12 @@ extern "C" int lcgan_sumsq(const float* x, float* out, int B, int64_t L, void* s
   const int cap = ceil_div(148 * 8, B);
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
-  sumsq_kernel<<<dim3(bx, B), kThreads, 0, (cudaStream_t)stream>>>(x, out, L);
+  int* sems = nullptr;
+  if (lcgan_det_enabled()) {
+    LCGAN_CHECK(B <= kDetSems, "sumsq: batch too large for deterministic mode");
+    LCGAN_CUDA(cudaGetSymbolAddress((void**)&sems, g_sems));
+  }
+  sumsq_kernel<<<dim3(bx, B), kThreads, 0, (cudaStream_t)stream>>>(x, out, L, sems);
   LCGAN_LAUNCH_CHECK();
   return 0;
 }
@@ -174,9 +190,9 @@ extern "C" int lcgan_rowscale(const float* x, const float* s, float* y, int B, i
 }
 
 extern "C" int lcgan_ema_lerp(float* const* dst, const float* const* src, const int64_t* numel, int n, float decay,
-                              void* stream) {
+                              const float* decay_dev, void* stream) {
   LCGAN_CHECK(dst && src && numel && n > 0 && n <= 65535, "ema_lerp: bad arguments");
-  ema_lerp_kernel<<<dim3(16, n), kThreads, 0, (cudaStream_t)stream>>>(dst, src, numel, decay);
+  ema_lerp_kernel<<<dim3(16, n), kThreads, 0, (cudaStream_t)stream>>>(dst, src, numel, decay, decay_dev);
   LCGAN_LAUNCH_CHECK();
   return 0;
 }

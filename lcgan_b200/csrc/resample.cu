@@ -8,6 +8,7 @@
 namespace {
 
 constexpr int kThreads = 256;
+__device__ int g_sems[kDetSems];     // deterministic-mode turn semaphores (common.cuh)
 constexpr int kStreamStages = 4;     // cp.async depth of the streaming reductions (act_bwd, modulate_bwd)
 
 template <typename T, int V>
@@ -310,7 +311,7 @@ template <typename T, int V, int STAGES>
 __global__ void __launch_bounds__(kThreads)
 act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ gout,
                const float* __restrict__ d, float* __restrict__ r0, float* __restrict__ r1, int P, int C,
-               float slope, float gain, int pix_per_block) {
+               float slope, float gain, int pix_per_block, int* sems) {
   const int cv = C / V;
   const int b = blockIdx.y;
   (void)pix_per_block;                       // only sizes the grid: blocks interleave over the pixels
@@ -318,13 +319,13 @@ act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict_
   for (int cg = 0; cg < cv; cg += kThreads) {
     const int ncv = min(kThreads, cv - cg);
     const int lanes = kThreads / ncv;          // pixels processed per block iteration
-    if ((int)threadIdx.x >= lanes * ncv) continue;
+    const bool active = (int)threadIdx.x < lanes * ncv;
     const int c = (cg + (int)threadIdx.x % ncv) * V;
     float s0[V], s1[V], dd[V];
 #pragma unroll
-    for (int i = 0; i < V; ++i) { s0[i] = 0.f; s1[i] = 0.f; dd[i] = d ? d[(int64_t)b * C + c + i] : 1.f; }
+    for (int i = 0; i < V; ++i) { s0[i] = 0.f; s1[i] = 0.f; dd[i] = (d && active) ? d[(int64_t)b * C + c + i] : 1.f; }
     const int64_t base = (int64_t)b * P * C + c;
-    int p = blockIdx.x * lanes + threadIdx.x / ncv;
+    int p = active ? blockIdx.x * lanes + threadIdx.x / ncv : P;   // inactive threads: empty pixel range
     const int pstep = gridDim.x * lanes;
     auto body = [&](float* g, const float* yy, int64_t off) {
 #pragma unroll
@@ -374,13 +375,43 @@ act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict_
         body(g, yy, off);
       }
     }
-    if (r0) {
+    if (sems) {
+      // deterministic mode: fixed-order sum over the pixel lanes of the block, then the blocks of
+      // this image add in blockIdx.x order (common.cuh)
+      __shared__ float red[kThreads * V];
+      const bool first = active && (int)threadIdx.x < ncv;
+      auto lane_sum = [&](float* sv) {
+        __syncthreads();
+        if (active) {
 #pragma unroll
-      for (int i = 0; i < V; ++i) atomicAdd(r0 + (int64_t)b * C + c + i, s0[i]);
-    }
-    if (r1) {
+          for (int i = 0; i < V; ++i) red[threadIdx.x * V + i] = sv[i];
+        }
+        __syncthreads();
+        if (first)
+          for (int l = 1; l < lanes; ++l)
 #pragma unroll
-      for (int i = 0; i < V; ++i) atomicAdd(r1 + (int64_t)b * C + c + i, s1[i]);
+            for (int i = 0; i < V; ++i) sv[i] += red[(l * ncv + threadIdx.x) * V + i];
+      };
+      if (r0) lane_sum(s0);
+      if (r1) lane_sum(s1);
+      det_block_begin(sems + b, blockIdx.x);
+      if (first) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          if (r0) det_add(r0 + (int64_t)b * C + c + i, s0[i]);
+          if (r1) det_add(r1 + (int64_t)b * C + c + i, s1[i]);
+        }
+      }
+      det_block_end(sems + b, blockIdx.x, gridDim.x);
+    } else if (active) {
+      if (r0) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) atomicAdd(r0 + (int64_t)b * C + c + i, s0[i]);
+      }
+      if (r1) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) atomicAdd(r1 + (int64_t)b * C + c + i, s1[i]);
+      }
     }
   }
 }
@@ -405,20 +436,20 @@ modulate_kernel(const T* __restrict__ x, const float* __restrict__ s, T* __restr
 template <typename T, int V>
 __global__ void __launch_bounds__(kThreads)
 modulate_bwd_kernel(const T* __restrict__ x, const T* __restrict__ t, const float* __restrict__ s,
-                    T* __restrict__ dx, float* __restrict__ ds, int P, int C, int pix_per_block) {
+                    T* __restrict__ dx, float* __restrict__ ds, int P, int C, int pix_per_block, int* sems) {
   const int cv = C / V;
   const int b = blockIdx.y;
   (void)pix_per_block;                       // only sizes the grid: blocks interleave over the pixels
   for (int cg = 0; cg < cv; cg += kThreads) {
     const int ncv = min(kThreads, cv - cg);
     const int lanes = kThreads / ncv;
-    if ((int)threadIdx.x >= lanes * ncv) continue;
+    const bool active = (int)threadIdx.x < lanes * ncv;
     const int c = (cg + (int)threadIdx.x % ncv) * V;
     float acc[V], ss[V];
 #pragma unroll
-    for (int i = 0; i < V; ++i) { acc[i] = 0.f; ss[i] = s[(int64_t)b * C + c + i]; }
+    for (int i = 0; i < V; ++i) { acc[i] = 0.f; ss[i] = active ? s[(int64_t)b * C + c + i] : 0.f; }
     const int64_t base = (int64_t)b * P * C + c;
-    int p = blockIdx.x * lanes + threadIdx.x / ncv;
+    int p = active ? blockIdx.x * lanes + threadIdx.x / ncv : P;
     const int pstep = gridDim.x * lanes;
     if constexpr (V > 1) {
       __shared__ uint4 stage[kStreamStages][2][kThreads];   // cp.async pipeline, see act_bwd_kernel
@@ -458,8 +489,30 @@ modulate_bwd_kernel(const T* __restrict__ x, const T* __restrict__ t, const floa
         stv<T, V>(dx + off, tv);
       }
     }
+    if (sems) {
+      // deterministic mode (see act_bwd_kernel)
+      __shared__ float red[kThreads * V];
+      const bool first = active && (int)threadIdx.x < ncv;
+      __syncthreads();
+      if (active) {
 #pragma unroll
-    for (int i = 0; i < V; ++i) atomicAdd(ds + (int64_t)b * C + c + i, acc[i]);
+        for (int i = 0; i < V; ++i) red[threadIdx.x * V + i] = acc[i];
+      }
+      __syncthreads();
+      if (first)
+        for (int l = 1; l < lanes; ++l)
+#pragma unroll
+          for (int i = 0; i < V; ++i) acc[i] += red[(l * ncv + threadIdx.x) * V + i];
+      det_block_begin(sems + b, blockIdx.x);
+      if (first) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) det_add(ds + (int64_t)b * C + c + i, acc[i]);
+      }
+      det_block_end(sems + b, blockIdx.x, gridDim.x);
+    } else if (active) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) atomicAdd(ds + (int64_t)b * C + c + i, acc[i]);
+    }
   }
 }
 
@@ -578,19 +631,16 @@ extern "C" int lcgan_act_bwd(const void* dy, const void* y, void* gout, const fl
   LCGAN_CHECK(N <= 65535, "act_bwd: batch too large");
   cudaStream_t s = (cudaStream_t)stream;
   const char* e_bps = getenv("LCGAN_ACT_BPS");          // tuning knobs (experiments only)
-  const char* e_st = getenv("LCGAN_ACT_STAGES");
   const int ppb = pix_per_block_for(N, P, e_bps ? atoi(e_bps) : 4);   // one resident wave (measured best: 3-6)
-  const bool deep = e_st && atoi(e_st) == 6;
   dim3 grid(ceil_div(P, ppb), N);
+  int* sems = nullptr;
+  if (lcgan_det_enabled() && (r0 || r1)) {
+    LCGAN_CHECK(N <= kDetSems, "act_bwd: batch too large for deterministic mode");
+    LCGAN_CUDA(cudaGetSymbolAddress((void**)&sems, g_sems));
+  }
 #define CALL(T, V)                                                                              \
-  do {                                                                                          \
-    if (deep)                                                                                   \
-      act_bwd_kernel<T, V, 6><<<grid, kThreads, 0, s>>>((const T*)dy, (const T*)y, (T*)gout, d, r0, r1, P, C, \
-                                                        slope, gain, ppb);                      \
-    else                                                                                        \
-      act_bwd_kernel<T, V, kStreamStages><<<grid, kThreads, 0, s>>>((const T*)dy, (const T*)y, (T*)gout, d, r0, \
-                                                                    r1, P, C, slope, gain, ppb); \
-  } while (0)
+  act_bwd_kernel<T, V, kStreamStages><<<grid, kThreads, 0, s>>>((const T*)dy, (const T*)y, (T*)gout, d, r0, \
+                                                                r1, P, C, slope, gain, ppb, sems)
   DISPATCH_TV(dt, C, CALL);
 #undef CALL
   LCGAN_LAUNCH_CHECK();
@@ -616,8 +666,13 @@ extern "C" int lcgan_modulate_bwd(const void* x, const void* t, const float* sc,
   const char* e_bps = getenv("LCGAN_ACT_BPS");          // tuning knob (experiments only)
   const int ppb = pix_per_block_for(N, P, e_bps ? atoi(e_bps) : 3);   // measured best: 1-3 (6.0 vs 5.2 TB/s at 8)
   dim3 grid(ceil_div(P, ppb), N);
+  int* sems = nullptr;
+  if (lcgan_det_enabled()) {
+    LCGAN_CHECK(N <= kDetSems, "modulate_bwd: batch too large for deterministic mode");
+    LCGAN_CUDA(cudaGetSymbolAddress((void**)&sems, g_sems));
+  }
 #define CALL(T, V)                                                                              \
-  modulate_bwd_kernel<T, V><<<grid, kThreads, 0, s>>>((const T*)x, (const T*)t, sc, (T*)dx, ds, P, C, ppb)
+  modulate_bwd_kernel<T, V><<<grid, kThreads, 0, s>>>((const T*)x, (const T*)t, sc, (T*)dx, ds, P, C, ppb, sems)
   DISPATCH_TV(dt, C, CALL);
 #undef CALL
   LCGAN_LAUNCH_CHECK();

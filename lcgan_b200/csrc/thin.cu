@@ -11,6 +11,12 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kMaxThin = 4;
+__device__ int g_sems[kDetSems];     // deterministic-mode turn semaphores (common.cuh)
+static int* det_sems() {             // nullptr unless deterministic mode is on
+  int* p = nullptr;
+  if (lcgan_det_enabled()) cudaGetSymbolAddress((void**)&p, g_sems);
+  return p;
+}
 constexpr int kSmemFloats = 11 * 1024;   // 44 KiB of weights in static shared memory
 
 template <typename T, int V> __device__ __forceinline__ void ldv(const T* p, float* f) {
@@ -325,7 +331,7 @@ thin_up2_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const void* __r
 template <typename TW, typename TT, int V, bool kThinIsG>
 __global__ void __launch_bounds__(kThreads)
 thin_wgrad_kernel(const lcgan_tapconv d, const TW* __restrict__ wide, const TT* __restrict__ thin,
-                  float* __restrict__ dw, float scale, int cv, int lanes, int64_t rows_per_block) {
+                  float* __restrict__ dw, float scale, int cv, int lanes, int64_t rows_per_block, int* sems) {
   __shared__ float red[kThreads * kMaxThin * V / 2];   // half the threads park their partials at a time
   const int per_lane = cv * d.ntaps;
   const int lane = threadIdx.x / per_lane;
@@ -396,15 +402,19 @@ thin_wgrad_kernel(const lcgan_tapconv d, const TW* __restrict__ wide, const TT* 
         for (int i = 0; i < V; ++i) acc[o][i] += p[o * V + i];
     }
   }
+  if (sems) det_block_begin(sems, blockIdx.x);       // deterministic mode: blocks add in index order
   if (active && lane == 0) {
     const int64_t wcol0 = (int64_t)d.wtap[t] * d.Cin;
     for (int o = 0; o < nthin; ++o)
 #pragma unroll
       for (int i = 0; i < V; ++i) {
-        if constexpr (kThinIsG) atomicAdd(dw + (int64_t)o * d.w_ld + wcol0 + v * V + i, acc[o][i] * scale);
-        else atomicAdd(dw + (int64_t)(v * V + i) * d.w_ld + wcol0 + o, acc[o][i] * scale);
+        float* dst = kThinIsG ? dw + (int64_t)o * d.w_ld + wcol0 + v * V + i
+                              : dw + (int64_t)(v * V + i) * d.w_ld + wcol0 + o;
+        if (sems) det_add(dst, acc[o][i] * scale);
+        else atomicAdd(dst, acc[o][i] * scale);
       }
   }
+  if (sems) det_block_end(sems, blockIdx.x, gridDim.x);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -418,7 +428,7 @@ thin_wgrad_kernel(const lcgan_tapconv d, const TW* __restrict__ wide, const TT* 
 template <typename TX, typename TG, int CO>
 __global__ void __launch_bounds__(kThreads)
 thin_up2_wgrad_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const TG* __restrict__ g,
-                      float* __restrict__ dw, float scale, int cv4, int lanes, uint32_t rows_per_block) {
+                      float* __restrict__ dw, float scale, int cv4, int lanes, uint32_t rows_per_block, int* sems) {
   constexpr int NA = 9 * CO * 4;
   __shared__ float red[(kThreads / 2) * NA];
   const int v = threadIdx.x % cv4, lane = threadIdx.x / cv4;
@@ -494,15 +504,20 @@ thin_up2_wgrad_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const TG*
           for (int i = 0; i < 4; ++i) acc[t][o][i] += p[(t * CO + o) * 4 + i];
     }
   }
+  if (sems) det_block_begin(sems, blockIdx.x);       // deterministic mode: blocks add in index order
   if (lane == 0) {
 #pragma unroll
     for (int t = 0; t < 9; ++t)
 #pragma unroll
       for (int o = 0; o < CO; ++o)
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          atomicAdd(dw + (int64_t)o * d.w_ld + (int64_t)t * d.Cin + v * 4 + i, acc[t][o][i] * scale);
+        for (int i = 0; i < 4; ++i) {
+          float* dst = dw + (int64_t)o * d.w_ld + (int64_t)t * d.Cin + v * 4 + i;
+          if (sems) det_add(dst, acc[t][o][i] * scale);
+          else atomicAdd(dst, acc[t][o][i] * scale);
+        }
   }
+  if (sems) det_block_end(sems, blockIdx.x, gridDim.x);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -701,7 +716,7 @@ int lcgan_thin_wgrad(const lcgan_tapconv& d, const void* x, const void* g, float
   blocks = (rows + rpb - 1) / rpb;
 #define TWG(TWIDE, TTHIN, VV, THIN_G)                                                                        \
   thin_wgrad_kernel<TWIDE, TTHIN, VV, THIN_G><<<(int)blocks, kThreads, 0, s>>>(                              \
-      d, (const TWIDE*)(THIN_G ? x : g), (const TTHIN*)(THIN_G ? g : x), dw, scale, cv, lanes, rpb)
+      d, (const TWIDE*)(THIN_G ? x : g), (const TTHIN*)(THIN_G ? g : x), dw, scale, cv, lanes, rpb, det_sems())
   if (thin_g) {
     if (xf && gf) TWG(float, float, 4, true); else if (xf) TWG(float, bf16, 4, true);
     else if (gf) TWG(bf16, float, 8, true); else TWG(bf16, bf16, 8, true);
@@ -717,7 +732,7 @@ int lcgan_thin_wgrad(const lcgan_tapconv& d, const void* x, const void* g, float
 // Fused x2 transposed conv with <= 4 output channels (all phases).  d describes phase (0,0) of the
 // plan: N, IH, IW, Cin, Cout, strides, dtypes, w_ld and the epilogue constants are used.
 extern "C" int lcgan_tapconv_up2_thin_eligible(const lcgan_tapconv* d) {
-  if (!d || d->Cout > kMaxThin || d->os != 2 || d->is != 1) return 0;
+  if (!d || d->Cout > kMaxThin || d->os != 2 || d->is != 1 || d->noise) return 0;
   if (9 * d->Cout * d->Cin > kSmemFloats) return 0;
   if (d->OH != 2 * d->IH || d->OW != 2 * d->IW) return 0;
   if ((int64_t)d->N * d->IH * d->IW >= (1LL << 31) - 65536) return 0;   // 32-bit pixel index in the kernel
@@ -770,9 +785,9 @@ extern "C" int lcgan_tapconv_up2_thin_wgrad(const lcgan_tapconv* d, const void* 
 #define UW(TXT, TGT)                                                                                         \
   do {                                                                                                       \
     if (d->Cout == 1)                                                                                        \
-      thin_up2_wgrad_kernel<TXT, TGT, 1><<<(int)blocks, kThreads, 0, s>>>(*d, (const TXT*)x, (const TGT*)g, dw2, scale, cv4, lanes, (uint32_t)rpb); \
+      thin_up2_wgrad_kernel<TXT, TGT, 1><<<(int)blocks, kThreads, 0, s>>>(*d, (const TXT*)x, (const TGT*)g, dw2, scale, cv4, lanes, (uint32_t)rpb, det_sems()); \
     else                                                                                                     \
-      thin_up2_wgrad_kernel<TXT, TGT, 2><<<(int)blocks, kThreads, 0, s>>>(*d, (const TXT*)x, (const TGT*)g, dw2, scale, cv4, lanes, (uint32_t)rpb); \
+      thin_up2_wgrad_kernel<TXT, TGT, 2><<<(int)blocks, kThreads, 0, s>>>(*d, (const TXT*)x, (const TGT*)g, dw2, scale, cv4, lanes, (uint32_t)rpb, det_sems()); \
   } while (0)
   if (xf && gf) UW(float, float); else if (xf) UW(float, bf16); else if (gf) UW(bf16, float); else UW(bf16, bf16);
 #undef UW

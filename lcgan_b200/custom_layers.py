@@ -93,7 +93,9 @@ class ModulatedConv2d(nn.Module):
         self.lr_mul = lr_mul
         self.eps = eps
 
-    def forward(self, x, s, slope=1.0, gain=1.0, out_dtype=None, out_nchw=False):
+    def forward(self, x, s, slope=1.0, gain=1.0, out_dtype=None, out_nchw=False, noise=None):
+        """noise: optional f32 [H_out, W_out] plane added between the conv (+bias) and the activation
+        (SynthesisLayer's noise injection, fused into the conv epilogue)."""
         w = self.weight.weight
         c = float(self.weight.c)
         # demodulation coefficients, fp32: d[b,o] = rsqrt(s^2 @ Wsq^T + eps)
@@ -106,8 +108,10 @@ class ModulatedConv2d(nn.Module):
             plan = plans.conv_transpose_up2(self.kernel_size, x.shape[2], x.shape[3])
         else:
             plan = plans.conv(self.kernel_size, 1, x.shape[2], x.shape[3])
-        return ops.ModConvAct.apply(_as_act(x), s.contiguous(), w, self.bias, d.contiguous(), c, plan, slope, gain,
-                                    float(self.lr_mul), out_dtype or ops.act_dtype(), out_nchw)
+        if noise is not None:
+            noise = noise.float().contiguous()
+        return ops.ModConvAct.apply(_as_act(x), s.contiguous(), w, self.bias, d.contiguous(), noise, c, plan, slope,
+                                    gain, float(self.lr_mul), out_dtype or ops.act_dtype(), out_nchw)
 
 
 class SynthesisLayer(nn.Module):
@@ -131,13 +135,11 @@ class SynthesisLayer(nn.Module):
         s = self.linear(latent.float())
         if not self.use_noise:
             return self.modulated_conv(x, s, slope, gain, out_dtype, out_nchw)
-        # noise sits between the conv and any activation (custom_layers.py:108-110); this branch
-        # is never constructed by cnn.py (use_noise=False everywhere) and is kept for the surface.
-        y = self.modulated_conv(x, s, 1.0, 1.0, out_dtype, out_nchw)
-        y = y + (self.noise_const * self.noise_strength * self.noise_gain).to(y.dtype)
-        if slope != 1.0 or gain != 1.0:
-            y = torch.nn.functional.leaky_relu(y, slope) * gain
-        return y
+        # custom_layers.py:108-110: x + noise_const * noise_strength * noise_gain, between the conv and any
+        # activation -> a [res, res] plane (a weight-sized torch op, differentiable w.r.t. noise_strength)
+        # that the conv epilogue adds before the leaky-relu.  cnn.py never enables it (use_noise=False).
+        plane = self.noise_const * self.noise_strength * self.noise_gain
+        return self.modulated_conv(x, s, slope, gain, out_dtype, out_nchw, noise=plane)
 
 
 class SynthesisBlock(nn.Module):

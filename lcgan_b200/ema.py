@@ -17,8 +17,13 @@ class Ema(object):
             for b_ema, b in zip(self.target.buffers(), self.source.buffers()):
                 b_ema.copy_(b)
 
-    def update(self, iter=None):
-        decay = 0.0 if (iter >= 0 and iter < self.start_iter) else self.decay
+    def decay_at(self, iter):
+        """ema.py:19-23: plain copy (decay 0) before start_iter."""
+        return 0.0 if (iter >= 0 and iter < self.start_iter) else self.decay
+
+    def update(self, iter=None, decay_dev=None):
+        """decay_dev: optional device scalar holding decay_at(iter) (CUDA-graph replays)."""
+        decay = self.decay_at(iter)
         with torch.no_grad():
             dst, src = [], []
             for p_ema, p in zip(self.target.parameters(), self.source.parameters()):
@@ -28,4 +33,4 @@ class Ema(object):
                     b_ema.copy_(b)
                 else:
                     dst.append(b_ema); src.append(b)
-            ops.ema_lerp_(dst, src, float(decay))
+            ops.ema_lerp_(dst, src, float(decay), decay_dev)

@@ -25,7 +25,6 @@ from torch.autograd.function import once_differentiable
 from . import _lib, plans
 from ._lib import BF16, F32, TapConvDesc
 
-_state = threading.local()
 _ACT_DTYPE = torch.bfloat16
 _USE_TC = os.environ.get("LCGAN_DISABLE_TC", "0") != "1"
 
@@ -51,20 +50,27 @@ def set_tensor_cores(flag: bool):
     _USE_TC = bool(flag)
 
 
+# A plain module-level flag, NOT a threading.local: backward nodes of CUDA tensors run on the autograd
+# engine's device thread, not on the thread that entered the context manager (conv2d_gradfix keeps a
+# module global for the same reason).
+_NO_WGRAD = False
+
+
 @contextlib.contextmanager
 def no_weight_gradients():
     """Skip weight/bias gradients inside (used for the R1 first-order pass, which only needs
     d logit / d image; same role as conv2d_gradfix.no_weight_gradients)."""
-    old = getattr(_state, "no_wgrad", False)
-    _state.no_wgrad = True
+    global _NO_WGRAD
+    old = _NO_WGRAD
+    _NO_WGRAD = True
     try:
         yield
     finally:
-        _state.no_wgrad = old
+        _NO_WGRAD = old
 
 
 def _wgrad_enabled():
-    return not getattr(_state, "no_wgrad", False)
+    return not _NO_WGRAD
 
 
 def _dt(t: torch.Tensor) -> int:
@@ -117,6 +123,16 @@ def _strides_nhwc(t):
 # ------------------------------------------------------------------------------------------
 _pack_cache = {}
 _pack_lock = threading.Lock()
+# Bumped by everything that rewrites parameters through raw pointers (ema_lerp_, the fused Adam kernel,
+# CUDA-graph replays that contain an optimizer step): those writes do not move Tensor._version, so the
+# generation is part of every cache tag.
+_generation = 0
+
+
+def bump_generation():
+    """Invalidate every cached weight pack / derived weight tensor."""
+    global _generation
+    _generation += 1
 
 
 def pack_weight(w: torch.Tensor, transposed: bool, dtype: torch.dtype) -> torch.Tensor:
@@ -128,7 +144,7 @@ def pack_weight(w: torch.Tensor, transposed: bool, dtype: torch.dtype) -> torch.
     cacheable = isinstance(w, torch.nn.Parameter)
     if cacheable:
         key = (id(w), transposed, dtype)
-        tag = (w._version, w.data_ptr())
+        tag = (w._version, w.data_ptr(), _generation)
         with _pack_lock:
             hit = _pack_cache.get(key)
             if hit is not None and hit[0] == tag:
@@ -168,7 +184,8 @@ def unpack_wgrad(dw2: torch.Tensor, wshape, transposed: bool) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------
 # raw launches
 # ------------------------------------------------------------------------------------------
-def _fill_desc(d: TapConvDesc, l: plans.Launch, x, y, cin, cout, w2, slope, gain, bias_scale, acc_scale=1.0):
+def _fill_desc(d: TapConvDesc, l: plans.Launch, x, y, cin, cout, w2, slope, gain, bias_scale, acc_scale=1.0,
+               noise=None):
     n = x.shape[0]
     d.N, d.IH, d.IW, d.Cin = n, x.shape[2], x.shape[3], cin
     d.OH, d.OW, d.Cout = y.shape[2], y.shape[3], cout
@@ -182,6 +199,7 @@ def _fill_desc(d: TapConvDesc, l: plans.Launch, x, y, cin, cout, w2, slope, gain
         d.dy[t], d.dx[t], d.wtap[t] = dy, dx, wt
     d.w_ld = w2.shape[1] if w2 is not None else len(l.taps) * cin
     d.acc_scale, d.bias_scale, d.slope, d.gain = acc_scale, bias_scale, slope, gain
+    d.noise, d.noise_scale = (noise.data_ptr(), 1.0) if noise is not None else (None, 0.0)
 
 
 _PROFILE_SHAPES = os.environ.get("LCGAN_PROFILE_SHAPES", "0") == "1"
@@ -259,9 +277,12 @@ def _tapconv_up2_fused(lib, d, x, w2, y, plan, rowscale, bias, slope, gain, bias
 
 
 def tapconv(x, w2, y, plan: plans.Plan, rowscale=None, bias=None, residual=None, slope=1.0, gain=1.0,
-            bias_scale=1.0, acc_scale=1.0):
-    """y = epilogue(tapconv(x, w2)) for every launch of the plan; x, y logical NCHW."""
+            bias_scale=1.0, acc_scale=1.0, noise=None):
+    """y = epilogue(tapconv(x, w2)) for every launch of the plan; x, y logical NCHW.  noise: optional
+    contiguous f32 [OH, OW] plane added before the activation (custom_layers.py:108-110)."""
     _need_cuda(x, w2, y)
+    if noise is not None:
+        assert noise.dtype == torch.float32 and noise.is_contiguous() and tuple(noise.shape) == (plan.OH, plan.OW)
     cout, cin = w2.shape[0], x.shape[1]
     assert w2.shape[1] == plan.k * plan.k * cin, (w2.shape, plan.k, cin)
     assert x.shape[2:] == (plan.IH, plan.IW) and y.shape[2:] == (plan.OH, plan.OW) and y.shape[1] == cout
@@ -272,11 +293,11 @@ def tapconv(x, w2, y, plan: plans.Plan, rowscale=None, bias=None, residual=None,
     st = _stream(x)
     d = TapConvDesc()
     if (_UP2_FUSED and _USE_TC and len(plan.launches) == 4 and plan.launches[0].os == 2 and residual is None
-            and cout % 16 == 0 and cin % 32 == 0 and cin <= _UP2_FUSED_MAX_CIN and x.dtype == torch.bfloat16
+            and noise is None and cout % 16 == 0 and cin % 32 == 0 and cin <= _UP2_FUSED_MAX_CIN and x.dtype == torch.bfloat16
             and w2.dtype == torch.bfloat16 and _is_cl_dense(x) and _is_cl_dense(y)):
         _tapconv_up2_fused(lib, d, x, w2, y, plan, rowscale, bias, slope, gain, bias_scale, acc_scale, st)
         return y
-    if len(plan.launches) == 4 and cout <= 4 and residual is None and plan.launches[0].os == 2:
+    if len(plan.launches) == 4 and cout <= 4 and residual is None and noise is None and plan.launches[0].os == 2:
         # x2 transposed conv of a flow layer: one fused launch for the four output phases
         _fill_desc(d, plan.launches[0], x, y, cin, cout, w2, slope, gain, bias_scale, acc_scale)
         if lib.lcgan_tapconv_up2_thin_eligible(C.byref(d)):
@@ -286,7 +307,7 @@ def tapconv(x, w2, y, plan: plans.Plan, rowscale=None, bias=None, residual=None,
                       nbytes=x.numel() * x.element_size() + y.numel() * y.element_size())
             return y
     for l in plan.launches:
-        _fill_desc(d, l, x, y, cin, cout, w2, slope, gain, bias_scale, acc_scale)
+        _fill_desc(d, l, x, y, cin, cout, w2, slope, gain, bias_scale, acc_scale, noise)
         fn = "lcgan_tapconv_tc" if (_USE_TC and lib.lcgan_tapconv_tc_eligible(C.byref(d))) else "lcgan_tapconv_simt"
         rows = x.shape[0] * l.MH * l.MW
         _lib.call(fn, C.byref(d), _ptr(x), _ptr(w2), _ptr(y), _ptr(rowscale), _ptr(bias), _ptr(residual), st,
@@ -677,17 +698,18 @@ class ModConvAct(torch.autograd.Function):
     First order only (the generator is never on the R1 path)."""
 
     @staticmethod
-    def forward(ctx, x, s, w, bias, d, wscale, plan, slope, gain, bias_scale, out_dtype, out_nchw):
+    def forward(ctx, x, s, w, bias, d, noise, wscale, plan, slope, gain, bias_scale, out_dtype, out_nchw):
         _need_cuda(x, s, w)
         assert _is_cl(x) and s.is_contiguous() and d.is_contiguous() and s.dtype == d.dtype == torch.float32
         compute = torch.float32 if x.dtype == torch.float32 else torch.bfloat16
         xs = _modulate_raw(x, s)
         w2 = pack_weight(w, False, compute)
         y = _alloc_out(x.shape[0], w2.shape[0], plan.OH, plan.OW, out_dtype, x.device, out_nchw)
-        tapconv(xs, w2, y, plan, d, bias, None, slope, gain, bias_scale, wscale)
+        tapconv(xs, w2, y, plan, d, bias, None, slope, gain, bias_scale, wscale, noise)
         del xs
         ctx.save_for_backward(x, s, w, bias, d, y)
         ctx.cfg = (wscale, plan, slope, gain, bias_scale)
+        ctx.has_noise, ctx.noise = noise is not None, noise
         return y
 
     @staticmethod
@@ -695,12 +717,16 @@ class ModConvAct(torch.autograd.Function):
     def backward(ctx, dy):
         x, s, w, bias, d, y = ctx.saved_tensors
         wscale, plan, slope, gain, bias_scale = ctx.cfg
-        need_x, need_s, need_w, need_b, need_d = ctx.needs_input_grad[:5]
+        need_x, need_s, need_w, need_b, need_d, need_nz = ctx.needs_input_grad[:6]
         compute = torch.float32 if x.dtype == torch.float32 else torch.bfloat16
         ycl = y if _is_cl(y) else _cl(y)
         g, r0, r1 = _act_bwd_raw(_cl(dy, ycl.dtype), ycl, d, slope, gain, need_b or need_d, need_d)
         # (g stays fp32 for the fp32-output layers - flow field, RGB - the thin kernels mix dtypes)
-        dx = ds = dw = db = dd = None
+        dx = ds = dw = db = dd = dnz = None
+        if ctx.has_noise and need_nz:
+            # d noise[h,w] = sum_{b,o} dz, dz = g / d[b,o]: a torch reduction, only on noise-enabled layers
+            # (cnn.py never enables them; custom_layers.py:98-101 keeps the option)
+            dnz = (g.float() / d[:, :, None, None]).sum(dim=(0, 1))
         if need_x or need_s:
             t = empty_cl(x.shape[0], x.shape[1], x.shape[2], x.shape[3], x.dtype, x.device)
             tapconv(g, pack_weight(w, True, compute), t, plans.adjoint(plan), acc_scale=wscale)
@@ -718,8 +744,12 @@ class ModConvAct(torch.autograd.Function):
         if need_b:
             db = r0.sum(0) * bias_scale
         if need_d:
-            dd = (r1 - (bias * bias_scale)[None] * r0) / d
-        return dx, ds, dw, db, dd, None, None, None, None, None, None, None
+            # r1 = sum_p dz * z with z = d*acc + bias (+ noise): remove the additive terms to get sum_p dz * acc
+            r1 = r1 - (bias * bias_scale)[None] * r0
+            if ctx.has_noise:
+                r1 = r1 - (g.float() * ctx.noise[None, None]).sum(dim=(2, 3)) / d
+            dd = r1 / d
+        return dx, ds, dw, db, dd, dnz, None, None, None, None, None, None, None
 
 
 class Warp(torch.autograd.Function):
@@ -837,8 +867,9 @@ class SumSq(torch.autograd.Function):
 _ema_tables = {}
 
 
-def ema_lerp_(dst_tensors, src_tensors, decay: float):
-    """dst = src.lerp(dst, decay) for every tensor pair, in ONE launch (ema.py:26-32)."""
+def ema_lerp_(dst_tensors, src_tensors, decay: float, decay_dev=None):
+    """dst = src.lerp(dst, decay) for every tensor pair, in ONE launch (ema.py:26-32).  decay_dev: optional
+    device f32 scalar that overrides `decay` (lets a captured CUDA graph follow the start_iter schedule)."""
     pairs = [(d, s) for d, s in zip(dst_tensors, src_tensors) if d.numel() > 0]
     if not pairs:
         return
@@ -855,4 +886,13 @@ def ema_lerp_(dst_tensors, src_tensors, decay: float):
         _ema_tables.clear()
         _ema_tables[key] = table
     _lib.call("lcgan_ema_lerp", _ptr(table[0]), _ptr(table[1]), _ptr(table[2]), len(pairs), C.c_float(decay),
-              _stream(pairs[0][0]), nbytes=3 * 4 * sum(k[2] for k in key))
+              _ptr(decay_dev), _stream(pairs[0][0]), nbytes=3 * 4 * sum(k[2] for k in key))
+    bump_generation()        # the destination parameters changed behind autograd's version counters
+
+
+def set_deterministic(flag: bool) -> bool:
+    """Ordered (turn-taking) reductions instead of fp32 atomics in every kernel that has them: two runs
+    on the same inputs are bit-identical.  Returns the previous setting.  (The rough-flow scatter
+    fallback of the warp backward stays atomic; smooth flows - everything at and near initialisation -
+    take the gather path, which is deterministic by construction.)"""
+    return bool(_lib.lib().lcgan_set_deterministic(1 if flag else 0))

@@ -12,7 +12,9 @@ import torch
 import torch.nn.functional as F
 
 from . import loss as L
+from . import ops
 from .ema import Ema
+from .optim import FusedAdam
 
 
 def requires_grad(model, flag=True):
@@ -78,10 +80,13 @@ def discriminator_loss(G, D, hp, it, z, data):
 class Trainer:
     """G, D (optionally DDP-wrapped), EMA copy and the two Adam optimizers (worker.py:75-112)."""
 
-    def __init__(self, G, D, hp, ema_decay=0.9999, ema_start=0, freeze_d_start=10 ** 9, freeze_d_layer=5):
+    def __init__(self, G, D, hp, ema_decay=0.9999, ema_start=0, freeze_d_start=10 ** 9, freeze_d_layer=5,
+                 fused_adam=True):
         self.G, self.D, self.hp = G, D, hp
-        self.g_opt = torch.optim.Adam(list(G.parameters()), lr=hp.lr, betas=(hp.beta1, hp.beta2), eps=1e-8)
-        self.d_opt = torch.optim.Adam(list(D.parameters()), lr=hp.lr, betas=(hp.beta1, hp.beta2), eps=1e-8)
+        # worker.py:98-110; fused_adam=False keeps torch.optim.Adam (what the reference's worker.py builds)
+        adam = FusedAdam if fused_adam else torch.optim.Adam
+        self.g_opt = adam(list(G.parameters()), lr=hp.lr, betas=(hp.beta1, hp.beta2), eps=1e-8)
+        self.d_opt = adam(list(D.parameters()), lr=hp.lr, betas=(hp.beta1, hp.beta2), eps=1e-8)
         self.G_ema = copy.deepcopy(_bare(G))
         self.ema = Ema(_bare(G), self.G_ema, ema_decay, ema_start)
         self.freeze_d_start, self.freeze_d_layer = freeze_d_start, freeze_d_layer
@@ -119,33 +124,46 @@ class GraphedTrainer(Trainer):
     (B200 guide: "capture launch-bound inner loops in CUDA graphs").  Five graphs cover the
     reference schedule: G even / G odd (+EMA), D even / D odd / D odd with R1.  Inputs are static
     device buffers that the caller fills before each replay; losses are left in device buffers.
-    Single-process only (DDP's reducer is not captured); requires_grad / freezeD flags are frozen
-    at capture time.
+    requires_grad / freezeD flags are frozen at capture time; the EMA decay is read from a device
+    scalar, so the ema.py:19-23 start_iter schedule is followed across replays.
+
+    world > 1: data parallel without the DDP wrapper (DDP's reducer is not capturable).  Rank 0's
+    initial weights are broadcast (what DDP's constructor does, worker.py:88-96); every parameter's
+    post-accumulate-grad hook copies the gradient into its slot of a flat bucket, and the moment a
+    bucket is complete its NCCL all-reduce (average) is issued on a side stream, so the exchange
+    overlaps the rest of backward (worker.py:88-96: DDP's bucketed overlap) - all captured in the graphs.
+    Parameters whose gradient stays None (unused heads on odd iterations, frozen layers) are skipped
+    by Adam exactly as under DDP(find_unused_parameters=True)  (dist_utils.GradExchange).
     """
 
     VARIANTS = ("g_even", "g_odd", "d_even", "d_odd", "d_r1")
+    BUCKET_BYTES = 48 << 20
 
     def __init__(self, G, D, hp, batch, device, world=1, **kw):
         super().__init__(G, D, hp, **kw)
         self.world = world
         if world > 1:
-            # data parallel without the DDP wrapper: rank 0's initial weights are broadcast (what DDP's
-            # constructor does, worker.py:88-96) and the gradient all-reduce is issued explicitly after
-            # backward, so it is captured into the graphs together with the kernels
             import torch.distributed as dist
+            from .dist_utils import GradExchange
             for t in list(G.parameters()) + list(G.buffers()) + list(D.parameters()) + list(D.buffers()):
                 dist.broadcast(t.data, 0)
             self.G_ema.load_state_dict(_bare(G).state_dict())
-        for opt in (self.g_opt, self.d_opt):          # Adam state on device so step() is capturable
-            for grp in opt.param_groups:
-                grp["capturable"] = True
-        res = _bare(G).img_resolution
-        self.z = {k: torch.zeros(batch, 64, device=device) for k in ("rand1", "rand2", "resample1", "resample2")}
-        self.zd = {k: torch.zeros(batch, 64, device=device) for k in ("rand1", "rand2")}
+            self.exchange = GradExchange({"g": G, "d": D}, device, world, self.BUCKET_BYTES)
+        for opt in (self.g_opt, self.d_opt):          # torch Adam: state on device so step() is capturable
+            if not isinstance(opt, FusedAdam):
+                for grp in opt.param_groups:
+                    grp["capturable"] = True
+        g = _bare(G)
+        res = g.img_resolution
+        dims = {"rand1": g.geo_noise_dim, "rand2": g.app_noise_dim, "resample1": g.geo_noise_dim,
+                "resample2": g.app_noise_dim}
+        self.z = {k: torch.zeros(batch, d, device=device) for k, d in dims.items()}
+        self.zd = {k: torch.zeros(batch, dims[k], device=device) for k in ("rand1", "rand2")}
         self.data = {k: torch.zeros(batch, 3, res, res, device=device)
                      for k in ("image", "geometry_change", "appearance_change")}
         self.g_loss = torch.zeros((), device=device)
         self.d_loss = torch.zeros((), device=device)
+        self.ema_decay = torch.full((), float(self.ema.decay_at(0)), device=device)
         self.graphs = {}
         self.launches = {}
 
@@ -155,35 +173,13 @@ class GraphedTrainer(Trainer):
             return "g_even" if it % 2 == 0 else "g_odd"
         return "d_even" if it % 2 == 0 else ("d_r1" if it % 8 == 1 else "d_odd")
 
-    def _allreduce_mean(self, params):
-        """Bucketed gradient all-reduce (mean) over NCCL - the one exchange step of the path."""
-        import torch.distributed as dist
-        grads = [p.grad for p in params if p.grad is not None]
-        bucket, size, cap = [], 0, 64 << 20
-        def flush():
-            if not bucket:
-                return
-            flat = torch.cat([g.reshape(-1) for g in bucket])
-            dist.all_reduce(flat)
-            flat.div_(self.world)
-            off = 0
-            for g in bucket:
-                g.copy_(flat[off:off + g.numel()].view_as(g))
-                off += g.numel()
-        for g in grads:
-            bucket.append(g); size += g.numel() * 4
-            if size >= cap:
-                flush(); bucket, size = [], 0
-        flush()
-
     def g_step(self, it, z):
         if self.world == 1:
             return super().g_step(it, z)
         requires_grad(self.G, True); requires_grad(self.D, False)
         self.g_opt.zero_grad()
         loss = generator_loss(self.G, self.D, self.hp, it, z)
-        loss.backward()
-        self._allreduce_mean(list(self.G.parameters()))
+        self.exchange.backward(loss, self.variant(it, "g"), "g")
         self.g_opt.step()
         return loss
 
@@ -195,28 +191,31 @@ class GraphedTrainer(Trainer):
             freeze_discriminator(self.D, self.freeze_d_layer)
         self.d_opt.zero_grad()
         loss = discriminator_loss(self.G, self.D, self.hp, it, z, data)
-        loss.backward()
-        self._allreduce_mean(list(self.D.parameters()))
+        frozen = "_frozen" if it >= self.freeze_d_start else ""      # a different set of gradients
+        self.exchange.backward(loss, self.variant(it, "d") + frozen, "d")
         self.d_opt.step()
         return loss
 
+    # ---- capture / replay -------------------------------------------------------------------------
+    _VARIANT_IT = {"g_even": 0, "g_odd": 3, "d_even": 0, "d_odd": 3, "d_r1": 1}
+
     def _run(self, name):
-        it = {"g_even": 0, "g_odd": 3, "d_even": 0, "d_odd": 3, "d_r1": 1}[name]
+        it = self._VARIANT_IT[name]
         if name.startswith("g"):
             loss = self.g_step(it, self.z)
-            self.ema.update(it)
+            self.ema.update(it, self.ema_decay)
             self.g_loss.copy_(loss.detach())
         else:
             loss = self.d_step(it, self.zd, self.data)
             self.d_loss.copy_(loss.detach())
 
     def capture(self, warmup=3):
-        from . import _lib, ops
+        from . import _lib
         dev = self.g_loss.device
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):                   # eager warm-up: lazy inits, Adam state
-            for _ in range(warmup):
+        with torch.cuda.stream(side):                   # eager warm-up: lazy inits, Adam state, bucket plans
+            for _ in range(max(warmup, 2)):
                 for name in self.VARIANTS:
                     self._run(name)
         torch.cuda.current_stream(dev).wait_stream(side)
@@ -248,10 +247,13 @@ class GraphedTrainer(Trainer):
 
     def replay_g(self, it):
         v = self.variant(it, "g")
+        self.ema_decay.fill_(float(self.ema.decay_at(it)))
         self.graphs[v].replay()
+        ops.bump_generation()          # the replay stepped the optimizer and the EMA behind autograd's back
         return self.launches[v]
 
     def replay_d(self, it):
         v = self.variant(it, "d")
         self.graphs[v].replay()
+        ops.bump_generation()
         return self.launches[v]

@@ -26,7 +26,7 @@ def _worker(rank, world, port, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from lcgan_b200 import cnn, dist_utils
-        from oracle.lcgan_oracle import Config
+        from lcgan_b200.config import Config
         res = {}
         res["local_batch"] = dist_utils.local_batch(32, world)
         res["seed"] = dist_utils.rank_seed(rank)
@@ -81,6 +81,58 @@ def test_two_rank_gloo_host_logic():
         assert r["max_ms"] == 11.0                       # max over ranks of 10, 11
         assert r["broadcast_ok"] and r["keys_prefixed"] and r["deepcopy_ok"]
         assert r["grad_avg_ok"] and r["frozen_ok"]
+
+
+def _exchange_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from lcgan_b200.dist_utils import GradExchange
+        torch.manual_seed(0)                               # same weights on every rank
+        net = torch.nn.Sequential(torch.nn.Linear(24, 40), torch.nn.Tanh(), torch.nn.Linear(40, 40), torch.nn.Tanh(),
+                                  torch.nn.Linear(40, 8))
+        unused = torch.nn.Linear(8, 8)                     # never touched by variant "a"
+        net.add_module("unused", unused)
+        fwd = lambda x: net[4](net[3](net[2](net[1](net[0](x)))))
+        ex = GradExchange({"n": net}, "cpu", world, bucket_bytes=4096)     # several buckets
+        torch.manual_seed(10 + rank)                       # different data per rank
+        xs = [torch.randn(6, 24) for _ in range(3)]
+        ok = True
+        for step, x in enumerate(xs):                      # step 0 records the order, 1..2 use the buckets
+            for variant in ("a", "b"):
+                net.zero_grad()
+                y = fwd(x)
+                loss = (y * y).mean() if variant == "a" else (unused(y) ** 2).mean()
+                ex.backward(loss, variant, "n")
+                mine = {k: (None if p.grad is None else p.grad.clone()) for k, p in net.named_parameters()}
+                # reference: plain backward + all-reduce of every gradient
+                net.zero_grad()
+                y = fwd(x)
+                loss = (y * y).mean() if variant == "a" else (unused(y) ** 2).mean()
+                loss.backward()
+                for k, p in net.named_parameters():
+                    if p.grad is None:
+                        ok &= mine[k] is None
+                        continue
+                    dist.all_reduce(p.grad); p.grad /= world
+                    ok &= mine[k] is not None and torch.allclose(mine[k], p.grad, rtol=1e-6, atol=1e-7)
+        out[rank] = {"ok": bool(ok), "buckets": len(ex.plans["a"].flats), "unused_none": mine is not None}
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_grad_exchange_matches_mean_of_rank_grads():
+    """dist_utils.GradExchange (the graph-capturable replacement of DDP's reducer): N-rank gradients ==
+    mean of the single-rank gradients, unused parameters keep grad None, several buckets per variant."""
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_exchange_worker, args=(world, port, out), nprocs=world, join=True)
+    for rank in range(world):
+        assert out[rank]["ok"], out[rank]
+        assert out[rank]["buckets"] >= 2
 
 
 def test_local_batch_rejects_bad_split():
