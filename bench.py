@@ -2,6 +2,7 @@
 """LC-GAN G+D training throughput on B200 (BASELINE.json metric), one JSON line on rank 0.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--res R] [--batch B] [--impl ours|reference]
+                  [--mode train|inference] [--freeze-d] [--config1]
 
 A *step* is one reference iteration (loader.py:44-54): generator step + EMA update + discriminator
 step on a global batch of B images, with the reference's loss schedule (aux losses on even
@@ -13,8 +14,11 @@ iteration index that is a multiple of 8, so K = 8*n covers whole schedule cycles
            copied from pinned host memory and both losses read back (.item()) every step
   roofline the dominant kernel (by summed device time in an event-instrumented pass): algorithmic
            FLOPs or bytes / event-measured duration, against MEASURED_PEAKS.json
-  cpu_baseline / --impl reference: the oracle port of the reference's CPU path (oracle/), timed on
-           the host cores on a bounded sample.
+  cpu_baseline / --impl reference: the reference's own modules (baseline/_ref: cnn.py, custom_layers.py, loss.py,
+           ema.py, unmodified) stepped by the restated worker.py schedule on the host cores (oracle/reference_arm.py),
+           on a bounded sample: half-iterations (alternating G and D steps) at batch 1 and the bench resolution.
+           --config1 runs BASELINE config 1 instead (256x256, batch 4, one warm-up iteration + one 8-iteration cycle).
+  --mode inference: BASELINE config 5 - generator_ema forward sweep over batch 1..64 (lcgan_b200.inference).
 """
 import argparse
 import json
@@ -47,6 +51,9 @@ def parse():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--freeze-d", action="store_true", help="post-freezeD schedule (worker.py:127-131)")
+    ap.add_argument("--mode", default="train", choices=["train", "inference"])
+    ap.add_argument("--config1", action="store_true",
+                    help="reference arm only: BASELINE config 1 (256x256 batch 4 on CPU, warm-up + one 8-iteration cycle)")
     return ap.parse_args()
 
 
@@ -112,52 +119,78 @@ class Clocks:
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference's CPU path
+# CPU arm: the reference's own modules on the host cores (oracle/reference_arm.py)
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_sample(res, iterations=(1, 0), budget_s=150.0):
-    """Time reference iterations 1 (G odd + D odd with R1) and 0 (G even + D even: aux + l_s) on the
-    host cores, fp32, all threads, at batch 1 and the bench resolution, through the oracle port.
-    Returns (img_per_s, cores, sample description)."""
-    import torch
-    from oracle import lcgan_oracle as O
+def _lr(res):
+    return 1e-3 if res == 1024 else 2e-3                     # README.md:29/45/49
+
+
+def cpu_reference_sample(res, half_steps=4, warmup=0, batch=1):
+    """Time `half_steps` half-iterations of the reference schedule (k even: G step + EMA of iteration k/2, k odd: D
+    step; 4 half-steps = iterations 0 and 1 = all four loss terms) on the host cores, fp32, all threads, at
+    `batch` and the bench resolution.  Returns (img_per_s, cores, kind, sample description, seconds per half-step)."""
+    from oracle import reference_arm as RA
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    cfg = O.Config(img_resolution=res)
-    hp = O.Hyper(lr=1e-3 if res == 1024 else 2e-3)
-    tr = O.OracleTrainer(cfg, hp, O.make_generator_state(cfg, 0), O.make_discriminator_state(cfg, 1))
-    gen = torch.Generator().manual_seed(1000)
-    b = 1
-    done, t_total = [], 0.0
-    for it in iterations:
-        zg, zd = O.synthetic_latents(b, cfg, gen), O.synthetic_latents(b, cfg, gen)
-        data = O.synthetic_data(b, cfg, gen)
-        t0 = time.perf_counter()
-        tr.iteration(it, zg, zd, data)
-        dt = time.perf_counter() - t0
-        done.append((it, dt)); t_total += dt
-        if t_total > budget_s / 3:
-            break
-    imgs = b * len(done)
-    desc = (f"oracle port (oracle/lcgan_oracle.py, torch CPU fp32, {torch.get_num_threads()} threads): full "
-            f"iterations {[i for i, _ in done]} at batch {b}, {res}x{res} "
-            f"({', '.join(f'it{i}={t:.1f}s' for i, t in done)}); img/s = images / time of these iterations"
-            + ("" if any(i % 2 == 0 for i, _ in done) else
-               " (odd iterations are the cheap ones - 1 G + 2 D passes - so this flatters the CPU by ~1.5x)"))
-    return imgs / t_total, cores, desc
+    tr, kind, what = RA.make_trainer(res, _lr(res), batch, cores)
+    if warmup:
+        RA.time_half_steps(tr, 0, warmup)
+    ts = RA.time_half_steps(tr, warmup, half_steps)
+    import torch
+    imgs = batch * half_steps / 2.0
+    desc = (f"{what}; torch CPU fp32, {torch.get_num_threads()} threads; half-iterations {warmup}..{warmup + half_steps - 1} "
+            f"of the reference schedule (even = G step + EMA, odd = D step; R1 at iteration 1) at batch {batch}, {res}x{res}: "
+            f"{', '.join(f'{t:.1f}s' for t in ts)}; img/s = batch * half_steps / 2 / time")
+    return imgs / sum(ts), cores, kind, desc, ts
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    v, cores, desc = cpu_reference_sample(args.res)
+    if args.config1:
+        return run_config1(args)
+    K, W = args.steps, args.warmup
+    v, cores, kind, desc, ts = cpu_reference_sample(args.res, half_steps=K, warmup=W)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "img/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * args.batch / v,
+            "steps": K, "warmup": W, "ms_per_step": 1000.0 * sum(ts) / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args.res, args.batch), "note": "CPU arm runs on host cores only"},
-            "cpu_baseline": {"value": v, "unit": "img/s", "cores": cores, "kind": "port", "sample": desc},
+            "config": {"workload": workload_name(args.res, args.batch), "resolution": args.res,
+                       "sample_batch": 1, "step": "one half-iteration (G step + EMA, or D step) of the reference "
+                       "schedule at batch 1 - a bounded sample of the batch-32 iteration",
+                       "note": "CPU arm runs on host cores only"},
+            "cpu_baseline": {"value": v, "unit": "img/s", "cores": cores, "kind": kind, "sample": desc},
             "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    _emit(line)
+
+
+def run_config1(args):
+    """BASELINE.json configs[0] / BASELINE.md section 4: 256x256, batch 4, CPU: one warm-up iteration, then one
+    8-iteration cycle (all loss variants at the reference's frequencies), per-variant step times."""
+    from oracle import reference_arm as RA
+    res, batch = 256, 4
+    cores = os.cpu_count() or 1
+    tr, kind, what = RA.make_trainer(res, _lr(res), batch, cores)
+    RA.time_half_steps(tr, 0, 2)                               # iteration 0 as warm-up
+    ts = RA.time_half_steps(tr, 16, 16)                        # iterations 8..15: one whole cycle
+    names = {}
+    for k, t in zip(range(16, 32), ts):
+        it = k // 2
+        v = ("G even" if it % 2 == 0 else "G odd") if k % 2 == 0 else \
+            ("D even" if it % 2 == 0 else ("D odd + R1" if it % 8 == 1 else "D odd"))
+        names.setdefault(v, []).append(round(t, 2))
+    total = sum(ts)
+    value = batch * 8 / total
+    import torch
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": 0, "steps": 8, "warmup": 1,
+            "ms_per_step": 1000.0 * total / 8, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "LC-GAN 256x256 G+D training (adv + aux + R1 + l_s at reference frequencies) batch 4 on CPU",
+                       "resolution": res, "global_batch": batch, "schedule": "iterations 8..15 (one 8-iteration cycle)",
+                       "step_seconds": names},
+            "cpu_baseline": {"value": value, "unit": "img/s", "cores": cores, "kind": kind,
+                             "sample": f"{what}; {torch.get_num_threads()} threads; BASELINE config 1, full cycle"},
+            "e2e": {"value": value, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     _emit(line)
 
 
@@ -182,6 +215,8 @@ def main():
     os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.mode == "inference":
+        return run_inference(args)
 
     import torch
     import torch.distributed as dist
@@ -343,8 +378,8 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         del tr, G, D
         torch.cuda.empty_cache()
-        v, cores, desc = cpu_reference_sample(res, iterations=(1,))
-        cpu = {"value": v, "unit": "img/s", "cores": cores, "kind": "port", "sample": desc}
+        v, cores, kind, desc, _ = cpu_reference_sample(res, half_steps=4)
+        cpu = {"value": v, "unit": "img/s", "cores": cores, "kind": kind, "sample": desc}
 
     if rank == 0:
         flop = FLOP_PER_IMG_ITER.get(res)
@@ -372,14 +407,17 @@ def main():
 
 def roofline_pass(step_fn, it0, _lib, pk):
     """One extra (untimed-for-the-headline) cycle with a CUDA event pair around every launch of our
-    library: per-kernel device time, algorithmic FLOPs (tap convs) and bytes.  The dominant kernel
-    by summed time is the one reported."""
+    library: per-kernel device time, algorithmic FLOPs (tap convs) and bytes, tap convs tagged by shape.
+    The dominant kernel by summed time is the one reported, at its dominant shape."""
     import torch
+    from lcgan_b200 import ops
+    ops.set_profile_shapes(True)
     _lib.profile_begin()
     for i in range(8):
         step_fn(it0 + i)
     torch.cuda.synchronize()
     stats = _lib.profile_end()
+    ops.set_profile_shapes(False)
     traffic = {}
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tp):
@@ -388,44 +426,149 @@ def roofline_pass(step_fn, it0, _lib, pk):
 
 
 def summarise_kernels(stats, pk, traffic_table):
-    """stats: {kernel: {n, ms, flops, bytes}} from the instrumented cycle -> (roofline object of the
-    dominant kernel, the 12 heaviest kernels).  A tap-conv kernel is held against the tensor peak, every
-    other kernel against the HBM peak; `hbm_top` adds the heaviest memory-bound kernel when the dominant
-    one is a tensor-core kernel."""
+    """stats: {"kernel" or "kernel|shape": {n, ms, flops, bytes}} from the instrumented cycle -> (roofline object,
+    the 12 heaviest kernels).  The roofline object describes the dominant kernel AT ITS DOMINANT SHAPE (most summed
+    time): algorithmic FLOPs and bytes per launch over the event-measured launch time; a shape whose arithmetic
+    intensity is below the measured ridge is held against the HBM peak, otherwise against the sustained bf16 peak.
+    `traffic` is the ncu DRAM byte count of that same shape when profiles/ncu_traffic.json has it.  `all_shapes`
+    keeps the kernel's aggregate, `hbm_top` the heaviest pure memory kernel."""
+    per_kernel, shapes = {}, {}
+    for name, st in stats.items():
+        k = name.split("|")[0]
+        agg = per_kernel.setdefault(k, {"n": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+        for f in agg:
+            agg[f] += st[f]
+        if "|" in name:
+            shapes.setdefault(k, {})[name.split("|", 1)[1]] = st
     rows = []
-    for name, s in stats.items():
-        rows.append({"kernel": name, "launches": s["n"], "ms": s["ms"], "tflops": (s["flops"] / (s["ms"] / 1e3) / 1e12)
-                     if s["flops"] and s["ms"] > 0 else None,
-                     "gbs": (s["bytes"] / (s["ms"] / 1e3) / 1e9) if s["bytes"] and s["ms"] > 0 else None})
+    for name, st in per_kernel.items():
+        rows.append({"kernel": name, "launches": st["n"], "ms": st["ms"],
+                     "tflops": (st["flops"] / (st["ms"] / 1e3) / 1e12) if st["flops"] and st["ms"] > 0 else None,
+                     "gbs": (st["bytes"] / (st["ms"] / 1e3) / 1e9) if st["bytes"] and st["ms"] > 0 else None})
     if not rows:
         return None, []
     rows.sort(key=lambda r: -r["ms"])
     total = sum(r["ms"] for r in rows) or 1.0
     for r in rows:
         r["share"] = r["ms"] / total
+    ridge = pk["tensor_sustained"] * 1e12 / (pk["hbm"] * 1e9)       # FLOP per byte
 
-    def hbm_obj(r):
-        s = stats[r["kernel"]]
-        return {"kernel": r["kernel"], "bound": "hbm", "achieved": r["gbs"], "peak": pk["hbm"], "unit": "GB/s",
-                "frac": (r["gbs"] or 0) / pk["hbm"], "traffic": traffic_table.get(r["kernel"]),
-                "peak_source": pk["src"], "avg_launch_ms": s["ms"] / max(s["n"], 1), "share_of_step": r["share"],
-                "bytes_per_launch": s["bytes"] / max(s["n"], 1)}
+    def obj(kernel, st, share, shape=None):
+        n = max(st["n"], 1)
+        t = st["ms"] / 1e3
+        ai = st["flops"] / st["bytes"] if st["flops"] and st["bytes"] else 0.0
+        key = kernel if shape is None else f"{kernel}|{shape}"
+        o = {"kernel": kernel, "shape": shape, "launches": st["n"], "avg_launch_ms": st["ms"] / n, "share_of_step": share,
+             "flop_per_launch": st["flops"] / n, "bytes_per_launch": st["bytes"] / n,
+             "traffic": traffic_table.get(key), "timing": "CUDA event pair around every launch, eager pass"}
+        if st["flops"] and ai >= ridge:
+            a = st["flops"] / t / 1e12
+            o.update({"bound": "tensor", "achieved": a, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
+                      "frac": a / pk["tensor_sustained"],
+                      "peak_source": pk["src"] + " (sustained: kernel timed inside a long step)"})
+        else:
+            a = st["bytes"] / t / 1e9 if t > 0 else 0.0
+            o.update({"bound": "hbm", "achieved": a, "peak": pk["hbm"], "unit": "GB/s", "frac": a / pk["hbm"],
+                      "peak_source": pk["src"]})
+            if st["flops"]:
+                o["tflops"] = st["flops"] / t / 1e12
+        return o
 
     top = rows[0]
-    s = stats[top["kernel"]]
-    if top["tflops"] is not None and "tapconv" in top["kernel"]:
-        roof = {"kernel": top["kernel"], "bound": "tensor", "achieved": top["tflops"], "peak": pk["tensor_sustained"],
-                "unit": "TFLOP/s", "frac": top["tflops"] / pk["tensor_sustained"],
-                "traffic": traffic_table.get(top["kernel"]),
-                "peak_source": pk["src"] + " (sustained: kernel timed inside a long step)",
-                "avg_launch_ms": s["ms"] / max(s["n"], 1), "share_of_step": top["share"],
-                "flop_per_launch": s["flops"] / max(s["n"], 1)}
-        mem = [r for r in rows if r["tflops"] is None and r["gbs"] is not None]
-        if mem:
-            roof["hbm_top"] = hbm_obj(mem[0])
+    sh = shapes.get(top["kernel"])
+    if sh:
+        name, st = max(sh.items(), key=lambda kv: kv[1]["ms"])
+        roof = obj(top["kernel"], st, st["ms"] / total, name)
+        roof["all_shapes"] = {"launches": top["launches"], "share_of_step": top["share"], "tflops": top["tflops"],
+                              "gbs": top["gbs"], "frac_of_tensor_peak": (top["tflops"] or 0) / pk["tensor_sustained"]}
+        roof["shapes"] = [dict(shape=k, launches=v["n"], ms=v["ms"],
+                               tflops=v["flops"] / (v["ms"] / 1e3) / 1e12 if v["flops"] and v["ms"] > 0 else None,
+                               gbs=v["bytes"] / (v["ms"] / 1e3) / 1e9 if v["bytes"] and v["ms"] > 0 else None)
+                          for k, v in sorted(sh.items(), key=lambda kv: -kv[1]["ms"])[:10]]
     else:
-        roof = hbm_obj(top)
+        roof = obj(top["kernel"], per_kernel[top["kernel"]], top["share"])
+    mem = [r for r in rows if r["tflops"] is None and r["gbs"] is not None]
+    if mem and mem[0]["kernel"] != top["kernel"]:
+        roof["hbm_top"] = obj(mem[0]["kernel"], per_kernel[mem[0]["kernel"]], mem[0]["share"])
     return roof, rows[:12]
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE config 5: generator-only inference sweep (worker.py:427-441, 447-485)
+# ---------------------------------------------------------------------------------------------
+G_GMAC_PER_IMG = {256: 56.3, 512: 71.5, 1024: 86.9}          # SURVEY section 8a (forward MACs per image)
+
+
+def run_inference(args):
+    import torch
+    import copy
+    from lcgan_b200 import _lib, cnn, ops
+    from lcgan_b200.config import Config
+    from lcgan_b200.inference import GeneratorRunner
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    _lib.build()
+    ops.set_precision(args.precision)
+    res = args.res
+    torch.manual_seed(0)
+    G = cnn.Generator(Config(img_resolution=res).namespace()).to(dev)
+    with torch.no_grad():                                     # a few training-mode forwards give avg_latent a value
+        for _ in range(3):
+            G(torch.randn(8, 64, device=dev), torch.randn(8, 64, device=dev))
+    runner = GeneratorRunner(copy.deepcopy(G), w_psi=0.7)
+    K, W = args.steps, max(args.warmup, 3)
+    sweep, clocks, pk = [], None, peaks()
+    flop_img = 2 * G_GMAC_PER_IMG.get(res, 0) * 1e9
+    for b in runner.batch_sizes:
+        zg, za = runner.static_inputs(b)
+        hz = [torch.randn(b, 64).pin_memory(), torch.randn(b, 64).pin_memory()]
+        hout = torch.empty(b, 3, res, res, dtype=torch.uint8).pin_memory()
+        for _ in range(W):
+            zg.normal_(); za.normal_(); runner.replay(b)
+        torch.cuda.synchronize()
+        if b == runner.batch_sizes[-1]:
+            clocks = Clocks(dev.index or 0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            zg.normal_(); za.normal_()
+            runner.replay(b)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / K
+        # end to end: latents from pinned host memory, uint8 images back to pinned host memory, every step
+        e0.record()
+        for _ in range(K):
+            zg.copy_(hz[0], non_blocking=True); za.copy_(hz[1], non_blocking=True)
+            _, _, u8 = runner.replay(b)
+            hout.copy_(u8, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_e = e0.elapsed_time(e1) / K
+        sweep.append({"batch": b, "ms": ms, "img_s": b / ms * 1e3, "e2e_img_s": b / ms_e * 1e3,
+                      "tflops": b * flop_img / (ms / 1e3) / 1e12 if flop_img else None,
+                      "frac_of_bf16_peak_sustained": b * flop_img / (ms / 1e3) / 1e12 / pk["tensor_sustained"] if flop_img else None,
+                      "launches_per_forward": runner.launches[b]})
+    clk = clocks.stop() if clocks else None
+    best = max(sweep, key=lambda r: r["img_s"])
+    bl = runner.batch_sizes[-1]
+    line = {"metric": "generator-only inference img/s", "value": best["img_s"], "unit": "img/s", "n_gpus": 1, "steps": K,
+            "warmup": W, "ms_per_step": best["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": f"LC-GAN {res}x{res} generator-only inference sweep (generator_ema, w_psi 0.7, batch 1-64), "
+                                   "random-init weights", "resolution": res, "best_batch": best["batch"],
+                       "cuda_graphs": True, "l2": "activations per layer exceed the 126 MB L2 from batch 2 up",
+                       "g_forward_gmac_per_img": G_GMAC_PER_IMG.get(res), "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9},
+            "clocks": clk,
+            "e2e": {"value": best["e2e_img_s"], "unit": "img/s", "h2d_bytes_per_step": best["batch"] * 2 * 64 * 4,
+                    "d2h_bytes_per_step": best["batch"] * 3 * res * res},
+            "gpu_launches": sum(runner.launches[b] for b in runner.batch_sizes) * (2 * K + W), "sweep": sweep,
+            "roofline": {"kernel": "generator forward (all kernels)", "bound": "tensor", "achieved": best["tflops"],
+                         "peak": pk["tensor_sustained"], "unit": "TFLOP/s", "frac": best["frac_of_bf16_peak_sustained"],
+                         "traffic": None, "peak_source": pk["src"]},
+            "cpu_baseline": None}
+    _emit(line)
 
 
 if __name__ == "__main__":

@@ -205,6 +205,20 @@ typedef struct lcgan_pack_chunk {
  * for up to LCGAN_MT_MAX weights in one launch; dt = dtype code of the packs. */
 int lcgan_pack_weights(const lcgan_pack_chunk* chunk, int dt, void* stream);
 
+/* ---- weight-/[b,C]-sized pieces of the modulated convolution (demod.cu; custom_layers.py:62-68) --- */
+/* d[b,o] = rsqrt(sum_c s[b,c]^2 wsq[o,c] + eps); s [B,I], wsq [O,I] (lcgan_pack_weights mode 2), d [B,O], all f32 */
+int lcgan_demod_fwd(const float* s, const float* wsq, float* d, int B, int O, int I, float eps, void* stream);
+/* backward of the above through q = sum_c s^2 wsq: with dq = -0.5 dd d^3,
+ *   ds[b,c] = 2 s[b,c] sum_o dq[b,o] wsq[o,c]                         (ds may be NULL)
+ *   dw[o,c,k] = 2 wscale^2 round_dt(w[o,c,k]) sum_b dq[b,o] s[b,c]^2    (dw [O,I,K] f32, may be NULL) */
+int lcgan_demod_bwd(const float* dd, const float* d, const float* s, const float* wsq, const float* w,
+                    float* ds, float* dw, int B, int O, int I, int K, float wscale, int dt, void* stream);
+/* Parameter-side gradients of the fused epilogue from the per-(b,o) sums of lcgan_act_bwd:
+ *   db[o] = bias_scale sum_b r0[b,o];   dd[b,o] = (r1[b,o] - bias[o] bias_scale r0[b,o]) / d[b,o]
+ * db or dd may be NULL (dd needs r1 and d; bias may be NULL). */
+int lcgan_epilogue_grads(const float* r0, const float* r1, const float* bias, const float* d, float bias_scale,
+                         float* db, float* dd, int B, int O, void* stream);
+
 /* Deterministic mode: reductions that finish with fp32 atomics (split-K weight gradients, per-(b,c)
  * sums) take ordered turns instead, so repeated runs are bit-identical.  Returns the previous setting.
  * Kernels launched in this mode must not run concurrently on two streams. */

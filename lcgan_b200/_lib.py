@@ -13,7 +13,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "liblcgan_b200.so")
-_SRCS = ["api.cu", "conv_simt.cu", "conv_tc.cu", "thin.cu", "resample.cu", "warp.cu", "loss.cu", "optim.cu"]
+_SRCS = ["api.cu", "conv_simt.cu", "conv_tc.cu", "thin.cu", "resample.cu", "warp.cu", "loss.cu", "optim.cu", "demod.cu"]
 _lock = threading.Lock()
 _lib = None
 
@@ -130,6 +130,10 @@ _SIGS = {
     "lcgan_adam_step": ([C.POINTER(AdamChunk), C.c_float, C.c_float, C.c_float, C.c_float, _VOIDP], C.c_int),
     "lcgan_pack_weights": ([C.POINTER(PackChunk), C.c_int, _VOIDP], C.c_int),
     "lcgan_set_deterministic": ([C.c_int], C.c_int),
+    "lcgan_demod_fwd": ([_FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_float, _VOIDP], C.c_int),
+    "lcgan_demod_bwd": ([_FP, _FP, _FP, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                         _VOIDP], C.c_int),
+    "lcgan_epilogue_grads": ([_FP, _FP, _FP, _FP, C.c_float, _FP, _FP, C.c_int, C.c_int, _VOIDP], C.c_int),
 }
 EXPORTS = tuple(_SIGS) + ("lcgan_last_error",)
 
@@ -158,8 +162,10 @@ def check(rc: int, what: str):
         raise RuntimeError(f"{what} failed (code {rc}): {lib().lcgan_last_error().decode()}")
 
 
-# launch counter: bench.py reports how many of OUR kernels ran inside the timed region
+# launch counters: bench.py reports how many of OUR kernels ran inside the timed region; `counts` keeps
+# them per entry point (tests assert e.g. that no weight-gradient kernel runs inside cal_derivative)
 launches = 0
+counts = {}
 
 
 _prof = None
@@ -192,6 +198,7 @@ def call(name: str, *args, flops=0, nbytes=0, tag=None):
     ALGORITHMIC work of the launch, used only by the profiling pass."""
     global launches
     launches += 1
+    counts[name] = counts.get(name, 0) + 1
     if _prof is None:
         check(getattr(lib(), name)(*args), name)
         return

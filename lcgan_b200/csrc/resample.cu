@@ -375,9 +375,11 @@ act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict_
         body(g, yy, off);
       }
     }
-    if (sems) {
-      // deterministic mode: fixed-order sum over the pixel lanes of the block, then the blocks of
-      // this image add in blockIdx.x order (common.cuh)
+    if (r0 || r1) {
+      // fixed-order sum over the pixel lanes of the block through shared memory, then ONE atomic per
+      // (b,c) and block.  (Per-thread atomics put gridDim.x * lanes ~ 10^4 adds on each of a few hundred
+      // addresses - at batch 4 the L2 atomic units serialised them into 0.5 ms per launch.)
+      // Deterministic mode: the blocks of an image add in blockIdx.x order instead (common.cuh).
       __shared__ float red[kThreads * V];
       const bool first = active && (int)threadIdx.x < ncv;
       auto lane_sum = [&](float* sv) {
@@ -394,24 +396,20 @@ act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict_
       };
       if (r0) lane_sum(s0);
       if (r1) lane_sum(s1);
-      det_block_begin(sems + b, blockIdx.x);
+      if (sems) det_block_begin(sems + b, blockIdx.x);
       if (first) {
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-          if (r0) det_add(r0 + (int64_t)b * C + c + i, s0[i]);
-          if (r1) det_add(r1 + (int64_t)b * C + c + i, s1[i]);
+          if (sems) {
+            if (r0) det_add(r0 + (int64_t)b * C + c + i, s0[i]);
+            if (r1) det_add(r1 + (int64_t)b * C + c + i, s1[i]);
+          } else {
+            if (r0) atomicAdd(r0 + (int64_t)b * C + c + i, s0[i]);
+            if (r1) atomicAdd(r1 + (int64_t)b * C + c + i, s1[i]);
+          }
         }
       }
-      det_block_end(sems + b, blockIdx.x, gridDim.x);
-    } else if (active) {
-      if (r0) {
-#pragma unroll
-        for (int i = 0; i < V; ++i) atomicAdd(r0 + (int64_t)b * C + c + i, s0[i]);
-      }
-      if (r1) {
-#pragma unroll
-        for (int i = 0; i < V; ++i) atomicAdd(r1 + (int64_t)b * C + c + i, s1[i]);
-      }
+      if (sems) det_block_end(sems + b, blockIdx.x, gridDim.x);
     }
   }
 }
@@ -489,8 +487,8 @@ modulate_bwd_kernel(const T* __restrict__ x, const T* __restrict__ t, const floa
         stv<T, V>(dx + off, tv);
       }
     }
-    if (sems) {
-      // deterministic mode (see act_bwd_kernel)
+    {
+      // block-level sum over the pixel lanes, then one atomic per (b,c) and block (see act_bwd_kernel)
       __shared__ float red[kThreads * V];
       const bool first = active && (int)threadIdx.x < ncv;
       __syncthreads();
@@ -503,15 +501,15 @@ modulate_bwd_kernel(const T* __restrict__ x, const T* __restrict__ t, const floa
         for (int l = 1; l < lanes; ++l)
 #pragma unroll
           for (int i = 0; i < V; ++i) acc[i] += red[(l * ncv + threadIdx.x) * V + i];
-      det_block_begin(sems + b, blockIdx.x);
+      if (sems) det_block_begin(sems + b, blockIdx.x);
       if (first) {
 #pragma unroll
-        for (int i = 0; i < V; ++i) det_add(ds + (int64_t)b * C + c + i, acc[i]);
+        for (int i = 0; i < V; ++i) {
+          if (sems) det_add(ds + (int64_t)b * C + c + i, acc[i]);
+          else atomicAdd(ds + (int64_t)b * C + c + i, acc[i]);
+        }
       }
-      det_block_end(sems + b, blockIdx.x, gridDim.x);
-    } else if (active) {
-#pragma unroll
-      for (int i = 0; i < V; ++i) atomicAdd(ds + (int64_t)b * C + c + i, acc[i]);
+      if (sems) det_block_end(sems + b, blockIdx.x, gridDim.x);
     }
   }
 }

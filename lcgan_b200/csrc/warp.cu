@@ -192,7 +192,7 @@ warp_bwd_kernel(const T* __restrict__ x, const float* __restrict__ flow, const T
           gix = fmaf(dot, tgx.w[k], gix);
           giy = fmaf(dot, tgy.w[k], giy);
           const float wgt = tp.w[k];
-          if (wgt != 0.f) {
+          if (wgt != 0.f && dx) {                // dx == nullptr: flow gradient only
             float* dp = dx + boff + (int64_t)tp.off[k] * C + v * V;
             if constexpr (V % 4 == 0) {
 #pragma unroll
@@ -217,6 +217,47 @@ warp_bwd_kernel(const T* __restrict__ x, const float* __restrict__ flow, const T
       const float d0 = gix * (0.5f * (float)W) * scale * (1.f - pc.th0 * pc.th0);
       const float d1 = giy * (0.5f * (float)H) * scale * (1.f - pc.th1 * pc.th1);
       *reinterpret_cast<float2*>(dflow + pix * 2) = make_float2(d0, d1);
+    }
+  }
+}
+
+// dx by GATHER over a fixed window, for images too small for the tiled kernels (the 8x8 / 16x16 blocks): source
+// pixel s collects w(s,p) g[p] from every output pixel p with |p - s| <= R per axis, R = the largest displacement
+// the bounded flow (|tanh| * scale) plus the bicubic footprint allow.  No atomics: deterministic mode uses it in
+// place of the scatter kernel.  A group of G lanes owns one source pixel and strides over its channel vectors.
+template <typename T, int V>
+__global__ void __launch_bounds__(kThreads)
+warp_dx_window_kernel(const float* __restrict__ flow, const T* __restrict__ dout, T* __restrict__ dx, int N, int H,
+                      int W, int C, float scale, int G, int Rx, int Ry) {
+  const int cv = C / V;
+  const int64_t npix = (int64_t)N * H * W;
+  const int gl = threadIdx.x % G;
+  const int64_t groups_per_grid = (int64_t)gridDim.x * (kThreads / G);
+  for (int64_t pix = blockIdx.x * (int64_t)(kThreads / G) + threadIdx.x / G; pix < npix; pix += groups_per_grid) {
+    const int sx = (int)(pix % W);
+    const int sy = (int)((pix / W) % H);
+    const int b = (int)(pix / ((int64_t)W * H));
+    const int64_t boff = (int64_t)b * H * W;
+    for (int v0 = gl; v0 < cv; v0 += G) {
+      float acc[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[i] = 0.f;
+      for (int h = max(sy - Ry, 0); h <= min(sy + Ry, H - 1); ++h)
+        for (int w = max(sx - Rx, 0); w <= min(sx + Rx, W - 1); ++w) {
+          const int64_t p = boff + (int64_t)h * W + w;
+          const PixCoord pc = source_index(flow, p, h, w, H, W, scale);
+          const int i = sx - pc.x0 + 1, j = sy - pc.y0 + 1;       // tap indices of s in p's footprint
+          if (i < 0 || i > 3 || j < 0 || j > 3) continue;
+          float wx[4], wy[4];
+          cubic_w(pc.tx, wx);
+          cubic_w(pc.ty, wy);
+          const float wgt = wy[j] * wx[i];
+          float g[V];
+          ldv<T, V>(dout + p * C + v0 * V, g);
+#pragma unroll
+          for (int k = 0; k < V; ++k) acc[k] = fmaf(g[k], wgt, acc[k]);
+        }
+      stv<T, V>(dx + pix * C + v0 * V, acc);
     }
   }
 }
@@ -838,6 +879,25 @@ extern "C" int lcgan_warp_bwd_tiled(const void* x, const float* flow, const void
     }
     LCGAN_LAUNCH_CHECK();
     skip = flag;                                          // the rest runs only if a tile gave up
+  }
+  if (!skip && lcgan_det_enabled()) {
+    // deterministic mode, image too small for the tiles: flow gradient from the per-pixel kernel (no dx),
+    // dx from the window gather (no atomics)
+    const int Rx = (int)(2.5f + fabsf(flow_scale) * 0.5f * (float)W) + 1, Ry = (int)(2.5f + fabsf(flow_scale) * 0.5f * (float)H) + 1;
+    const int64_t npix = (int64_t)N * H * W;
+#define CALLD(T, V)                                                                                             \
+  do {                                                                                                          \
+    const int G = group_size(C / V);                                                                            \
+    warp_bwd_kernel<T, V><<<grid_for_groups(npix, G), kThreads, 0, s>>>(                                        \
+        (const T*)x, flow, (const T*)dout, nullptr, dflow, N, H, W, C, flow_scale, G, nullptr);                 \
+    warp_dx_window_kernel<T, V><<<grid_for_groups(npix, G), kThreads, 0, s>>>(                                  \
+        flow, (const T*)dout, (T*)dx, N, H, W, C, flow_scale, G, Rx, Ry);                                       \
+  } while (0)
+    if (dt == LCGAN_F32) { if (C % 4 == 0) CALLD(float, 4); else CALLD(float, 1); }
+    else { if (C % 8 == 0) CALLD(bf16, 8); else CALLD(bf16, 1); }
+#undef CALLD
+    LCGAN_LAUNCH_CHECK();
+    return 0;
   }
   zero_unless_tiled_kernel<<<egrid, 256, 0, s>>>(reinterpret_cast<float4*>(acc), n4, skip);
   launch_atomic_bwd(x, flow, dout, acc, dflow, dt, N, H, W, C, flow_scale, skip, s);

@@ -98,19 +98,17 @@ class ModulatedConv2d(nn.Module):
         (SynthesisLayer's noise injection, fused into the conv epilogue)."""
         w = self.weight.weight
         c = float(self.weight.c)
-        # demodulation coefficients, fp32: d[b,o] = rsqrt(s^2 @ Wsq^T + eps)
+        # demodulation coefficients, fp32: d[b,o] = rsqrt(s^2 @ Wsq^T + eps), Wsq cached per weight version
         # (from the weights as the conv sees them: rounded to the compute dtype, scaled in fp32)
-        wq = w.to(ops.act_dtype()).float() if ops.act_dtype() != torch.float32 else w
-        wsq = (wq * c).square().sum(dim=(2, 3))
-        s = s.float()
-        d = torch.rsqrt(ops.linear_act(s * s, wsq, None, wscale=1.0, bias_scale=1.0) + self.eps)
+        s = s.float().contiguous()
+        d = ops.Demod.apply(s, w, c, float(self.eps), ops.act_dtype())
         if self.up > 1:
             plan = plans.conv_transpose_up2(self.kernel_size, x.shape[2], x.shape[3])
         else:
             plan = plans.conv(self.kernel_size, 1, x.shape[2], x.shape[3])
         if noise is not None:
             noise = noise.float().contiguous()
-        return ops.ModConvAct.apply(_as_act(x), s.contiguous(), w, self.bias, d.contiguous(), noise, c, plan, slope,
+        return ops.ModConvAct.apply(_as_act(x), s, w, self.bias, d, noise, c, plan, slope,
                                     gain, float(self.lr_mul), out_dtype or ops.act_dtype(), out_nchw)
 
 

@@ -25,7 +25,8 @@ from torch.autograd.function import once_differentiable
 from . import _lib, plans
 from ._lib import BF16, F32, TapConvDesc
 
-_ACT_DTYPE = torch.bfloat16
+# LCGAN_PRECISION=fp32 selects the accurate mode at import (the reference's unmodified main.py has no flag for it)
+_ACT_DTYPE = torch.float32 if os.environ.get("LCGAN_PRECISION", "bf16") == "fp32" else torch.bfloat16
 _USE_TC = os.environ.get("LCGAN_DISABLE_TC", "0") != "1"
 
 
@@ -119,9 +120,10 @@ def _strides_nhwc(t):
 
 
 # ------------------------------------------------------------------------------------------
-# weight packing (cached per parameter version)
+# weight packing and derived weight tables (cached per parameter version)
 # ------------------------------------------------------------------------------------------
-_pack_cache = {}
+_pack_cache = {}      # (id(w), kind) -> (tag, tensor);  kind = ("pack", transposed, dtype) | ("wsq", dtype, c)
+_demand = {}          # id(w) -> set of kinds ever requested for that parameter (what prepack refreshes)
 _pack_lock = threading.Lock()
 # Bumped by everything that rewrites parameters through raw pointers (ema_lerp_, the fused Adam kernel,
 # CUDA-graph replays that contain an optimizer step): those writes do not move Tensor._version, so the
@@ -135,36 +137,137 @@ def bump_generation():
     _generation += 1
 
 
+def _tag(w):
+    return (w._version, w.data_ptr(), _generation)
+
+
+def _forget(wid):
+    with _pack_lock:
+        for k in [k for k in _pack_cache if k[0] == wid]:
+            _pack_cache.pop(k, None)
+        _demand.pop(wid, None)
+
+
+def _cache_get(w, kind):
+    with _pack_lock:
+        hit = _pack_cache.get((id(w), kind))
+        if hit is not None and hit[0] == _tag(w):
+            return hit[1]
+    return None
+
+
+def _cache_put(w, kind, t):
+    with _pack_lock:
+        if id(w) not in _demand:
+            weakref.finalize(w, _forget, id(w))
+            _demand[id(w)] = set()
+        _demand[id(w)].add(kind)
+        _pack_cache[(id(w), kind)] = (_tag(w), t)
+
+
+def _kernel_packable(w, dtype):
+    return (w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() and w.dim() in (2, 4)
+            and dtype in (torch.float32, torch.bfloat16))
+
+
+def _pack_shape(w, kind):
+    o, i = w.shape[0], w.shape[1]
+    k = w.shape[2] * w.shape[3] if w.dim() == 4 else 1
+    if kind[0] == "wsq":
+        return (o, i), torch.float32
+    return ((i, k * o) if kind[1] else (o, k * i)), kind[2]
+
+
+def _launch_packs(entries):
+    """entries: [(w, kind, dst)] -> lcgan_pack_weights launches of up to MT_MAX tensors per compute dtype."""
+    by_dt = {}
+    for e in entries:
+        dt = e[1][2] if e[1][0] == "pack" else e[1][1]
+        by_dt.setdefault(dt, []).append(e)
+    for dt, lst in by_dt.items():
+        for i0 in range(0, len(lst), _lib.MT_MAX):
+            part = lst[i0:i0 + _lib.MT_MAX]
+            ch = _lib.PackChunk()
+            for j, (w, kind, dst) in enumerate(part):
+                ch.src[j], ch.dst[j] = w.data_ptr(), dst.data_ptr()
+                ch.O[j], ch.I[j] = w.shape[0], w.shape[1]
+                ch.K[j] = w.shape[2] * w.shape[3] if w.dim() == 4 else 1
+                if kind[0] == "wsq":
+                    ch.mode[j], ch.scale[j] = 2, kind[2]
+                else:
+                    ch.mode[j], ch.scale[j] = (1 if kind[1] else 0), 1.0
+            ch.count = len(part)
+            _lib.call("lcgan_pack_weights", C.byref(ch), BF16 if dt == torch.bfloat16 else F32, _stream(part[0][0]),
+                      tag="pack_weights", nbytes=sum(w.numel() * 6 for w, _, _ in part))
+
+
+def _derive(w, kind):
+    """One cached weight-derived tensor, computed by our pack kernel (torch fallback for odd inputs)."""
+    cacheable = isinstance(w, torch.nn.Parameter)
+    if cacheable:
+        hit = _cache_get(w, kind)
+        if hit is not None:
+            return hit
+    wd = w.detach()
+    dtype = kind[2] if kind[0] == "pack" else kind[1]
+    if _kernel_packable(wd, dtype):
+        shape, odt = _pack_shape(wd, kind)
+        dst = torch.empty(shape, dtype=odt, device=wd.device)
+        _launch_packs([(wd, kind, dst)])
+    elif kind[0] == "pack":
+        w4 = wd[:, :, None, None] if wd.dim() == 2 else wd
+        perm = (1, 2, 3, 0) if kind[1] else (0, 2, 3, 1)
+        dst = w4.permute(*perm).reshape(w4.shape[perm[0]], -1).to(dtype).contiguous()
+    else:
+        w4 = wd[:, :, None, None] if wd.dim() == 2 else wd
+        dst = (w4.to(dtype).float() * kind[2]).square().sum(dim=(2, 3))
+    if cacheable:
+        _cache_put(w, kind, dst)
+    return dst
+
+
 def pack_weight(w: torch.Tensor, transposed: bool, dtype: torch.dtype) -> torch.Tensor:
     """W2[o][tap*Cin + c] = w[o, c, kh, kw]  (transposed: rows = c, contraction over o), cast to the
     compute dtype.  The equalized-lr constant is NOT folded in: the parameter values themselves are
     rounded to bf16 and the constant is applied to the fp32 accumulator (lcgan_tapconv.acc_scale).
-    Packs of nn.Parameters are cached until the parameter's version counter moves (optimizer
-    step, load_state_dict); the cache entry dies with the parameter."""
-    cacheable = isinstance(w, torch.nn.Parameter)
-    if cacheable:
-        key = (id(w), transposed, dtype)
-        tag = (w._version, w.data_ptr(), _generation)
-        with _pack_lock:
-            hit = _pack_cache.get(key)
-            if hit is not None and hit[0] == tag:
-                return hit[1]
-    wd = w.detach()
-    if wd.dim() == 2:
-        wd = wd[:, :, None, None]
-    perm = (1, 2, 3, 0) if transposed else (0, 2, 3, 1)
-    p = wd.permute(*perm).reshape(wd.shape[perm[0]], -1).to(dtype).contiguous()
-    if cacheable:
-        with _pack_lock:
-            if key not in _pack_cache:
-                weakref.finalize(w, _pack_cache.pop, key, None)
-            _pack_cache[key] = (tag, p)
-    return p
+    Packs of nn.Parameters are cached until the parameter changes (version counter, or the generation
+    bumped by raw-pointer writers); the cache entry dies with the parameter."""
+    if w.dim() == 2 and not transposed and w.dtype == dtype and w.is_contiguous():
+        return w.detach()                        # a plain [O][I] matrix already is its forward pack
+    return _derive(w, ("pack", bool(transposed), dtype))
+
+
+def weight_sq(w: torch.Tensor, wscale: float, dtype: torch.dtype) -> torch.Tensor:
+    """Wsq[o,c] = sum_k (round_dtype(w[o,c,k]) * wscale)^2 (f32) - the demodulation table of
+    custom_layers.py:65-67, from the weights as the conv sees them."""
+    return _derive(w, ("wsq", dtype, float(wscale)))
+
+
+def prepack(*modules):
+    """Refresh, in a few multi-tensor launches, every cached pack / table of the modules' parameters that
+    is stale (optimizer step, EMA, load_state_dict).  Only kinds requested before are refreshed, so the
+    first iteration packs lazily and later ones in bulk."""
+    entries = []
+    for m in modules:
+        for w in m.parameters():
+            kinds = _demand.get(id(w))
+            if not kinds or not w.is_cuda:
+                continue
+            wd = w.detach()
+            for kind in kinds:
+                dtype = kind[2] if kind[0] == "pack" else kind[1]
+                if _cache_get(w, kind) is None and _kernel_packable(wd, dtype):
+                    shape, odt = _pack_shape(wd, kind)
+                    dst = torch.empty(shape, dtype=odt, device=wd.device)
+                    entries.append((wd, kind, dst))
+                    _cache_put(w, kind, dst)
+    if entries:
+        _launch_packs(entries)
 
 
 def clear_pack_cache():
     """Drop every cached weight pack (called around CUDA-graph capture so that each graph records
-    its own packing kernels and no eager path keeps a graph-pool tensor)."""
+    its own packing kernels and no eager path keeps a graph-pool tensor).  The demand sets survive."""
     with _pack_lock:
         _pack_cache.clear()
 
@@ -203,6 +306,12 @@ def _fill_desc(d: TapConvDesc, l: plans.Launch, x, y, cin, cout, w2, slope, gain
 
 
 _PROFILE_SHAPES = os.environ.get("LCGAN_PROFILE_SHAPES", "0") == "1"
+
+
+def set_profile_shapes(flag: bool):
+    """Tag tap-conv launches with their shape in the profiling pass (bench.py reports the dominant shape)."""
+    global _PROFILE_SHAPES
+    _PROFILE_SHAPES = bool(flag)
 
 
 def _shape_tag(fn, d):
@@ -397,22 +506,23 @@ class ConvFwd(torch.autograd.Function):
             dx = ConvFwd.apply(dy, w, ctx.wscale, plans.adjoint(ctx.plan), not ctx.transposed,
                                ctx.x_dtype, ctx.x_nchw)
         if ctx.needs_input_grad[1] and _wgrad_enabled():
-            dw = ConvWgrad.apply(x, dy, ctx.plan, ctx.transposed, tuple(w.shape)) * ctx.wscale
+            dw = ConvWgrad.apply(x, dy, ctx.plan, ctx.transposed, tuple(w.shape), ctx.wscale)
         return dx, dw, None, None, None, None, None
 
 
 class ConvWgrad(torch.autograd.Function):
-    """dw[o,c,t] = sum x[p+t, c] g[p, o]   (transposed: sum x[p+t, o] g[p, c])."""
+    """dw[o,c,t] = scale * sum x[p+t, c] g[p, o]   (transposed: sum x[p+t, o] g[p, c]); scale carries the
+    equalized-lr constant, applied by the kernel's epilogue."""
 
     @staticmethod
-    def forward(ctx, x, g, plan, transposed, wshape):
-        ctx.plan, ctx.transposed, ctx.wshape = plan, transposed, wshape
+    def forward(ctx, x, g, plan, transposed, wshape, scale=1.0):
+        ctx.plan, ctx.transposed, ctx.wshape, ctx.scale = plan, transposed, wshape, scale
         ctx.x_fmt = (x.dtype, x.is_contiguous() and not _is_cl(x))
         ctx.g_fmt = (g.dtype, g.is_contiguous() and not _is_cl(g))
         ctx.save_for_backward(x, g)
         o, i = wshape[0], wshape[1]
         cin, cout = (o, i) if transposed else (i, o)
-        dw2 = tapconv_wgrad(x, g, plan, cin, cout)
+        dw2 = tapconv_wgrad(x, g, plan, cin, cout, scale=scale)
         return unpack_wgrad(dw2, wshape, transposed).contiguous()
 
     @staticmethod
@@ -420,10 +530,10 @@ class ConvWgrad(torch.autograd.Function):
         x, g = ctx.saved_tensors
         dx = dg = None
         if ctx.needs_input_grad[0]:
-            dx = ConvFwd.apply(g, ggw, 1.0, plans.adjoint(ctx.plan), not ctx.transposed, *ctx.x_fmt)
+            dx = ConvFwd.apply(g, ggw, ctx.scale, plans.adjoint(ctx.plan), not ctx.transposed, *ctx.x_fmt)
         if ctx.needs_input_grad[1]:
-            dg = ConvFwd.apply(x, ggw, 1.0, ctx.plan, ctx.transposed, *ctx.g_fmt)
-        return dx, dg, None, None, None
+            dg = ConvFwd.apply(x, ggw, ctx.scale, ctx.plan, ctx.transposed, *ctx.g_fmt)
+        return dx, dg, None, None, None, None
 
 
 class ActBwd(torch.autograd.Function):
@@ -436,15 +546,10 @@ class ActBwd(torch.autograd.Function):
         n, c, h, w = y.shape
         dy = _cl(dy, y.dtype)
         assert _is_cl(y)
-        gout = torch.empty_like(y)
-        r0 = torch.zeros((n, c), dtype=torch.float32, device=y.device) if want_r0 else None
-        r1 = torch.zeros((n, c), dtype=torch.float32, device=y.device) if want_r1 else None
-        _lib.call("lcgan_act_bwd", _ptr(dy), _ptr(y), _ptr(gout), _ptr(d), _ptr(r0), _ptr(r1), _dt(y),
-                  n, h * w, c, C.c_float(slope), C.c_float(gain), _stream(y),
-                  nbytes=3 * y.numel() * y.element_size())
+        gout, r0, r1 = _act_bwd_raw(dy, y, d, slope, gain, want_r0, want_r1)
         ctx.save_for_backward(y, d)
         ctx.slope, ctx.gain = slope, gain
-        outs = (gout, r0 if want_r0 else gout.new_zeros(()), r1 if want_r1 else gout.new_zeros(()))
+        outs = (gout, r0 if want_r0 else _placeholder(y.device), r1 if want_r1 else _placeholder(y.device))
         ctx.mark_non_differentiable(outs[1], outs[2])
         return outs
 
@@ -499,13 +604,20 @@ class ConvAct(torch.autograd.Function):
         if need_x:
             dx = ConvFwd.apply(g, w, wscale, plans.adjoint(plan), True, *ctx.x_fmt)
         if need_w:
-            dw = ConvWgrad.apply(x, g, plan, False, tuple(w.shape)) * wscale
-        if need_b:
-            db = r0.sum(0) * bias_scale
-        if need_rs:
-            beff = (bias * bias_scale)[None] if bias is not None else 0.0
-            drs = (r1 - beff * r0) / rowscale
+            dw = ConvWgrad.apply(x, g, plan, False, tuple(w.shape), wscale)
+        if need_b or need_rs:
+            db, drs = _epilogue_grads(r0, r1, bias, rowscale, bias_scale, need_b, need_rs)
         return dx, dw, db, drs, dres, None, None, None, None, None, None, None
+
+
+def _epilogue_grads(r0, r1, bias, d, bias_scale, want_db, want_dd):
+    """db[o] = bias_scale sum_b r0;  dd[b,o] = (r1 - bias*bias_scale*r0) / d  - one launch."""
+    n, c = r0.shape
+    db = torch.empty((c,), dtype=torch.float32, device=r0.device) if want_db else None
+    dd = torch.empty((n, c), dtype=torch.float32, device=r0.device) if want_dd else None
+    _lib.call("lcgan_epilogue_grads", _ptr(r0), _ptr(r1 if want_dd else None), _ptr(bias), _ptr(d if want_dd else None),
+              C.c_float(bias_scale), _ptr(db), _ptr(dd), n, c, _stream(r0))
+    return db, dd
 
 
 def conv_act(x, w, bias=None, rowscale=None, residual=None, *, wscale=1.0, plan, slope=1.0, gain=1.0,
@@ -672,11 +784,24 @@ class Modulate(torch.autograd.Function):
         return dx, ds
 
 
+_placeholders = {}
+
+
+def _placeholder(device):
+    """A shared 0-dim zero standing in for an output that was not requested (no fill kernel per call)."""
+    t = _placeholders.get(device)
+    if t is None:
+        t = _placeholders[device] = torch.zeros((), device=device)
+    return t
+
+
 def _act_bwd_raw(dy, y, d, slope, gain, want_r0, want_r1):
     n, c, h, w = y.shape
     gout = torch.empty_like(y)
-    r0 = torch.zeros((n, c), dtype=torch.float32, device=y.device) if want_r0 else None
-    r1 = torch.zeros((n, c), dtype=torch.float32, device=y.device) if want_r1 else None
+    r0 = r1 = None
+    if want_r0 or want_r1:                      # one zero-fill for both reduction buffers
+        r = torch.zeros((2, n, c), dtype=torch.float32, device=y.device)
+        r0, r1 = (r[0] if want_r0 else None), (r[1] if want_r1 else None)
     _lib.call("lcgan_act_bwd", _ptr(dy), _ptr(y), _ptr(gout), _ptr(d), _ptr(r0), _ptr(r1), _dt(y),
               n, h * w, c, C.c_float(slope), C.c_float(gain), _stream(y), nbytes=3 * y.numel() * y.element_size())
     return gout, r0, r1
@@ -741,15 +866,48 @@ class ModConvAct(torch.autograd.Function):
             dw2 = tapconv_wgrad(xs, g, plan, x.shape[1], w.shape[0], scale=wscale)
             dw = unpack_wgrad(dw2, tuple(w.shape), False).contiguous()
             del xs
-        if need_b:
-            db = r0.sum(0) * bias_scale
-        if need_d:
+        if need_b or need_d:
             # r1 = sum_p dz * z with z = d*acc + bias (+ noise): remove the additive terms to get sum_p dz * acc
-            r1 = r1 - (bias * bias_scale)[None] * r0
-            if ctx.has_noise:
+            if need_d and ctx.has_noise:
                 r1 = r1 - (g.float() * ctx.noise[None, None]).sum(dim=(2, 3)) / d
-            dd = r1 / d
+            db, dd = _epilogue_grads(r0, r1, bias, d, bias_scale, need_b, need_d)
         return dx, ds, dw, db, dd, dnz, None, None, None, None, None, None, None
+
+
+class Demod(torch.autograd.Function):
+    """Demodulation coefficients d[b,o] = rsqrt(sum_c s[b,c]^2 Wsq[o,c] + eps), Wsq = sum_k (w c)^2
+    (custom_layers.py:65-67), from the weights as the conv sees them (rounded to the compute dtype, scaled
+    in fp32).  Forward and backward are one launch each (plus the cached Wsq table); first order only."""
+
+    @staticmethod
+    def forward(ctx, s, w, wscale, eps, dtype):
+        _need_cuda(s, w)
+        assert s.dtype == torch.float32 and s.is_contiguous() and w.dtype == torch.float32 and w.is_contiguous()
+        wsq = weight_sq(w, wscale, dtype)
+        b, i = s.shape
+        o = w.shape[0]
+        d = torch.empty((b, o), dtype=torch.float32, device=s.device)
+        _lib.call("lcgan_demod_fwd", _ptr(s), _ptr(wsq), _ptr(d), b, o, i, C.c_float(eps), _stream(s))
+        ctx.save_for_backward(s, w, d)
+        ctx.cfg = (wscale, dtype)
+        return d
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dd):
+        s, w, d = ctx.saved_tensors
+        wscale, dtype = ctx.cfg
+        b, i = s.shape
+        o = w.shape[0]
+        k = w.shape[2] * w.shape[3] if w.dim() == 4 else 1
+        dd = dd.contiguous().float()
+        ds = torch.empty_like(s) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w) if (ctx.needs_input_grad[1] and _wgrad_enabled()) else None
+        if ds is not None or dw is not None:
+            _lib.call("lcgan_demod_bwd", _ptr(dd), _ptr(d), _ptr(s), _ptr(weight_sq(w, wscale, dtype)), _ptr(w),
+                      _ptr(ds), _ptr(dw), b, o, i, k, C.c_float(wscale), BF16 if dtype == torch.bfloat16 else F32,
+                      _stream(s))
+        return ds, dw, None, None, None
 
 
 class Warp(torch.autograd.Function):

@@ -93,6 +93,7 @@ class Trainer:
 
     def g_step(self, it, z):
         requires_grad(self.G, True); requires_grad(self.D, False)
+        ops.prepack(self.G, self.D)                    # stale weight packs / demod tables, in bulk
         self.g_opt.zero_grad()
         loss = generator_loss(self.G, self.D, self.hp, it, z)
         loss.backward()
@@ -103,6 +104,7 @@ class Trainer:
         requires_grad(self.G, False); requires_grad(self.D, True)
         if it >= self.freeze_d_start:
             freeze_discriminator(self.D, self.freeze_d_layer)
+        ops.prepack(self.G, self.D)
         self.d_opt.zero_grad()
         loss = discriminator_loss(self.G, self.D, self.hp, it, z, data)
         loss.backward()
@@ -177,6 +179,7 @@ class GraphedTrainer(Trainer):
         if self.world == 1:
             return super().g_step(it, z)
         requires_grad(self.G, True); requires_grad(self.D, False)
+        ops.prepack(self.G, self.D)                    # stale weight packs / demod tables, in bulk
         self.g_opt.zero_grad()
         loss = generator_loss(self.G, self.D, self.hp, it, z)
         self.exchange.backward(loss, self.variant(it, "g"), "g")
@@ -189,6 +192,7 @@ class GraphedTrainer(Trainer):
         requires_grad(self.G, False); requires_grad(self.D, True)
         if it >= self.freeze_d_start:
             freeze_discriminator(self.D, self.freeze_d_layer)
+        ops.prepack(self.G, self.D)
         self.d_opt.zero_grad()
         loss = discriminator_loss(self.G, self.D, self.hp, it, z, data)
         frozen = "_frozen" if it >= self.freeze_d_start else ""      # a different set of gradients

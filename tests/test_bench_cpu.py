@@ -9,7 +9,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_one_json_line_with_the_contract_keys():
-    """`bench.py --impl reference` = the oracle port of the reference's CPU path, bounded sample."""
+    """`bench.py --impl reference` = the reference's own modules (baseline/_ref or /root/reference) on the host
+    cores, stepped by the restated worker.py schedule; K timed half-iterations after W warm-up ones."""
     env = dict(os.environ, LCGAN_BENCH_RES="32")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1",
                           "--steps", "2", "--warmup", "1"], capture_output=True, text=True, env=env, timeout=600,
@@ -21,7 +22,11 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["impl"] == "reference" and d["unit"] == "img/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["n_gpus"] == 1 and d["gpu_launches"] == 0
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "oracle" in cb["sample"]
+    from oracle import reference_arm as RA
+    want = "reference" if RA.find_checkout() else "port"
+    assert cb["kind"] == want and cb["cores"] >= 1 and cb["value"] == d["value"]
+    assert ("unmodified reference modules" if want == "reference" else "oracle port") in cb["sample"]
+    assert d["steps"] == 2 and d["warmup"] == 1 and d["ms_per_step"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
 
@@ -81,4 +86,15 @@ def test_roofline_summary_of_an_instrumented_cycle():
     roof, _ = bench.summarise_kernels(stats, pk, {})
     assert roof["kernel"] == "act_bwd" and roof["bound"] == "hbm" and roof["traffic"] is None
     assert bench.summarise_kernels({}, pk, {}) == (None, [])
+    json.dumps(roof)
+    # shape-tagged tap convs: the dominant SHAPE of the dominant kernel is reported, traffic looked up for that shape;
+    # a shape below the ridge (AI = 100 FLOP/B < 1400e12 / 6500e9 = 215) is held against the HBM peak
+    stats = {"tapconv_tc|A": {"n": 4, "ms": 30.0, "flops": 3.0e12, "bytes": 3.0e10},
+             "tapconv_tc|B": {"n": 6, "ms": 10.0, "flops": 1.0e13, "bytes": 1.0e10},
+             "box3": {"n": 2, "ms": 5.0, "flops": 0, "bytes": 2.0e10}}
+    roof, rows = bench.summarise_kernels(stats, pk, {"tapconv_tc|A": 7.7e9})
+    assert roof["kernel"] == "tapconv_tc" and roof["shape"] == "A" and roof["bound"] == "hbm" and roof["traffic"] == 7.7e9
+    assert abs(roof["achieved"] - 1000.0) < 1e-6 and abs(roof["bytes_per_launch"] - 7.5e9) < 1
+    assert abs(roof["all_shapes"]["tflops"] - 1.3e13 / 0.04 / 1e12) < 1e-6 and len(roof["shapes"]) == 2
+    assert rows[0]["kernel"] == "tapconv_tc" and rows[0]["launches"] == 10
     json.dumps(roof)

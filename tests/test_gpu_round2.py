@@ -1,0 +1,307 @@
+"""Host-visible behaviour added in round 2, on the B200: fused multi-tensor Adam, multi-tensor weight packs,
+the fused demodulation Function, stale-pack protection around EMA / raw-pointer writers, the R1
+first-order pass skipping weight gradients, deterministic (bit-reproducible) mode, fused noise injection."""
+import copy
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _setup():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from lcgan_b200 import ops
+    yield
+    ops.set_precision("bf16")
+    ops.set_deterministic(False)
+
+
+def _models(res, mode, seed=0):
+    from lcgan_b200 import cnn, ops
+    from lcgan_b200.config import Config
+    from oracle import lcgan_oracle as O
+    ops.set_precision(mode)
+    cfg = Config(img_resolution=res)
+    gsd, dsd = O.make_generator_state(cfg, seed), O.make_discriminator_state(cfg, seed + 1)
+    G, D = cnn.Generator(cfg.namespace()), cnn.Discriminator(cfg.namespace())
+    G.load_state_dict(gsd); D.load_state_dict(dsd)
+    return O, cfg, gsd, dsd, G.cuda(), D.cuda()
+
+
+@pytest.mark.parametrize("beta1", [0.0, 0.5])
+def test_fused_adam_matches_torch_adam(beta1):
+    """worker.py:98-110: torch.optim.Adam(betas=(0,.99), eps=1e-8).  Same trajectories over 20 steps, including
+    parameters whose gradient is None in some steps (they keep their own step count, like torch's)."""
+    from lcgan_b200.optim import FusedAdam
+    torch.manual_seed(0)
+    shapes = [(512, 512, 3, 3), (64,), (7, 5), (1,), (2048, 130), ()]
+    pa = [torch.randn(s, device="cuda").requires_grad_() for s in shapes]
+    pb = [p.detach().clone().requires_grad_() for p in pa]
+    oa = torch.optim.Adam(pa, lr=2e-3, betas=(beta1, 0.99), eps=1e-8)
+    ob = FusedAdam(pb, lr=2e-3, betas=(beta1, 0.99), eps=1e-8)
+    for step in range(20):
+        for i, (a, b) in enumerate(zip(pa, pb)):
+            if (step + i) % 3 == 2:
+                a.grad = b.grad = None
+                continue
+            g = torch.randn_like(a) * (10.0 ** ((i % 4) - 2))
+            a.grad, b.grad = g.clone(), g.clone()
+        oa.step(); ob.step()
+    for a, b in zip(pa, pb):
+        assert rel_l2(b.detach(), a.detach()) < 2e-6
+    assert float(ob.state[pb[0]]["step"]) == float(oa.state[pa[0]]["step"])
+
+
+def test_fused_adam_is_graph_capturable():
+    from lcgan_b200.optim import FusedAdam
+    torch.manual_seed(1)
+    p = [torch.randn(300, 40, device="cuda").requires_grad_(), torch.randn(17, device="cuda").requires_grad_()]
+    q = [t.detach().clone().requires_grad_() for t in p]
+    grads = [torch.randn_like(t) for t in p]
+    for t, g in zip(p, grads):
+        t.grad = g
+    for t, g in zip(q, grads):
+        t.grad = g.clone()
+    opt, ref = FusedAdam(p, lr=1e-2, betas=(0.0, 0.99)), torch.optim.Adam(q, lr=1e-2, betas=(0.0, 0.99))
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        opt.step(); ref.step()
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        opt.step()
+    for _ in range(4):                      # capture does not execute: 4 replays = steps 2..5
+        g.replay(); ref.step()
+    torch.cuda.synchronize()
+    for a, b in zip(p, q):
+        assert rel_l2(a.detach(), b.detach()) < 2e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_pack_kernels_match_torch(dtype):
+    """ops.pack_weight / weight_sq / prepack (lcgan_pack_weights) vs the permute/cast/square/sum they replace."""
+    from lcgan_b200 import ops
+    torch.manual_seed(2)
+    ws = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in [(96, 64, 3, 3), (32, 128, 1, 1), (48, 80)]]
+    def ref_pack(w, tr):
+        w4 = w.detach()[:, :, None, None] if w.dim() == 2 else w.detach()
+        perm = (1, 2, 3, 0) if tr else (0, 2, 3, 1)
+        return w4.permute(*perm).reshape(w4.shape[perm[0]], -1).to(dtype)
+    for w in ws:
+        for tr in (False, True):
+            assert torch.equal(ops.pack_weight(w, tr, dtype), ref_pack(w, tr))
+    c = 0.37
+    for w in ws[:2]:
+        ref = (w.detach().to(dtype).float() * c).square().sum(dim=(2, 3))
+        assert rel_l2(ops.weight_sq(w, c, dtype), ref) < 1e-6
+    # raw-pointer style update (no version bump) + generation bump -> prepack refreshes everything in bulk
+    mod = torch.nn.ParameterList(ws)
+    for w in ws:
+        w.detach().mul_(1.5)
+    ops.bump_generation()
+    from lcgan_b200 import _lib
+    n0 = _lib.counts.get("lcgan_pack_weights", 0)
+    ops.prepack(mod)
+    assert _lib.counts["lcgan_pack_weights"] - n0 <= 2
+    n1 = _lib.counts["lcgan_pack_weights"]
+    for w in ws:
+        for tr in (False, True):
+            assert torch.equal(ops.pack_weight(w, tr, dtype), ref_pack(w, tr))
+    assert _lib.counts["lcgan_pack_weights"] == n1, "packs after prepack must be cache hits"
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_demod_function_matches_autograd(mode):
+    """ops.Demod (custom_layers.py:65-67 in shared-weight form) forward and gradients vs plain torch autograd."""
+    from lcgan_b200 import ops
+    ops.set_precision(mode)
+    dt = ops.act_dtype()
+    torch.manual_seed(3)
+    b, o, i = 5, 96, 64
+    w = torch.nn.Parameter(torch.randn(o, i, 3, 3, device="cuda"))
+    s = (torch.randn(b, i, device="cuda") + 1).requires_grad_()
+    c, eps = 1 / (i * 9) ** 0.5, 1e-8
+    d = ops.Demod.apply(s, w, c, eps, dt)
+    gd = torch.randn_like(d)
+    d.backward(gd)
+    w2 = w.detach().clone().requires_grad_(); s2 = s.detach().clone().requires_grad_()
+    wq = w2.to(dt).float() if dt != torch.float32 else w2
+    d2 = torch.rsqrt((s2 * s2) @ (wq * c).square().sum(dim=(2, 3)).t() + eps)
+    d2.backward(gd)
+    assert rel_l2(d, d2) < 1e-5
+    assert rel_l2(s.grad, s2.grad) < 1e-5
+    assert rel_l2(w.grad, w2.grad) < 1e-5
+
+
+def test_ema_forward_is_not_stale_after_update():
+    """G_ema forward -> Ema.update (raw-pointer kernel, no version bump) -> forward must see the
+    new weights.  Also after a graph-style raw update of the source generator."""
+    from lcgan_b200.ema import Ema
+    O, cfg, gsd, dsd, G, D = _models(16, "bf16")
+    G_ema = copy.deepcopy(G)
+    ema = Ema(G, G_ema, decay=0.5, start_iter=0)
+    z1, z2 = torch.randn(2, 64, device="cuda"), torch.randn(2, 64, device="cuda")
+    with torch.no_grad():
+        a = G_ema(z1, z2, 1.0).clone()
+        for p in G.parameters():                     # move the source far enough to matter in bf16
+            p.mul_(1.25)
+        ema.update(0)
+        b = G_ema(z1, z2, 1.0).clone()
+        fresh = copy.deepcopy(G_ema)                 # new Parameters: nothing cached for them
+        c = fresh(z1, z2, 1.0)
+    assert rel_l2(b, a) > 1e-2, "G_ema output did not change after Ema.update: stale weight packs"
+    assert rel_l2(b, c) < 1e-6
+
+
+def test_r1_first_order_pass_launches_no_weight_gradient_kernels():
+    """loss.cal_derivative wraps autograd.grad in ops.no_weight_gradients(); backward nodes run
+    on the autograd thread, so the flag must not be thread-local."""
+    from lcgan_b200 import _lib, loss
+    O, cfg, gsd, dsd, G, D = _models(32, "bf16")
+    img = (torch.rand(4, 3, 32, 32, device="cuda") * 2 - 1).requires_grad_()
+    for p in D.parameters():
+        p.requires_grad = True
+    logit, _, _ = D(img, False)
+    wg = [k for k in ("lcgan_tapconv_wgrad_tc", "lcgan_tapconv_wgrad_simt", "lcgan_tapconv_up2_thin_wgrad")]
+    before = {k: _lib.counts.get(k, 0) for k in wg}
+    fwd_before = _lib.counts.get("lcgan_tapconv_tc", 0)
+    g = loss.cal_derivative(inputs=img, outputs=logit.sum(), device="cuda")
+    torch.cuda.synchronize()
+    assert _lib.counts.get("lcgan_tapconv_tc", 0) > fwd_before, "the data-gradient pass must run our kernels"
+    assert {k: _lib.counts.get(k, 0) for k in wg} == before, "weight-gradient kernels ran inside cal_derivative"
+    assert g.shape == img.shape and bool(torch.isfinite(g).all())
+    # and the penalty's own backward does produce weight gradients
+    (0.5 * g.square().sum()).backward()
+    assert sum(_lib.counts.get(k, 0) for k in wg) > sum(before.values())
+    # (biases only enter through the leaky-relu masks, so the penalty gives them no gradient)
+    assert all(p.grad is not None for n, p in D.named_parameters()
+               if n.endswith("weight.weight") and "projection_header" not in n)
+
+
+def _all_grads(mode, res=32, b=4):
+    """Gradients of every step variant that exists (G even, D even, D odd + R1) from fixed weights and inputs."""
+    from lcgan_b200 import train_step as T
+    from lcgan_b200.config import Hyper
+    O, cfg, gsd, dsd, G, D = _models(res, mode)
+    gen = torch.Generator().manual_seed(21)
+    z = O.synthetic_latents(b, cfg, gen, "cuda")
+    data = O.synthetic_data(b, cfg, gen, "cuda")
+    hp = Hyper()
+    out = {}
+    for which, it in (("g", 0), ("d", 0), ("d", 1)):
+        G.load_state_dict(gsd); G.zero_grad(); D.zero_grad()
+        T.requires_grad(G, which == "g"); T.requires_grad(D, which == "d")
+        loss = T.generator_loss(G, D, hp, it, z) if which == "g" else T.discriminator_loss(G, D, hp, it, z, data)
+        loss.backward()
+        net = G if which == "g" else D
+        out[(which, it)] = (loss.detach().clone(), {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None})
+    return out
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_deterministic_mode_is_bit_reproducible(mode):
+    """the accurate mode must be run-to-run reproducible.  With ops.set_deterministic(True) every
+    reduction that used fp32 atomics takes ordered turns: two runs give bit-identical losses and gradients."""
+    from lcgan_b200 import ops
+    ops.set_deterministic(True)
+    a = _all_grads(mode)
+    b = _all_grads(mode)
+    for key in a:
+        assert torch.equal(a[key][0], b[key][0]), key
+        assert a[key][1].keys() == b[key][1].keys()
+        for k in a[key][1]:
+            assert torch.equal(a[key][1][k], b[key][1][k]), (key, k)
+    # and it computes the same thing as the default (atomic) mode, up to summation order
+    ops.set_deterministic(False)
+    c = _all_grads(mode)
+    for key in a:
+        for k in a[key][1]:
+            assert rel_l2(c[key][1][k], a[key][1][k]) < (1e-4 if mode == "fp32" else 2e-2), (key, k)
+
+
+@pytest.mark.parametrize("mode,up", [("fp32", 1), ("fp32", 2), ("bf16", 1), ("bf16", 2)])
+def test_noise_injection_fused_in_epilogue(mode, up):
+    """SynthesisLayer(use_noise=True) (custom_layers.py:98-101,108-110): conv -> + noise_const*strength*0.01 -> the
+    activation the caller fuses.  Forward and every gradient vs the oracle's modulated conv + plain torch ops."""
+    from lcgan_b200 import custom_layers as CL, ops
+    from oracle import lcgan_oracle as O
+    ops.set_precision(mode)
+    dt = ops.act_dtype()
+    tol = 1e-4 if mode == "fp32" else 1e-2
+    torch.manual_seed(5)
+    cin, cout, res, b, lat = 64, 64, 32, 3, 512
+    layer = CL.SynthesisLayer(cin, cout, lat, res, up=up, use_noise=True).cuda()
+    with torch.no_grad():
+        layer.noise_strength.fill_(7.0)            # init is 0: give the term weight
+        layer.modulated_conv.bias.normal_()
+    rin = res // up
+    x = torch.randn(b, cin, rin, rin, device="cuda").to(dt).float()
+    latent = torch.randn(b, lat, device="cuda")
+    gy = torch.randn(b, cout, res, res, device="cuda").to(dt).float()
+    xm = x.to(dt).contiguous(memory_format=torch.channels_last).requires_grad_()
+    y = layer(xm, latent, slope=0.2, gain=1.4)
+    y.backward(gy.to(dt).contiguous(memory_format=torch.channels_last))
+    # reference: oracle layer on the same parameters (conv weight rounded like the kernel sees it)
+    sd = {"l." + k: v.detach().clone() for k, v in layer.state_dict().items()}
+    kw = "l.modulated_conv.weight.weight"
+    sd[kw] = sd[kw].to(dt).float()
+    for v in sd.values():
+        if v.is_floating_point():
+            v.requires_grad_(True)
+    xo = x.clone().requires_grad_()
+    yo = O.synth_layer(sd, "l", xo, latent, up=up) + sd["l.noise_const"] * sd["l.noise_strength"] * 0.01
+    yo = F.leaky_relu(yo, 0.2) * 1.4
+    yo.backward(gy)
+    assert rel_l2(y.float(), yo.detach()) < tol
+    gt = 10 * tol                                    # lrelu mask flips on the rounded pre-activation (bf16)
+    assert rel_l2(xm.grad.float(), xo.grad) < gt
+    assert rel_l2(layer.noise_strength.grad, sd["l.noise_strength"].grad) < gt
+    for k, p in layer.named_parameters():
+        assert rel_l2(p.grad, sd["l." + k].grad) < gt, k
+
+
+@pytest.mark.parametrize("name,mode", [("model_r16_b4.pt", "fp32"), ("model_r32_b2.pt", "bf16")])
+def test_inference_runner_matches_reference_golden(golden_dir, name, mode):
+    """BASELINE config 5 (worker.py:427-441, cnn.py:99-101): generator_ema(geo, app, w_psi=0.7) through the captured
+    GeneratorRunner == the unmodified reference's output (golden g_image_psi07), for a captured batch size, for a
+    padded one, and again after the weights changed (refresh)."""
+    import os
+    from lcgan_b200.inference import GeneratorRunner
+    g = torch.load(os.path.join(golden_dir, name), weights_only=False)
+    O, cfg, gsd, dsd, G, D = _models(g["res"], mode, g["seed"])
+    tol = 1e-4 if mode == "fp32" else 1e-2
+    gen = torch.Generator().manual_seed(1000 + g["seed"])
+    z = O.synthetic_latents(g["b"], cfg, gen, "cuda")
+    with torch.no_grad():
+        G(z["rand1"], z["rand2"])                         # the golden run's training-mode forward set avg_latent
+    runner = GeneratorRunner(G, w_psi=0.7, batch_sizes=(g["b"], 8))
+    img = runner(z["rand1"], z["rand2"])
+    assert img.shape == g["g_image_psi07"].shape and img.dtype == torch.float32
+    assert rel_l2(img.cpu(), g["g_image_psi07"]) < tol
+    # a batch size that is not captured is padded up to the next one; per-sample results do not change
+    part = runner(z["rand1"][:1], z["rand2"][:1]) if g["b"] > 1 else img[:1]
+    assert rel_l2(part, img[:1]) < 1e-6
+    big = runner(z["rand1"].repeat(3, 1)[:5], z["rand2"].repeat(3, 1)[:5])
+    assert rel_l2(big[:g["b"]], img) < 1e-6
+    _, img01, u8 = runner.replay(g["b"])
+    assert float(img01.min()) >= 0.0 and float(img01.max()) <= 1.0 and u8.dtype == torch.uint8
+    assert torch.equal(u8, ((img.clamp(-1, 1) + 1) / 2 * 255 + 0.5).clamp(0, 255).to(torch.uint8))
+    # no autograd state is kept by the captured forward
+    assert not img.requires_grad
+    # weights change -> refresh() -> new output; without refresh the graph would keep the old packs
+    with torch.no_grad():
+        for p in G.parameters():
+            p.mul_(1.1)
+    runner.refresh()
+    img2 = runner(z["rand1"], z["rand2"])
+    with torch.no_grad():
+        ref2 = G(z["rand1"], z["rand2"], 0.7)
+    assert rel_l2(img2, ref2) < 1e-6 and rel_l2(img2, img) > 1e-3

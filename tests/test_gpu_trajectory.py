@@ -1,15 +1,26 @@
-"""100-step loss trajectories: lcgan_b200 (fp32 and bf16 modes) vs the oracle trained from the
-same weights on the same latents and images (res 32, batch 8, reference hyper-parameters).
+"""100-step loss trajectories against a MEASURED noise floor (north_star: "loss trajectories over 100 steps within 1%").
 
-north_star asks for "within 1%".  Measured on the B200 (numerics): this GAN with Adam
-(beta1 = 0, lr 2e-3) is a chaotic map - the oracle and our fp32 path, which agree to 1e-7 on
-iteration 0, are 1e-4 apart at iteration 2, 1e-2 at iteration 8 and O(0.2) at iteration 11, i.e.
-fp32 rounding noise alone exceeds 1% after ~8 iterations.  What can be checked, and is:
-  * the first iterations, before amplification: fp32 <= 1e-3, bf16 <= 1e-2;
-  * the 100-step mean of each loss: within a factor of 3 of the oracle's (a sanity bound - training
-    neither diverges nor collapses; run-to-run, atomics ordering alone moves this mean by 5-50%);
-  * bf16 diverges no faster than the fp32 noise floor allows (same order of magnitude at step 8).
+The LC-GAN iteration with Adam(beta1 = 0) is a chaotic map: rounding differences between two correct evaluations
+grow exponentially until the trajectories decorrelate.  So the floor is measured, not assumed:
+  * tests/golden/trajectory_noise_floor.json (oracle/make_noise_floor.py) holds the oracle's own CPU runs of these
+    100 iterations: fp32 with 8 threads, fp32 with 1 thread (summation order only), and fp64 for the first 12;
+  * here the oracle runs on the B200 in fp64 (the truth; pinned to the committed CPU fp64 steps) and in fp32 (cuDNN,
+    TF32 off);
+  * divergence(t) of a run = max over {g_loss, d_loss} of |run - fp64| / max(|fp64|, 1e-6); the noise floor F(t) is
+    the largest divergence among the three oracle fp32 runs, and its running maximum defines the window in which
+    the oracle agrees with itself to 1%.
+What is asserted for our CUDA path (fp32 mode run deterministically, and bf16 mode):
+  1. inside that window our fp32 trajectory is within 1% of the truth - north_star's criterion, where any
+     implementation can meet it;
+  2. over all 100 steps our fp32 divergence never runs ahead of the floor by more than a fixed factor
+     (running maxima: ours <= K * floor + 1e-6) - i.e. we diverge like the oracle diverges from itself;
+  3. bf16 starts 3-4 orders of magnitude above the fp32 floor (operand rounding) and is amplified at the same
+     rate: within 1% while amplification * initial error allows, and its 100-step mean losses stay within the
+     spread of the oracle's own decorrelated runs.
+The curves are written to gpurun_out/trajectory_curves.json (profiles/ keeps a B200 copy).
 """
+import json
+import os
 import statistics
 
 import pytest
@@ -17,18 +28,24 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+K_FLOOR = 20.0          # criterion 2: allowed lead over the oracle's self-divergence (running maxima)
 
-def _run(mode, steps, res=32, b=8):
+
+def _run(mode, steps, res, b, data_seed):
     from lcgan_b200 import cnn, ops, train_step as T
     from oracle import lcgan_oracle as O
     dev = "cuda"
     cfg, hp = O.Config(img_resolution=res), O.Hyper()
-    gen = torch.Generator().manual_seed(5)
+    gen = torch.Generator().manual_seed(data_seed)
     gsd, dsd = O.make_generator_state(cfg, 0), O.make_discriminator_state(cfg, 1)
-    if mode == "oracle":
-        tr = O.OracleTrainer(cfg, hp, {k: v.to(dev) for k, v in gsd.items()}, {k: v.to(dev) for k, v in dsd.items()})
+    if mode.startswith("oracle"):
+        dt = torch.float64 if mode == "oracle_fp64" else torch.float32
+        tr = O.OracleTrainer(cfg, hp, {k: v.to(dev, dt) for k, v in gsd.items()}, {k: v.to(dev, dt) for k, v in dsd.items()})
     else:
+        dt = torch.float32
         ops.set_precision(mode)
+        ops.set_deterministic(True)
         G, D = cnn.Generator(cfg.namespace()), cnn.Discriminator(cfg.namespace())
         G.load_state_dict(gsd); D.load_state_dict(dsd)
         tr = T.Trainer(G.to(dev), D.to(dev), hp)
@@ -36,7 +53,21 @@ def _run(mode, steps, res=32, b=8):
     for it in range(steps):
         zg, zd = O.synthetic_latents(b, cfg, gen, dev), O.synthetic_latents(b, cfg, gen, dev)
         data = O.synthetic_data(b, cfg, gen, dev)
-        out.append(tr.iteration(it, zg, zd, data))
+        cast = lambda d: {k: v.to(dt) for k, v in d.items()}
+        g, d = tr.iteration(it, cast(zg), cast(zd), cast(data))
+        out.append((float(g), float(d)))
+    return out
+
+
+def _div(run, truth):
+    return [max(abs(a - t) / max(abs(t), 1e-6) for a, t in zip(r, tr)) for r, tr in zip(run, truth)]
+
+
+def _cummax(xs):
+    out, m = [], 0.0
+    for x in xs:
+        m = max(m, x)
+        out.append(m)
     return out
 
 
@@ -46,28 +77,52 @@ def test_loss_trajectories_100_steps():
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     from lcgan_b200 import ops
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "trajectory_noise_floor.json")))
+    steps, res, b, seed = gold["steps"], gold["res"], gold["batch"], gold["data_seed"]
     try:
-        steps = 100
-        ref = _run("oracle", steps)
-        runs = {m: _run(m, steps) for m in ("fp32", "bf16")}
+        truth = _run("oracle_fp64", steps, res, b, seed)
+        runs = {m: _run(m, steps, res, b, seed) for m in ("oracle_fp32", "fp32", "bf16")}
+        rerun = _run("fp32", 12, res, b, seed)
     finally:
         ops.set_precision("bf16")
+        ops.set_deterministic(False)
+    runs["oracle_cpu_fp32_t8"], runs["oracle_cpu_fp32_t1"] = gold["fp32_t8"], gold["fp32_t1"]
 
-    def rel(a, o):
-        return abs(a - o) / max(abs(o), 1e-6)
+    # the truth is pinned: the B200 fp64 oracle reproduces the committed CPU fp64 iterations
+    n64 = len(gold["fp64"])
+    d64 = _div(truth[:n64], gold["fp64"])
+    assert max(d64) < 1e-6, d64
+    # deterministic mode: the fp32 run repeats bit for bit
+    assert rerun == runs["fp32"][:12], "fp32 deterministic mode is not run-to-run reproducible"
 
-    for mode, early_tol in (("fp32", 1e-3), ("bf16", 1e-2)):
-        r = runs[mode]
-        assert all(torch.isfinite(torch.tensor(x)).all() for x in r)
-        for it in range(3):
-            for j in range(2):
-                assert rel(r[it][j], ref[it][j]) < early_tol, (mode, it, j, r[it], ref[it])
-        for j in range(2):
-            m_ref = statistics.mean(x[j] for x in ref)
-            m_run = statistics.mean(x[j] for x in r)
-            assert m_ref / 3 < m_run < m_ref * 3, (mode, j, m_run, m_ref)
-    # bf16 error at the edge of the predictable window is the same order as the fp32 noise floor
+    div = {k: _div(v, truth) for k, v in runs.items()}
+    floor = [max(div[k][t] for k in ("oracle_fp32", "oracle_cpu_fp32_t8", "oracle_cpu_fp32_t1")) for t in range(steps)]
+    cfloor, cours, cbf = _cummax(floor), _cummax(div["fp32"]), _cummax(div["bf16"])
+    window = next((t for t, v in enumerate(cfloor) if v > 1e-2), steps)      # oracle agrees with itself to 1% before this
+    curves = {"steps": steps, "window_1pct": window, "divergence": div, "floor": floor, "truth": truth,
+              "ours_fp32": runs["fp32"], "ours_bf16": runs["bf16"], "K": K_FLOOR}
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):
+        json.dump(curves, open(os.path.join(out_dir, "trajectory_curves.json"), "w"))
+
+    assert all(all(x == x and abs(x) < 1e4 for x in r) for m in ("fp32", "bf16") for r in runs[m])
+    # 1. within 1% wherever the oracle is within 1% of itself
+    assert window >= 3, ("noise floor exceeds 1% almost immediately", cfloor[:6])
+    assert all(div["fp32"][t] < 1e-2 for t in range(window)), ("fp32", window, div["fp32"][:window])
+    # 2. never ahead of the floor by more than K (running maxima), over all 100 steps
+    lead = max(cours[t] / (K_FLOOR * cfloor[t] + 1e-6) for t in range(steps))
+    assert lead <= 1.0, ("fp32 diverges faster than the oracle from itself", lead, cours[:12], cfloor[:12])
+    # 3. bf16: same amplification from a larger start.  A(t) = floor amplification relative to iteration 0.
+    amp = [cfloor[t] / max(cfloor[0], 1e-9) for t in range(steps)]
+    e0 = max(div["bf16"][0], 1e-4)
+    assert e0 < 1e-2, ("bf16 first iteration", div["bf16"][0])
+    bf_window = next((t for t in range(steps) if K_FLOOR * e0 * amp[t] > 1e-2), steps)
+    assert all(div["bf16"][t] < 1e-2 for t in range(min(bf_window, window))), ("bf16", bf_window, div["bf16"][:bf_window])
     for j in range(2):
-        f8 = max(rel(runs["fp32"][it][j], ref[it][j]) for it in range(6, 10))
-        b8 = max(rel(runs["bf16"][it][j], ref[it][j]) for it in range(6, 10))
-        assert b8 < max(10 * f8, 0.3), (j, f8, b8)
+        means = [statistics.mean(x[j] for x in runs[k]) for k in ("oracle_fp32", "oracle_cpu_fp32_t8", "oracle_cpu_fp32_t1")]
+        means.append(statistics.mean(x[j] for x in truth))
+        lo, hi = min(means), max(means)
+        slack = 0.5 * (hi - lo) + 0.25 * abs(statistics.mean(means))
+        for m in ("fp32", "bf16"):
+            mine = statistics.mean(x[j] for x in runs[m])
+            assert lo - slack <= mine <= hi + slack, (m, j, mine, means)
