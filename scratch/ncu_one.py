@@ -15,6 +15,24 @@ for w in which:
             w2 = torch.randn(C, 9 * C, device=dev).bfloat16(); plan = plans.conv(3, 1, R, R)
             y = ops.empty_cl(N, C, R, R, torch.bfloat16, dev); bias = torch.randn(C, device=dev)
             ops.tapconv(x, w2, y, plan, None, bias, None, slope=0.2, gain=1.4)
+        elif w == "fwd64":
+            x64 = cl(torch.randn(N, 64, 512, 512, device=dev).bfloat16())
+            w2 = torch.randn(64, 9 * 64, device=dev).bfloat16(); plan = plans.conv(3, 1, 512, 512)
+            y = ops.empty_cl(N, 64, 512, 512, torch.bfloat16, dev); bias = torch.randn(64, device=dev)
+            ops.tapconv(x64, w2, y, plan, None, bias, None, slope=0.2, gain=1.4)
+            del x64, y
+        elif w == "fwd128":
+            x128 = cl(torch.randn(N, 128, 256, 256, device=dev).bfloat16())
+            w2 = torch.randn(128, 9 * 128, device=dev).bfloat16(); plan = plans.conv(3, 1, 256, 256)
+            y = ops.empty_cl(N, 128, 256, 256, torch.bfloat16, dev); bias = torch.randn(128, device=dev)
+            ops.tapconv(x128, w2, y, plan, None, bias, None, slope=0.2, gain=1.4)
+            del x128, y
+        elif w == "up64":
+            x64 = cl(torch.randn(N, 64, 512, 512, device=dev).bfloat16())
+            w2 = torch.randn(32, 9 * 64, device=dev).bfloat16(); plan = plans.conv_transpose_up2(3, 512, 512)
+            y = ops.empty_cl(N, 32, 1024, 1024, torch.bfloat16, dev); bias = torch.randn(32, device=dev)
+            ops.tapconv(x64, w2, y, plan, None, bias, None)
+            del x64, y
         elif w in ("wg32", "wg64"):
             Cw = int(w[2:]); Rw = {32: 1024, 64: 512}[Cw]
             xw = cl(torch.randn(N, Cw, Rw, Rw, device=dev).bfloat16()); gw = cl(torch.randn(N, Cw, Rw, Rw, device=dev).bfloat16())

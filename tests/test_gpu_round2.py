@@ -133,7 +133,9 @@ def test_demod_function_matches_autograd(mode):
     gd = torch.randn_like(d)
     d.backward(gd)
     w2 = w.detach().clone().requires_grad_(); s2 = s.detach().clone().requires_grad_()
-    wq = w2.to(dt).float() if dt != torch.float32 else w2
+    # rounding to the compute dtype with a straight-through gradient kept in fp32 (autograd's own backward of
+    # .to(bf16).float() would round the GRADIENT to bf16 as well)
+    wq = w2 + (w2.to(dt).float() - w2).detach()
     d2 = torch.rsqrt((s2 * s2) @ (wq * c).square().sum(dim=(2, 3)).t() + eps)
     d2.backward(gd)
     assert rel_l2(d, d2) < 1e-5
