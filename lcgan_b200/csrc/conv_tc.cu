@@ -30,6 +30,7 @@ constexpr int kMaxBN = 128;
 constexpr int kABytes = kTileM * kBlockK * 2;  // 16 KiB
 constexpr int kBBytes = kMaxBN * kBlockK * 2;  // 16 KiB
 constexpr int kThreads = 192;                  // warp0: TMA, warp1: MMA, warps 2-5: epilogue
+constexpr int kMaxSmem = 232448;                // opt-in dynamic shared memory per block on sm_100 (227 KiB)
 constexpr int kFwdThreads = 608;               // warps: 0 TMA, 1+6 MMA issuers, 2-5 / 7-10 / 11-14 / 15-18 epilogue groups
 
 struct TcParams {
@@ -39,7 +40,9 @@ struct TcParams {
   int ntaps, kpt, kc;                           // kc = channels per k-block (64 or 32), kpt = Cin / kc
   int dy[LCGAN_MAX_TAPS], dx[LCGAN_MAX_TAPS], wtap[LCGAN_MAX_TAPS];
   int BN, n_tiles, total_tiles;
-  int rowshare;                                 // 3x3 stride-1: one tall A tile per dx serves the 3 dy taps
+  int lw, lh;                                   // log2(tiles_w), log2(tiles_h): tile decode by shifts
+  int rowshare;                                 // 3x3 stride-1: 1/2 = one tall A tile per dx serves the 3 dy taps;
+                                                // 3 = ONE haloed (wt+2) x (ht+2) tile serves all nine taps
   int grp_wtap[3][3];                           // [dx+1][dy+1] -> weight tap index
   int stages, a_bytes, b_bytes, wres_bytes;     // rowshare == 2: all 9 taps' weights stay resident in smem
   long long ys_n, ys_h, ys_w;
@@ -236,7 +239,7 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
     tma_prefetch_desc(&tmw);
     for (int i = 0; i < p.stages; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
     mbar_init(s.wfull, 1);
-    for (int i = 0; i < kAccStages; ++i) { mbar_init(&s.done[i], p.rowshare == 2 ? 1 : 2); mbar_init(&s.acc_empty[i], 8); }
+    for (int i = 0; i < kAccStages; ++i) { mbar_init(&s.done[i], p.rowshare >= 2 ? 1 : 2); mbar_init(&s.acc_empty[i], 8); }
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<kAccStages * kMaxBN>(s.tmem_slot);
@@ -252,7 +255,27 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
       const uint32_t leader = elect_one();
       const uint32_t tx_bytes = p.rowshare ? (uint32_t)p.a_bytes + 3 * wtile : (kTileM + p.BN) * p.kc * 2;
       int g = 0;                                            // k-block counter across tiles
-      if (p.rowshare == 2) {
+      if (p.rowshare == 3) {
+        // haloed small-channel mode: resident weights, and ONE TMA box per tile - the (wt+2) x (ht+2) pixel
+        // neighbourhood of the 8 x 16 lattice tile.  Tap (dy, dx) is read by the MMA straight out of that
+        // box through its descriptor start offset (rows (dy*(wt+2) + dx) further on, SBO = one stored row of
+        // wt+2 pixels): the swizzle XOR is a function of the absolute shared-memory address for both the
+        // TMA write and the MMA read (probed on the B200: profiles/r02_probe_halo_single_copy_tile.txt).
+        mbar_expect_tx(s.wfull, 9 * p.kpt * wtile, leader);
+        for (int j = 0; j < 3; ++j)
+          for (int dyi = 0; dyi < 3; ++dyi)
+            for (int cb = 0; cb < p.kpt; ++cb)
+              tma_load_2d(s.wres + ((j * 3 + dyi) * p.kpt + cb) * wtile, &tmw, s.wfull,
+                          p.grp_wtap[j][dyi] * p.Cin + cb * p.kc, 0, leader);
+        const uint32_t box_bytes = (uint32_t)(p.wt + 2) * (p.ht + 2) * p.kc * 2;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++g) {
+          const int tw = tile & (p.tiles_w - 1), th = (tile >> p.lw) & (p.tiles_h - 1), tb = tile >> (p.lw + p.lh);
+          const int st = g % p.stages, ph = (g / p.stages) & 1;
+          mbar_wait(&s.empty[st], ph ^ 1);
+          mbar_expect_tx(&s.full[st], box_bytes, leader);
+          tma_load_4d(s.a(st), &tmx, &s.full[st], 0, tw * p.wt - 1, th * p.ht - 1, tb, leader);
+        }
+      } else if (p.rowshare == 2) {
         // small-channel mode: the 9 taps' weights are loaded once and stay in smem; one stage = the
         // three tall (dx = -1,0,+1) A tiles of a whole output tile -> 3*kpt TMA issues per tile
         const uint32_t a_tile = (uint32_t)(p.ht + 2) * 16 * p.kc * 2;
@@ -263,10 +286,7 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
               tma_load_2d(s.wres + ((j * 3 + dyi) * p.kpt + cb) * wtile, &tmw, s.wfull,
                           p.grp_wtap[j][dyi] * p.Cin + cb * p.kc, 0, leader);
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++g) {
-          int t = tile;
-          const int tw = t % p.tiles_w; t /= p.tiles_w;
-          const int th = t % p.tiles_h;
-          const int tb = t / p.tiles_h;
+          const int tw = tile & (p.tiles_w - 1), th = (tile >> p.lw) & (p.tiles_h - 1), tb = tile >> (p.lw + p.lh);
           const int st = g % p.stages, ph = (g / p.stages) & 1;
           mbar_wait(&s.empty[st], ph ^ 1);
           mbar_expect_tx(&s.full[st], 3 * p.kpt * a_tile, leader);
@@ -278,10 +298,8 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
       } else
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int nt_i = tile % p.n_tiles;
-        int t = tile / p.n_tiles;
-        const int tw = t % p.tiles_w; t /= p.tiles_w;
-        const int th = t % p.tiles_h;
-        const int tb = t / p.tiles_h;
+        const int t = tile / p.n_tiles;
+        const int tw = t & (p.tiles_w - 1), th = (t >> p.lw) & (p.tiles_h - 1), tb = t >> (p.lw + p.lh);
         const int n0 = tw * p.wt, m0 = th * p.ht, b0 = tb * p.nt, o0 = nt_i * p.BN;
         for (int kb = 0; kb < nkb; ++kb, ++g) {
           const int st = g % p.stages, ph = (g / p.stages) & 1;
@@ -312,7 +330,42 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
       const uint32_t leader = elect_one();
       const uint32_t idesc = make_idesc(p.BN, false, false);
       int g = 0, li = 0;
-      if (p.rowshare == 2) {
+      if (p.rowshare == 3) {
+        mbar_wait(s.wfull, 0);
+        const uint32_t row16 = (uint32_t)(p.kc * 2) >> 4;               // one stored pixel, in 16-byte units
+        const uint32_t pitch = (uint32_t)(p.wt + 2) * row16;              // one stored row of wt+2 pixels
+        const uint32_t w_tl = wtile >> 4;
+        const uint64_t bd0 = make_desc(smem_u32(s.wres), 16, 16 * p.kc, p.kc);
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li, ++g) {
+          if ((li & 1) != mine) continue;
+          const int as = li % kAccStages, aph = (li / kAccStages) & 1;
+          mbar_wait(&s.acc_empty[as], aph ^ 1);
+          const int st = g % p.stages, ph = (g / p.stages) & 1;
+          mbar_wait(&s.full[st], ph);
+          tc_fence_after();
+          const uint32_t tacc = tmem_base + (uint32_t)(as * kMaxBN);
+          // 8-row core groups = the 8 pixels of one lattice row; consecutive groups one stored row apart
+          const uint64_t ad0 = make_desc(smem_u32(s.a(st)), 16, (uint32_t)(p.wt + 2) * p.kc * 2, p.kc);
+          uint32_t first = 0;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+#pragma unroll
+            for (int dyi = 0; dyi < 3; ++dyi) {
+              const uint64_t ad = ad0 + (uint32_t)(dyi * pitch + j * row16);
+              const uint64_t bd = bd0 + (uint32_t)((j * 3 + dyi) * w_tl);
+              umma_f16(tacc, ad, bd, idesc, first, leader);
+              umma_f16(tacc, ad + 2, bd + 2, idesc, 1, leader);
+              if (p.kc == 64) {
+                umma_f16(tacc, ad + 4, bd + 4, idesc, 1, leader);
+                umma_f16(tacc, ad + 6, bd + 6, idesc, 1, leader);
+              }
+              first = 1;
+            }
+          }
+          umma_commit(&s.empty[st], leader);
+          umma_commit(&s.done[as], leader);
+        }
+      } else if (p.rowshare == 2) {
         const uint32_t a_tile = (uint32_t)(p.ht + 2) * 16 * p.kc * 2;
         mbar_wait(s.wfull, 0);
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li, ++g) {
@@ -395,23 +448,50 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
     const int q = warp % 4;
     const int r = q * 32 + lane;
     const int ni = r % p.wt, mi = (r / p.wt) % p.ht, bi = r / (p.wt * p.ht);
+    // Folded epilogue constants: for gain > 0, lrelu(v) * gain = lrelu(v * gain), and for 0 < slope <= 1,
+    // lrelu(t) = max(t, slope * t): three instructions per element (fma, mul, max).  ncu had this kernel
+    // at 28 thread-instructions per output element with the issue slots 58 % busy - tile decode by
+    // division and a four-step epilogue - which is what bounded the small-channel layers.
+    const float asg = p.acc_scale * p.gain, bsg = p.bias_scale * p.gain;
+    // one 16-column chunk per thread and tile (BN <= 32, a single channel tile): its bias and the current
+    // image's row scales stay in registers
+    const bool cache = p.BN <= 32 && p.n_tiles == 1 && p.cblk == 0;
+    float csc[16], cbi[16];
+    int cached_b = -1;
+    if (cache) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int o = half * 16 + i;
+        cbi[i] = (bias && o < p.Cout) ? bias[o] * bsg : 0.f;
+        csc[i] = asg;
+      }
+    }
     int li = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li) {
       if ((li & 1) != eg) continue;
-      const int nt_i = tile % p.n_tiles;
-      int t = tile / p.n_tiles;
-      const int tw = t % p.tiles_w; t /= p.tiles_w;
-      const int th = t % p.tiles_h;
-      const int tb = t / p.tiles_h;
+      int nt_i = 0, t = tile;
+      if (p.n_tiles > 1) { nt_i = tile % p.n_tiles; t = tile / p.n_tiles; }
+      const int tw = t & (p.tiles_w - 1), th = (t >> p.lw) & (p.tiles_h - 1), tb = t >> (p.lw + p.lh);
       const int n0 = tw * p.wt, m0 = th * p.ht, b0 = tb * p.nt, o0 = nt_i * p.BN;
       const int b = b0 + bi;
       const bool live = b < p.N;
       const long long pix = (long long)b * p.ys_n + (long long)((m0 + mi) * p.os + p.py) * p.ys_h +
                             (long long)((n0 + ni) * p.os + p.px) * p.ys_w;
-      const float nz = (p.noise && live) ? p.noise[(long long)((m0 + mi) * p.os + p.py) * p.OW + (n0 + ni) * p.os + p.px] *
-                                           p.noise_scale : 0.f;
-      // resident mode: 4 single accumulators; ring mode: 2 pairs of partial accumulators
-      const bool ring = p.rowshare != 2;
+      const float nzg = (p.noise && live) ? p.noise[(long long)((m0 + mi) * p.os + p.py) * p.OW + (n0 + ni) * p.os + p.px] *
+                                            p.noise_scale * p.gain : 0.f;
+      if (cache && rowscale && live && b != cached_b) {
+        const float4* rs = reinterpret_cast<const float4*>(rowscale + (long long)b * p.Cout + half * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (half * 16 + 4 * i < p.Cout) {
+            const float4 sc = rs[i];
+            csc[4 * i] = sc.x * asg; csc[4 * i + 1] = sc.y * asg; csc[4 * i + 2] = sc.z * asg; csc[4 * i + 3] = sc.w * asg;
+          }
+        }
+        cached_b = b;
+      }
+      // resident modes: 4 single accumulators; ring mode: 2 pairs of partial accumulators
+      const bool ring = p.rowshare < 2;
       const int as = ring ? (li & 1) : li % kAccStages, aph = ring ? (li >> 1) & 1 : (li / kAccStages) & 1;
       mbar_wait(&s.done[as], aph);
       tc_fence_after();
@@ -427,27 +507,40 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
           const long long yo = p.cblk ? (long long)(oc / p.cblk) * p.ys_blk + oc % p.cblk : oc;
           const int crow = p.cblk ? p.cperiod : p.Cout;
           float f[16];
+          if (cache) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * p.acc_scale;
-          if (rowscale) {
-            const float4* rs = reinterpret_cast<const float4*>(rowscale + (long long)b * crow + o);
+            for (int i = 0; i < 16; ++i) f[i] = fmaf(__uint_as_float(v[i]), csc[i], cbi[i] + nzg);
+          } else {
+            if (rowscale) {
+              const float4* rs = reinterpret_cast<const float4*>(rowscale + (long long)b * crow + o);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 sc = rs[i];
-              f[4 * i] *= sc.x; f[4 * i + 1] *= sc.y; f[4 * i + 2] *= sc.z; f[4 * i + 3] *= sc.w;
+              for (int i = 0; i < 4; ++i) {
+                const float4 sc = rs[i];
+                f[4 * i] = __uint_as_float(v[4 * i]) * (sc.x * asg); f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) * (sc.y * asg);
+                f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) * (sc.z * asg); f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) * (sc.w * asg);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * asg;
+            }
+            if (bias) {
+              const float4* bp = reinterpret_cast<const float4*>(bias + o);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 bb = bp[i];
+                f[4 * i] = fmaf(bb.x, bsg, f[4 * i]); f[4 * i + 1] = fmaf(bb.y, bsg, f[4 * i + 1]);
+                f[4 * i + 2] = fmaf(bb.z, bsg, f[4 * i + 2]); f[4 * i + 3] = fmaf(bb.w, bsg, f[4 * i + 3]);
+              }
+            }
+            if (p.noise) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] += nzg;
             }
           }
-          if (bias) {
-            const float4* bp = reinterpret_cast<const float4*>(bias + o);
+          if (p.slope != 1.f) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 bb = bp[i];
-              f[4 * i] += bb.x * p.bias_scale; f[4 * i + 1] += bb.y * p.bias_scale;
-              f[4 * i + 2] += bb.z * p.bias_scale; f[4 * i + 3] += bb.w * p.bias_scale;
-            }
+            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], f[i] * p.slope);
           }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = (f[i] + nz > 0.f ? f[i] + nz : (f[i] + nz) * p.slope) * p.gain;
           if (p.y_f32) {
             float* yp = reinterpret_cast<float*>(y) + pix + yo;
             if (residual) {
@@ -772,12 +865,12 @@ EncodeTiledFn get_encode() {
 // 4-D map over a dense channels-last bf16 tensor [N, H, W, C]: box {64, wt, ht, nt} walked with
 // element stride `es` along W and H.
 int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int wt, int ht, int nt, int es, int kc,
-                 int extra_rows = 0) {
+                 int extra_rows = 0, int extra_cols = 0) {
   EncodeTiledFn enc = get_encode();
   LCGAN_CHECK(enc != nullptr, "cuTensorMapEncodeTiled unavailable (driver too old?)");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)(wt * es), (cuuint32_t)(ht * es + extra_rows), (cuuint32_t)nt};
+  cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)(wt * es + extra_cols), (cuuint32_t)(ht * es + extra_rows), (cuuint32_t)nt};
   cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
@@ -899,9 +992,10 @@ static int tapconv_tc_launch(const lcgan_tapconv* d, const void* x, const void* 
   p.noise = d->noise; p.noise_scale = d->noise_scale; p.OW = d->OW;
   LCGAN_CHECK(!(d->noise && cblk), "tapconv_tc_blocked: no noise term in the blocked-output form");
 
-  // row-shared mode: full 3x3 stride-1 tap set on a 16-wide, 8-tall, single-image tile
-  p.rowshare = 0;
-  if (d->ntaps == 9 && d->is == 1 && p.wt == 16 && p.ht == 8 && p.nt == 1) {
+  LCGAN_CHECK(d->gain > 0.f && d->slope > 0.f && d->slope <= 1.f, "tapconv_tc: needs gain > 0 and 0 < slope <= 1");
+  // full 3x3 stride-1 tap set?
+  bool full3x3 = false;
+  if (d->ntaps == 9 && d->is == 1) {
     int seen = 0;
     for (int t = 0; t < 9; ++t) {
       const int dy = d->dy[t], dx = d->dx[t];
@@ -909,23 +1003,43 @@ static int tapconv_tc_launch(const lcgan_tapconv* d, const void* x, const void* 
       p.grp_wtap[dx + 1][dy + 1] = d->wtap[t];
       seen |= 1 << ((dy + 1) * 3 + dx + 1);
     }
-    p.rowshare = (seen == 0x1FF) && getenv("LCGAN_NO_ROWSHARE") == nullptr;
+    full3x3 = seen == 0x1FF;
   }
+  p.rowshare = 0;
   p.wres_bytes = 0;
+  int smem_bytes = fwd_smem_bytes();
   const int budget = 3 * (20 * 1024 + 3 * kBBytes);        // bytes available for the operand ring
-  if (p.rowshare && d->Cout <= kMaxBN && 9 * p.BN * d->Cin * 2 <= 80 * 1024 && getenv("LCGAN_NO_RESIDENT") == nullptr) {
-    // small-channel layers: resident weights, one stage per output tile
-    p.rowshare = 2;
+  if (full3x3 && (d->Cin == 32 || d->Cin == 64) && d->Cout <= kMaxBN && d->MW % 8 == 0 && d->MH % 16 == 0 &&
+      9 * p.BN * d->Cin * 2 <= 80 * 1024 && getenv("LCGAN_NO_HALO") == nullptr) {
+    // haloed small-channel mode: 8-wide x 16-tall lattice tiles, ONE (8+2) x (16+2) pixel box per tile serves all
+    // nine taps, weights resident; stage stride padded to the swizzle period
+    p.rowshare = 3;
+    p.wt = 8; p.ht = 16; p.nt = 1;
+    p.tiles_w = d->MW / p.wt; p.tiles_h = d->MH / p.ht;
     p.wres_bytes = 9 * p.BN * d->Cin * 2;
-    p.a_bytes = 3 * p.kpt * (p.ht + 2) * 16 * p.kc * 2;
+    p.a_bytes = ((p.wt + 2) * (p.ht + 2) * p.kc * 2 + 1023) & ~1023;
     p.b_bytes = 0;
-    p.stages = (budget - p.wres_bytes) / p.a_bytes;
-    if (p.stages > 8) p.stages = 8;
+    p.stages = (kMaxSmem - 2048 - p.wres_bytes) / p.a_bytes;
+    if (p.stages > 12) p.stages = 12;
     p.stages &= ~1;                                         // even: see the two-issuer note in the kernel
-    if (p.stages < 2) { p.rowshare = 1; p.wres_bytes = 0; }
+    smem_bytes = 1024 + p.wres_bytes + p.stages * p.a_bytes + 256;
+  } else if (full3x3 && p.wt == 16 && p.ht == 8 && p.nt == 1 && getenv("LCGAN_NO_ROWSHARE") == nullptr) {
+    // row-shared mode: 16-wide, 8-tall, single-image tile; one tall A tile per dx serves the three dy taps
+    p.rowshare = 1;
+    if (d->Cout <= kMaxBN && 9 * p.BN * d->Cin * 2 <= 80 * 1024 && getenv("LCGAN_NO_RESIDENT") == nullptr) {
+      // small-channel layers: resident weights, one stage per output tile
+      p.rowshare = 2;
+      p.wres_bytes = 9 * p.BN * d->Cin * 2;
+      p.a_bytes = 3 * p.kpt * (p.ht + 2) * 16 * p.kc * 2;
+      p.b_bytes = 0;
+      p.stages = (budget - p.wres_bytes) / p.a_bytes;
+      if (p.stages > 8) p.stages = 8;
+      p.stages &= ~1;                                         // even: see the two-issuer note in the kernel
+      if (p.stages < 2) { p.rowshare = 1; p.wres_bytes = 0; }
+    }
+    if (p.rowshare == 1 && p.kc == 64 && getenv("LCGAN_ROWSHARE_WIDE") == nullptr) p.rowshare = 0;   // measured slower on 64-ch k-blocks
   }
-  if (p.rowshare == 1 && p.kc == 64 && getenv("LCGAN_ROWSHARE_WIDE") == nullptr) p.rowshare = 0;   // measured slower on 64-ch k-blocks
-  if (p.rowshare == 2) {
+  if (p.rowshare >= 2) {
   } else if (p.rowshare) {
     p.a_bytes = (p.ht + 2) * 16 * p.kc * 2;                 // 20 KiB (kc=64) / 10 KiB (kc=32)
     p.b_bytes = 3 * p.BN * p.kc * 2;
@@ -935,20 +1049,23 @@ static int tapconv_tc_launch(const lcgan_tapconv* d, const void* x, const void* 
   } else {
     p.a_bytes = kABytes; p.b_bytes = kBBytes; p.stages = kFwdStages;
   }
+  for (p.lw = 0; (1 << p.lw) < p.tiles_w; ++p.lw) {}
+  for (p.lh = 0; (1 << p.lh) < p.tiles_h; ++p.lh) {}
   CUtensorMap tmx, tmw;
-  if (int e = make_act_map(&tmx, x, d->N, d->IH, d->IW, d->Cin, p.wt, p.ht, p.nt, d->is, p.kc, p.rowshare ? 2 : 0)) return e;
+  if (int e = make_act_map(&tmx, x, d->N, d->IH, d->IW, d->Cin, p.wt, p.ht, p.nt, d->is, p.kc, p.rowshare ? 2 : 0,
+                           p.rowshare == 3 ? 2 : 0)) return e;
   if (int e = make_w_map(&tmw, w2, d->Cout, d->w_ld, p.BN, p.kc)) return e;
 
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(tapconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem_bytes());
+    attr_err = cudaFuncSetAttribute(tapconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
   });
   LCGAN_CHECK(attr_err == cudaSuccess, "tapconv_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(attr_err));
   p.n_tiles = (d->Cout + p.BN - 1) / p.BN;
   p.total_tiles = p.tiles_w * p.tiles_h * tiles_b * p.n_tiles;
   const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();   // persistent: one CTA per SM
-  tapconv_tc_kernel<<<grid, kFwdThreads, fwd_smem_bytes(), (cudaStream_t)stream>>>(tmx, tmw, p, y, rowscale, bias, residual);
+  tapconv_tc_kernel<<<grid, kFwdThreads, smem_bytes, (cudaStream_t)stream>>>(tmx, tmw, p, y, rowscale, bias, residual);
   LCGAN_LAUNCH_CHECK();
   return 0;
 }

@@ -52,6 +52,10 @@ CASES = [  # kind, k, N, Cin, Cout, H, W
     # many tiles per persistent CTA (ring wrap-around, TMEM stage reuse, the two-issuer resident mode)
     ("s1", 3, 8, 32, 32, 128, 128), ("s1", 3, 4, 64, 64, 128, 128), ("s1", 3, 4, 128, 128, 128, 64),
     ("s2", 3, 4, 64, 128, 128, 128),
+    # haloed single-copy tiles (3x3 stride 1, Cin 32 / 64, Cout <= 128): 8 x 16 lattice tiles, image borders on every
+    # side of a tile, one tile per image, 16 / 64 output channels, many images, non-square maps
+    ("s1", 3, 3, 32, 16, 16, 8), ("s1", 3, 2, 32, 64, 32, 16), ("s1", 3, 33, 64, 64, 16, 32), ("s1", 3, 2, 32, 32, 256, 256),
+    ("s1", 3, 2, 64, 48, 64, 128),
 ]
 
 
