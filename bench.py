@@ -490,6 +490,13 @@ def summarise_kernels(stats, pk, traffic_table):
     mem = [r for r in rows if r["tflops"] is None and r["gbs"] is not None]
     if mem and mem[0]["kernel"] != top["kernel"]:
         roof["hbm_top"] = obj(mem[0]["kernel"], per_kernel[mem[0]["kernel"]], mem[0]["share"])
+    # the heaviest (kernel, shape) pairs of the whole step, whatever kernel they belong to
+    flat = [(k, sh_, v) for k, d_ in shapes.items() for sh_, v in d_.items()]
+    flat.sort(key=lambda e: -e[2]["ms"])
+    roof["top_shapes"] = [dict(kernel=k, shape=sh_, launches=v["n"], ms=v["ms"], share=v["ms"] / total,
+                               tflops=v["flops"] / (v["ms"] / 1e3) / 1e12 if v["flops"] and v["ms"] > 0 else None,
+                               gbs=v["bytes"] / (v["ms"] / 1e3) / 1e9 if v["bytes"] and v["ms"] > 0 else None)
+                          for k, sh_, v in flat[:24]]
     return roof, rows[:12]
 
 

@@ -842,6 +842,143 @@ tapconv_wgrad_tn_kernel(const __grid_constant__ CUtensorMap tmg, const __grid_co
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// weight-gradient kernel for 3x3 stride-1 layers with 32 / 64 channels, TRANSPOSED and HALOED:
+//   D^T[(dx, c) x (dy, o)] += X_shift(dy, dx)[px x c]^T * G[px x o]      over the pixels of a K-split
+// The layer input is loaded ONCE per 8 x 16 lattice tile as the (8+2) x (16+2)-pixel box of the forward
+// kernel's haloed mode; a tap is a descriptor start offset into it.  Two more descriptor facts make the
+// shape efficient:
+//   * the dx = 0,1,2 views differ by one stored pixel, so with LBO = one pixel row they ARE the consecutive
+//     M blocks of a single MN-major A operand: one MMA covers three taps (M = 3 x 32 of 128 rows for 32
+//     channels; for 64 channels taps dx = 0,1 fill M = 128 and dx = 2 takes a second MMA);
+//   * putting (dx, c) on M and o on N avoids padding a 32-channel gradient to M = 128 (the layout that made
+//     the previous small-channel kernel tensor-bound at 4x the useful work).
+// Rows of A past the last tap read whatever follows in shared memory: each D row depends on its own A row
+// only, and those rows are never stored.  ncu on the previous kernel: 27.9 GB L2->SM per launch for 4.3 GB of
+// operands (every tap re-loaded its own shifted tile); here each pixel of X and G enters shared memory once.
+// ---------------------------------------------------------------------------------------------
+constexpr int kWhStagesMax = 6;
+
+struct WhParams {
+  int N, Cin, Cout;
+  int tiles_w, tiles_h, lw, lh, tiles_total, tiles_per_split;
+  int kcx, kcg;                                 // channels per swizzle row of X / G (= Cin, Cout: 32 or 64)
+  int stages, x_bytes, g_bytes;                 // per-stage bytes (x_bytes padded to the swizzle period)
+  int grp_wtap[3][3];                           // [dx+1][dy+1] -> weight tap index
+  long long w_ld;
+  float scale;
+  int* sems;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+tapconv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUtensorMap tmx,
+                          const WhParams p, float* __restrict__ dw) {
+  extern __shared__ uint8_t smem_raw[];
+  const Smem s = carve(smem_raw, p.stages, p.x_bytes, p.g_bytes);
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int t_begin = blockIdx.x * p.tiles_per_split;
+  const int t_end = min(p.tiles_total, t_begin + p.tiles_per_split);
+  const int nkb = t_end - t_begin;
+  constexpr int WT = 8, HT = 16;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmg);
+    tma_prefetch_desc(&tmx);
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    mbar_init(&s.done[0], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(s.tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s.tmem_slot;
+  const uint32_t rowx = (uint32_t)p.kcx * 2, rowg = (uint32_t)p.kcg * 2;       // bytes of one stored pixel
+  const int nh = p.Cin == 64 ? 2 : 1;                                           // MMAs per (dy, K-step)
+
+  if (warp == 0) {
+    const uint32_t leader = elect_one();
+    const uint32_t tx_bytes = (uint32_t)(WT + 2) * (HT + 2) * rowx + (uint32_t)WT * HT * rowg;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int st = kb % p.stages, ph = (kb / p.stages) & 1;
+      mbar_wait(&s.empty[st], ph ^ 1);
+      const int t = t_begin + kb;
+      const int tw = t & (p.tiles_w - 1), th = (t >> p.lw) & (p.tiles_h - 1), tb = t >> (p.lw + p.lh);
+      mbar_expect_tx(&s.full[st], tx_bytes, leader);
+      tma_load_4d(s.a(st), &tmx, &s.full[st], 0, tw * WT - 1, th * HT - 1, tb, leader);
+      tma_load_4d(s.b(st), &tmg, &s.full[st], 0, tw * WT, th * HT, tb, leader);
+    }
+  } else if (warp == 1) {
+    const uint32_t leader = elect_one();
+    const uint32_t idesc = make_idesc(p.Cout, true, true);
+    const uint32_t row16 = rowx >> 4, pitch16 = (uint32_t)(WT + 2) * row16;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int st = kb % p.stages, ph = (kb / p.stages) & 1;
+      mbar_wait(&s.full[st], ph);
+      tc_fence_after();
+      // A = X: MN-major, M blocks (taps dx, dx+1, ..) one stored pixel apart, 8-pixel K groups one stored row apart
+      const uint64_t ad0 = make_desc(smem_u32(s.a(st)), rowx, (uint32_t)(WT + 2) * rowx, p.kcx);
+      // B = G: MN-major, one channel box, 8-pixel K groups contiguous
+      const uint64_t bd0 = make_desc(smem_u32(s.b(st)), (uint32_t)WT * HT * rowg, 8 * rowg, p.kcg);
+#pragma unroll
+      for (int k = 0; k < HT / 2; ++k) {                   // one MMA K-step = 16 pixels = two lattice rows
+        const uint64_t bd = bd0 + (uint32_t)(k * 16 * (rowg >> 4));
+#pragma unroll
+        for (int dyi = 0; dyi < 3; ++dyi) {
+          const uint64_t ad = ad0 + (uint32_t)((dyi + 2 * k) * pitch16);
+          umma_f16(tmem_base + (uint32_t)(dyi * nh * p.Cout), ad, bd, idesc, (kb | k) != 0, leader);
+          if (nh == 2) umma_f16(tmem_base + (uint32_t)((dyi * 2 + 1) * p.Cout), ad + 2 * row16, bd, idesc, (kb | k) != 0, leader);
+        }
+      }
+      umma_commit(&s.empty[st], leader);
+    }
+    umma_commit(&s.done[0], leader);
+  } else {
+    const int q = warp % 4;
+    const int r = q * 32 + lane;                           // accumulator row = (tap dx, input channel c)
+    mbar_wait(&s.done[0], 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    int* sem = p.sems ? p.sems + q : nullptr;              // deterministic mode: K-splits add in order
+    if (sem) {
+      if (lane == 0) det_wait_turn(sem, blockIdx.x);
+      __syncwarp();
+    }
+    for (int dyi = 0; dyi < 3; ++dyi)
+      for (int h = 0; h < nh; ++h) {
+        const int dxi = nh == 2 ? 2 * h + r / 64 : r / 32;
+        const int c = nh == 2 ? r % 64 : r % 32;
+        const bool live = dxi < 3 && nkb > 0;
+        float* col = dw + (long long)p.grp_wtap[live ? dxi : 0][dyi] * p.Cin + c;
+        for (int o0 = 0; o0 < p.Cout; o0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(trow + (uint32_t)((dyi * nh + h) * p.Cout + o0), v);
+          tmem_ld_wait();
+          if (live) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float* dst = col + (long long)(o0 + i) * p.w_ld;
+              if (sem) det_add(dst, __uint_as_float(v[i]) * p.scale);
+              else atomicAdd(dst, __uint_as_float(v[i]) * p.scale);
+            }
+          }
+        }
+      }
+    if (sem) {
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) det_pass_turn(sem, blockIdx.x, gridDim.x);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -1104,6 +1241,51 @@ extern "C" int lcgan_tapconv_wgrad_tc(const lcgan_tapconv* d, const void* x, con
   if (lcgan_det_enabled()) {
     LCGAN_CHECK(base * 4 <= kDetSems, "tapconv_wgrad_tc: too many tiles for deterministic mode");
     LCGAN_CUDA(cudaGetSymbolAddress((void**)&p.sems, g_sems));
+  }
+
+  // 3x3 stride-1, 32 / 64 channels on both sides: transposed, haloed kernel
+  if (d->ntaps == 9 && d->is == 1 && d->os == 1 && (d->Cin == 32 || d->Cin == 64) && (d->Cout == 32 || d->Cout == 64) &&
+      d->MW % 8 == 0 && d->MH % 16 == 0 && getenv("LCGAN_NO_WGRAD_HALO") == nullptr) {
+    WhParams h{};
+    int seen = 0;
+    for (int t = 0; t < 9; ++t) {
+      const int dy = d->dy[t], dx = d->dx[t];
+      if (dy < -1 || dy > 1 || dx < -1 || dx > 1) { seen = -1; break; }
+      h.grp_wtap[dx + 1][dy + 1] = d->wtap[t];
+      seen |= 1 << ((dy + 1) * 3 + dx + 1);
+    }
+    if (seen == 0x1FF) {
+      h.N = d->N; h.Cin = d->Cin; h.Cout = d->Cout;
+      h.tiles_w = d->MW / 8; h.tiles_h = d->MH / 16;
+      for (h.lw = 0; (1 << h.lw) < h.tiles_w; ++h.lw) {}
+      for (h.lh = 0; (1 << h.lh) < h.tiles_h; ++h.lh) {}
+      h.tiles_total = h.tiles_w * h.tiles_h * d->N;
+      int hs = sm_count();
+      if (hs > h.tiles_total) hs = h.tiles_total;
+      h.tiles_per_split = (h.tiles_total + hs - 1) / hs;
+      hs = (h.tiles_total + h.tiles_per_split - 1) / h.tiles_per_split;
+      h.kcx = d->Cin; h.kcg = d->Cout;
+      h.x_bytes = (10 * 18 * h.kcx * 2 + 1023) & ~1023;
+      h.g_bytes = 8 * 16 * h.kcg * 2;
+      h.stages = (kMaxSmem - 2048) / (h.x_bytes + h.g_bytes);
+      if (h.stages > kWhStagesMax) h.stages = kWhStagesMax;
+      h.w_ld = d->w_ld; h.scale = scale; h.sems = nullptr;
+      if (lcgan_det_enabled()) LCGAN_CUDA(cudaGetSymbolAddress((void**)&h.sems, g_sems));
+      const int smem = 1024 + h.stages * (h.x_bytes + h.g_bytes) + 256;
+      CUtensorMap tmgh, tmxh;
+      if (int e = make_act_map(&tmgh, g, d->N, d->OH, d->OW, d->Cout, 8, 16, 1, 1, h.kcg)) return e;
+      if (int e = make_act_map(&tmxh, x, d->N, d->IH, d->IW, d->Cin, 8, 16, 1, 1, h.kcx, 2, 2)) return e;
+      static std::once_flag once3;
+      static cudaError_t attr_err3 = cudaSuccess;
+      std::call_once(once3, [] {
+        attr_err3 = cudaFuncSetAttribute(tapconv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+      });
+      LCGAN_CHECK(attr_err3 == cudaSuccess, "tapconv_wgrad_halo: cannot raise dynamic shared memory: %s",
+                  cudaGetErrorString(attr_err3));
+      tapconv_wgrad_halo_kernel<<<hs, kThreads, smem, (cudaStream_t)stream>>>(tmgh, tmxh, h, dw2);
+      LCGAN_LAUNCH_CHECK();
+      return 0;
+    }
   }
 
   if (d->ntaps * d->Cin <= kTnMaxN && d->Cin % 16 == 0 && getenv("LCGAN_NO_WGRAD_TN") == nullptr) {
