@@ -402,7 +402,12 @@ def main():
         }
         _emit(line)
     if world > 1:
-        dist.destroy_process_group()
+        # leave without NCCL's teardown: destroy_process_group() can wait forever on communicators that captured
+        # CUDA graphs once used (seen on the B200 box), and the line above is already out
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def roofline_pass(step_fn, it0, _lib, pk):

@@ -96,8 +96,13 @@ for name, it in T.GraphedTrainer._VARIANT_IT.items():
     worst[name] = (w, len(plan.flats))
 if rank == 0:
     print("RESULT " + json.dumps(worst), flush=True)
+# a captured graph that still holds NCCL kernels makes destroy_process_group() wait forever: drop the graphs first,
+# and leave without the teardown
+tr.graphs.clear()
+torch.cuda.synchronize()
 dist.barrier()
-dist.destroy_process_group()
+sys.stdout.flush()
+os._exit(0)
 '''
 
 
@@ -109,7 +114,7 @@ def test_graph_captured_nccl_gradients_equal_mean_of_rank_gradients(tmp_path):
     env = dict(os.environ, LCGAN_ROOT=ROOT)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                         "--master-addr", "127.0.0.1", "--master-port", "29731", str(script)],
-                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=1200)
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=420)
     assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-5000:])
     line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1]
     worst = json.loads(line[7:])
