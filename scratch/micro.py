@@ -28,6 +28,17 @@ for w in which:
         else:
             ms = timeit(lambda: ops.tapconv_wgrad(x, g, plan, C, C))
         print(f"{w:8s} {ms:8.3f} ms  {flops/ms/1e9:8.1f} TF/s  {nbytes/ms/1e6:8.0f} GB/s (algorithmic)")
+    elif w in ("rgbout", "rgbin"):
+        R = 1024
+        if w == "rgbout":
+            x = cl(torch.randn(N, 32, R, R, device=dev).bfloat16()); w2 = torch.randn(3, 32, device=dev).bfloat16()
+            y = torch.empty(N, 3, R, R, device=dev); rs = torch.rand(N, 3, device=dev) + 0.5; bias = torch.randn(3, device=dev)
+            ms = timeit(lambda: ops.tapconv(x, w2, y, plans.conv(1, 1, R, R), rs, bias, None)); tr = x.numel() * 2 + y.numel() * 4
+        else:
+            x = torch.randn(N, 3, R, R, device=dev); w2 = torch.randn(32, 3, device=dev)
+            y = ops.empty_cl(N, 32, R, R, torch.bfloat16, dev); bias = torch.randn(32, device=dev)
+            ms = timeit(lambda: ops.tapconv(x, w2, y, plans.conv(1, 1, R, R), None, bias, None, slope=0.2)); tr = x.numel() * 4 + y.numel() * 2
+        print(f"{w:8s} {ms:8.3f} ms  {tr/ms/1e6:8.0f} GB/s (algorithmic)")
     elif w in ("flowf", "flowd", "floww"):
         C, R = 64, 512
         x = cl(torch.randn(N, C, R, R, device=dev).bfloat16())
