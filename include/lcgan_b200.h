@@ -197,7 +197,8 @@ typedef struct lcgan_pack_chunk {
   const float* src[LCGAN_MT_MAX];  /* w [O][I][K] f32 (K = kh*kw) */
   void* dst[LCGAN_MT_MAX];
   int32_t O[LCGAN_MT_MAX], I[LCGAN_MT_MAX], K[LCGAN_MT_MAX];
-  int32_t mode[LCGAN_MT_MAX];      /* 0: [O][K*I] (forward), 1: [I][K*O] (data gradient), 2: Wsq [O][I] f32 */
+  int32_t mode[LCGAN_MT_MAX];      /* 0: [O][K*I] (forward), 1: [I][K*O] (data gradient), 2: Wsq [O][I] f32,
+                                      3: [4*O][4*I] fused x2 transposed-conv weight (lcgan_tapconv_tc_blocked) */
   float scale[LCGAN_MT_MAX];       /* mode 2: sum_k (round(w)*scale)^2 */
   int32_t count;
 } lcgan_pack_chunk;

@@ -501,7 +501,26 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
       const bool has0 = !ring || nkb > 1 || (g0 & 1) == 0, has1 = ring && (nkb > 1 || (g0 & 1) == 1);
       // 16 accumulator columns -> scale, bias, activation, residual, store
       auto finish16 = [&](const uint32_t* v, int oc) {
-        if (live && oc < p.Cout) {
+        if (live && p.cblk == 4) {
+          // narrow blocked form (2-channel x2 transposed conv): columns 0..7 = (py, px, ch); each py half is one
+          // float4 = the two horizontally adjacent output pixels x 2 channels
+          if (oc == 0) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              float f[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int o = i & 1;
+                float t = __uint_as_float(v[4 * h + i]) * asg;
+                if (rowscale) t *= rowscale[(long long)b * 2 + o];
+                if (bias) t = fmaf(bias[o], bsg, t);
+                f[i] = fmaxf(t, t * p.slope);
+              }
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + pix + (long long)h * p.ys_blk) =
+                  make_float4(f[0], f[1], f[2], f[3]);
+            }
+          }
+        } else if (live && oc < p.Cout) {
           // o: channel whose rowscale / bias apply; yo: element offset of the chunk inside the pixel
           const int o = p.cblk ? oc % p.cperiod : oc;
           const long long yo = p.cblk ? (long long)(oc / p.cblk) * p.ys_blk + oc % p.cblk : oc;
@@ -1066,14 +1085,19 @@ int tn_smem_bytes() { return kTnStages * (kWgABytes + kTnXBytes) + 1024 + 256; }
 
 }  // namespace
 
-extern "C" int lcgan_tapconv_tc_eligible(const lcgan_tapconv* d) {
+static int tc_eligible(const lcgan_tapconv* d, bool narrow_out);
+extern "C" int lcgan_tapconv_tc_eligible(const lcgan_tapconv* d) { return tc_eligible(d, false); }
+
+// narrow_out: 8 output channels (the blocked form of a 2-channel x2 transposed conv), stored as float4 pieces
+static int tc_eligible(const lcgan_tapconv* d, bool narrow_out) {
   if (!d) return 0;
   if (d->x_dtype != LCGAN_BF16) return 0;
-  if (d->Cin % 32 != 0 || d->Cout % 16 != 0) return 0;
+  if (d->Cin % 32 != 0 || (narrow_out ? d->Cout != 8 : d->Cout % 16 != 0)) return 0;
   if (!dense_cl(d->xs_n, d->xs_h, d->xs_w, d->xs_c, d->N, d->IH, d->IW, d->Cin)) return 0;
   // output: channel-innermost, 16-byte aligned pixel rows (dense channels-last or any such strides)
-  if (d->ys_c != 1 || (d->OW > 1 && d->ys_w % 8 != 0) || (d->OH > 1 && d->ys_h % 8 != 0) ||
-      (d->N > 1 && d->ys_n % 8 != 0)) return 0;
+  const int al = narrow_out ? 4 : 8;          // elements per 16 bytes of the narrowest store (f32 float4 / bf16 x 8)
+  if (d->ys_c != 1 || (d->OW > 1 && d->ys_w % al != 0) || (d->OH > 1 && d->ys_h % al != 0) ||
+      (d->N > 1 && d->ys_n % al != 0)) return 0;
   int wt, ht, nt;
   if (!lattice_tile(d->MW, d->MH, &wt, &ht, &nt)) return 0;
   if (d->is < 1 || d->is > 2 || d->os < 1 || d->os > 2) return 0;
@@ -1098,16 +1122,18 @@ extern "C" int lcgan_tapconv_tc(const lcgan_tapconv* d, const void* x, const voi
 extern "C" int lcgan_tapconv_tc_blocked(const lcgan_tapconv* d, const void* x, const void* w2, void* y,
                                         const float* rowscale, const float* bias, int cblk, int64_t ys_blk,
                                         int cperiod, void* stream) {
-  LCGAN_CHECK(d && cblk > 0 && cblk % 16 == 0 && cperiod > 0 && cperiod % 16 == 0 && d->Cout % cblk == 0 &&
-              cblk % cperiod == 0 && ys_blk % 8 == 0,
-              "tapconv_tc_blocked: need cblk %% 16 == 0, cperiod %% 16 == 0, cperiod | cblk | Cout, ys_blk %% 8 == 0");
+  const bool narrow = d && cblk == 4 && cperiod == 2 && d->Cout == 8 && d->y_dtype == LCGAN_F32 && ys_blk % 4 == 0;
+  LCGAN_CHECK(narrow || (d && cblk > 0 && cblk % 16 == 0 && cperiod > 0 && cperiod % 16 == 0 && d->Cout % cblk == 0 &&
+                         cblk % cperiod == 0 && ys_blk % 8 == 0),
+              "tapconv_tc_blocked: need cblk %% 16 == 0, cperiod %% 16 == 0, cperiod | cblk | Cout, ys_blk %% 8 == 0 "
+              "(or the narrow form: Cout 8, cblk 4, cperiod 2, f32 output)");
   return tapconv_tc_launch(d, x, w2, y, rowscale, bias, nullptr, stream, cblk, ys_blk, cperiod);
 }
 
 static int tapconv_tc_launch(const lcgan_tapconv* d, const void* x, const void* w2, void* y, const float* rowscale,
                              const float* bias, const void* residual, void* stream, int cblk, long long ys_blk,
                              int cperiod) {
-  LCGAN_CHECK(lcgan_tapconv_tc_eligible(d), "tapconv_tc: descriptor not eligible for the tensor-core path");
+  LCGAN_CHECK(tc_eligible(d, cblk == 4), "tapconv_tc: descriptor not eligible for the tensor-core path");
   LCGAN_CHECK(d->w_dtype == LCGAN_BF16, "tapconv_tc: weights must be bf16");
   LCGAN_CHECK(x && w2 && y, "tapconv_tc: null tensor pointer");
   LCGAN_CHECK(((uintptr_t)x % 16 == 0) && ((uintptr_t)w2 % 16 == 0) && ((uintptr_t)y % 16 == 0) &&
@@ -1121,7 +1147,8 @@ static int tapconv_tc_launch(const lcgan_tapconv* d, const void* x, const void* 
   p.kc = d->Cin % 64 == 0 ? 64 : 32;
   p.ntaps = d->ntaps; p.kpt = d->Cin / p.kc;
   for (int t = 0; t < d->ntaps; ++t) { p.dy[t] = d->dy[t]; p.dx[t] = d->dx[t]; p.wtap[t] = d->wtap[t]; }
-  p.BN = d->Cout >= kMaxBN ? kMaxBN : d->Cout;       // Cout % 16 == 0
+  p.BN = d->Cout >= kMaxBN ? kMaxBN : (d->Cout < 16 ? 16 : d->Cout);   // Cout % 16 == 0 (narrow form: 8 of 16 columns,
+                                                                        // the weight box rows past Cout are zero-filled by TMA)
   p.ys_n = d->ys_n; p.ys_h = d->ys_h; p.ys_w = d->ys_w;
   p.y_f32 = d->y_dtype == LCGAN_F32;
   p.acc_scale = d->acc_scale; p.bias_scale = d->bias_scale; p.slope = d->slope; p.gain = d->gain;

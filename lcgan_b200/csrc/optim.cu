@@ -70,6 +70,7 @@ __global__ void adam_count_kernel(const lcgan_adam_chunk ch) {
 //   mode 1: dst[c][k*O + o] = w[o][c][k]      (data-gradient layout)
 //   mode 2: dst[o][c] = sum_k (q(w[o][c][k]) * scale)^2   (f32; q = rounding to the pack dtype)  - the
 //           demodulation table Wsq of custom_layers.py:65-67
+//   mode 3: the [4*O][4*I] phase-major / tap-major weight of the fused x2 transposed conv (K = 9)
 // Modes 0 / 1 go through a shared-memory tile of 32 output channels x 32 input channels x K: the source rows
 // (32*K contiguous floats) are read coalesced, and the destination is written in runs of 32 contiguous elements
 // (c-fastest for mode 0, o-fastest for mode 1).  (A destination-ordered gather read the 260 MB of discriminator
@@ -83,6 +84,22 @@ pack_kernel(const lcgan_pack_chunk ch) {
   const int j = blockIdx.y;
   const float* __restrict__ w = ch.src[j];
   const int O = ch.O[j], I = ch.I[j], K = ch.K[j], mode = ch.mode[j];
+  if (mode == 3) {
+    // fused x2 transposed conv (lcgan_tapconv_tc_blocked): dst[(py*2+px)*O + o][(dy*2+dx)*I + c] =
+    // w[o][c][ki][kj], ki = py+1-2dy, kj = px+1-2dx, zero where a kernel index falls outside 0..2 (K = 9)
+    T* dst = reinterpret_cast<T*>(ch.dst[j]);
+    const int64_t n = 16LL * O * I;
+    for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+      const int c = (int)(i % I);
+      int64_t r = i / I;
+      const int tap = (int)(r % 4); r /= 4;
+      const int o = (int)(r % O), ph = (int)(r / O);
+      const int ki = (ph >> 1) + 1 - 2 * (tap >> 1), kj = (ph & 1) + 1 - 2 * (tap & 1);
+      const bool ok = ki >= 0 && ki <= 2 && kj >= 0 && kj <= 2;
+      stf(dst + i, ok ? w[((int64_t)o * I + c) * 9 + ki * 3 + kj] : 0.f);
+    }
+    return;
+  }
   if (mode == 2) {
     const float sc = ch.scale[j];
     float* dst = reinterpret_cast<float*>(ch.dst[j]);
@@ -146,7 +163,8 @@ extern "C" int lcgan_pack_weights(const lcgan_pack_chunk* ch, int dt, void* stre
   LCGAN_CHECK(ch && ch->count > 0 && ch->count <= LCGAN_MT_MAX, "pack_weights: bad chunk");
   for (int k = 0; k < ch->count; ++k)
     LCGAN_CHECK(ch->src[k] && ch->dst[k] && ch->O[k] > 0 && ch->I[k] > 0 && ch->K[k] > 0 && ch->K[k] <= kPackMaxK &&
-                ch->mode[k] >= 0 && ch->mode[k] <= 2, "pack_weights: bad chunk entry %d", k);
+                ch->mode[k] >= 0 && ch->mode[k] <= 3 && (ch->mode[k] != 3 || ch->K[k] == 9),
+                "pack_weights: bad chunk entry %d", k);
   cudaStream_t s = (cudaStream_t)stream;
   // 37 KB of static shared memory per block.  The two 8192x2048 head weights dominate (16 384 tiles each), and a
   // tile is latency-bound (4 KB in, barrier, 2 KB out): 4 blocks per SM and tensor keep enough tiles in flight;

@@ -175,15 +175,21 @@ def _pack_shape(w, kind):
     k = w.shape[2] * w.shape[3] if w.dim() == 4 else 1
     if kind[0] == "wsq":
         return (o, i), torch.float32
+    if kind[0] == "up2f":
+        return (4 * o, 4 * i), kind[1]
     return ((i, k * o) if kind[1] else (o, k * i)), kind[2]
+
+
+def _kind_dtype(kind):
+    """compute dtype of a cached kind: ("pack", transposed, dtype) | ("wsq", dtype, c) | ("up2f", dtype)"""
+    return kind[2] if kind[0] == "pack" else kind[1]
 
 
 def _launch_packs(entries):
     """entries: [(w, kind, dst)] -> lcgan_pack_weights launches of up to MT_MAX tensors per compute dtype."""
     by_dt = {}
     for e in entries:
-        dt = e[1][2] if e[1][0] == "pack" else e[1][1]
-        by_dt.setdefault(dt, []).append(e)
+        by_dt.setdefault(_kind_dtype(e[1]), []).append(e)
     for dt, lst in by_dt.items():
         for i0 in range(0, len(lst), _lib.MT_MAX):
             part = lst[i0:i0 + _lib.MT_MAX]
@@ -194,6 +200,8 @@ def _launch_packs(entries):
                 ch.K[j] = w.shape[2] * w.shape[3] if w.dim() == 4 else 1
                 if kind[0] == "wsq":
                     ch.mode[j], ch.scale[j] = 2, kind[2]
+                elif kind[0] == "up2f":
+                    ch.mode[j], ch.scale[j] = 3, 1.0
                 else:
                     ch.mode[j], ch.scale[j] = (1 if kind[1] else 0), 1.0
             ch.count = len(part)
@@ -209,11 +217,13 @@ def _derive(w, kind):
         if hit is not None:
             return hit
     wd = w.detach()
-    dtype = kind[2] if kind[0] == "pack" else kind[1]
-    if _kernel_packable(wd, dtype):
+    dtype = _kind_dtype(kind)
+    if _kernel_packable(wd, dtype) and (kind[0] != "up2f" or (wd.dim() == 4 and wd.shape[2] == wd.shape[3] == 3)):
         shape, odt = _pack_shape(wd, kind)
         dst = torch.empty(shape, dtype=odt, device=wd.device)
         _launch_packs([(wd, kind, dst)])
+    elif kind[0] == "up2f":
+        dst = fused_up2_weights(_derive(w, ("pack", False, dtype)), wd.shape[1])
     elif kind[0] == "pack":
         w4 = wd[:, :, None, None] if wd.dim() == 2 else wd
         perm = (1, 2, 3, 0) if kind[1] else (0, 2, 3, 1)
@@ -255,7 +265,7 @@ def prepack(*modules):
                 continue
             wd = w.detach()
             for kind in kinds:
-                dtype = kind[2] if kind[0] == "pack" else kind[1]
+                dtype = _kind_dtype(kind)
                 if _cache_get(w, kind) is None and _kernel_packable(wd, dtype):
                     shape, odt = _pack_shape(wd, kind)
                     dst = torch.empty(shape, dtype=odt, device=wd.device)
@@ -357,14 +367,18 @@ def fused_up2_weights(w2: torch.Tensor, cin: int) -> torch.Tensor:
     return wf
 
 
-def _tapconv_up2_fused(lib, d, x, w2, y, plan, rowscale, bias, slope, gain, bias_scale, acc_scale, st):
+_FLOW_TC = os.environ.get("LCGAN_NO_FLOW_TC", "0") != "1"
+
+
+def _tapconv_up2_fused(lib, d, x, w2, y, plan, rowscale, bias, slope, gain, bias_scale, acc_scale, st, wf=None):
     """conv_transpose2d(k3, s2, p1, op1) as a 4-tap conv over the input lattice with 4*Cout output channels
     (phase-major): out(2m+py, 2n+px) = sum_{dy,dx in {0,1}} x[m+dy, n+dx] w[py+1-2dy, px+1-2dx]; the
     (phase, tap) blocks with a kernel index outside 0..2 are zero.  The epilogue scatters channel block
     (py, px) to output pixel (2m+py, 2n+px) (lcgan_tapconv_tc_blocked)."""
     cout, cin = w2.shape[0], x.shape[1]
     n, _, h, w = x.shape
-    wf = fused_up2_weights(w2, cin)
+    if wf is None:
+        wf = fused_up2_weights(w2, cin)
     d.N, d.IH, d.IW, d.Cin = n, h, w, cin
     d.OH, d.OW, d.Cout = h, w, 4 * cout
     d.xs_n, d.xs_h, d.xs_w, d.xs_c = _strides_nhwc(x)
@@ -377,7 +391,7 @@ def _tapconv_up2_fused(lib, d, x, w2, y, plan, rowscale, bias, slope, gain, bias
         d.dy[t], d.dx[t], d.wtap[t] = dy, dx, t
     d.w_ld = 4 * cin
     d.acc_scale, d.bias_scale, d.slope, d.gain = acc_scale, bias_scale, slope, gain
-    if not lib.lcgan_tapconv_tc_eligible(C.byref(d)):
+    if cout != 2 and not lib.lcgan_tapconv_tc_eligible(C.byref(d)):
         raise RuntimeError("fused x2 transposed conv: descriptor not eligible for the tensor-core path")
     _lib.call("lcgan_tapconv_tc_blocked", C.byref(d), _ptr(x), _ptr(wf), _ptr(y), _ptr(rowscale), _ptr(bias),
               2 * cout, C.c_int64(ysh), cout, st, tag=_shape_tag("lcgan_tapconv_tc_up2fused", d),
@@ -386,7 +400,7 @@ def _tapconv_up2_fused(lib, d, x, w2, y, plan, rowscale, bias, slope, gain, bias
 
 
 def tapconv(x, w2, y, plan: plans.Plan, rowscale=None, bias=None, residual=None, slope=1.0, gain=1.0,
-            bias_scale=1.0, acc_scale=1.0, noise=None):
+            bias_scale=1.0, acc_scale=1.0, noise=None, up2f=None):
     """y = epilogue(tapconv(x, w2)) for every launch of the plan; x, y logical NCHW.  noise: optional
     contiguous f32 [OH, OW] plane added before the activation (custom_layers.py:108-110)."""
     _need_cuda(x, w2, y)
@@ -405,6 +419,12 @@ def tapconv(x, w2, y, plan: plans.Plan, rowscale=None, bias=None, residual=None,
             and noise is None and cout % 16 == 0 and cin % 32 == 0 and cin <= _UP2_FUSED_MAX_CIN and x.dtype == torch.bfloat16
             and w2.dtype == torch.bfloat16 and _is_cl_dense(x) and _is_cl_dense(y)):
         _tapconv_up2_fused(lib, d, x, w2, y, plan, rowscale, bias, slope, gain, bias_scale, acc_scale, st)
+        return y
+    if (up2f is not None and _USE_TC and _FLOW_TC and cout == 2 and len(plan.launches) == 4 and plan.launches[0].os == 2
+            and residual is None and noise is None and cin % 32 == 0 and x.dtype == torch.bfloat16
+            and y.dtype == torch.float32 and _is_cl_dense(x) and _is_cl_dense(y)):
+        # flow layer (C -> 2, x2): one tensor-core launch over the input lattice, 8 = 4 phases x 2 channels columns
+        _tapconv_up2_fused(lib, d, x, w2, y, plan, rowscale, bias, slope, gain, bias_scale, acc_scale, st, wf=up2f)
         return y
     if len(plan.launches) == 4 and cout <= 4 and residual is None and noise is None and plan.launches[0].os == 2:
         # x2 transposed conv of a flow layer: one fused launch for the four output phases
@@ -830,7 +850,11 @@ class ModConvAct(torch.autograd.Function):
         xs = _modulate_raw(x, s)
         w2 = pack_weight(w, False, compute)
         y = _alloc_out(x.shape[0], w2.shape[0], plan.OH, plan.OW, out_dtype, x.device, out_nchw)
-        tapconv(xs, w2, y, plan, d, bias, None, slope, gain, bias_scale, wscale, noise)
+        up2f = None
+        if (w.shape[0] == 2 and len(plan.launches) == 4 and compute == torch.bfloat16 and _FLOW_TC and _USE_TC
+                and out_dtype == torch.float32 and not out_nchw):
+            up2f = _derive(w, ("up2f", compute))
+        tapconv(xs, w2, y, plan, d, bias, None, slope, gain, bias_scale, wscale, noise, up2f)
         del xs
         ctx.save_for_backward(x, s, w, bias, d, y)
         ctx.cfg = (wscale, plan, slope, gain, bias_scale)

@@ -46,7 +46,9 @@ for w in which:
         if w == "flowf":
             w2 = ops.pack_weight(wt, False, torch.bfloat16)
             y = ops.empty_cl(N, 2, 2 * R, 2 * R, torch.float32, dev)
-            ms = timeit(lambda: ops.tapconv(x, w2, y, plan, None, None, None)); tr = x.numel() * 2 + y.numel() * 4
+            wp = torch.nn.Parameter(wt)
+            wf = ops._derive(wp, ("up2f", torch.bfloat16)) if os.environ.get("LCGAN_NO_FLOW_TC") != "1" else None
+            ms = timeit(lambda: ops.tapconv(x, w2, y, plan, None, None, None, up2f=wf)); tr = x.numel() * 2 + y.numel() * 4
         elif w == "flowd":
             g = cl(torch.randn(N, 2, 2 * R, 2 * R, device=dev)); w2 = ops.pack_weight(wt, True, torch.bfloat16)
             y = ops.empty_cl(N, C, R, R, torch.bfloat16, dev)

@@ -131,3 +131,31 @@ def test_fused_up2_matches_four_phase_path(case, out_f32):
     a, b = outs
     assert torch.isfinite(b).all()
     assert rel_l2(b, a) < (1e-5 if out_f32 else 4e-3), f"{case}: {rel_l2(b, a)}"
+
+
+@pytest.mark.parametrize("case", [(2, 64, 16, 16), (3, 128, 8, 16), (1, 32, 64, 32), (5, 64, 4, 4)])   # N, Cin, H, W
+def test_flow_layer_on_tensor_cores_matches_thin_kernel(case):
+    """The flow layers (conv_transpose2d k3 s2, C -> 2, fp32 out: custom_layers.py:78,150) as ONE tensor-core launch
+    (narrow blocked epilogue: 4 phases x 2 channels) against the CUDA-core all-phase kernel, with every epilogue term;
+    the fused weight comes from the multi-tensor pack kernel (mode 3) and must equal the torch construction."""
+    from lcgan_b200 import ops, plans, _lib
+    N, Cin, H, W = case
+    plan = plans.conv_transpose_up2(3, H, W)
+    x = _cl(torch.randn(N, Cin, H, W, device="cuda").bfloat16())
+    wparam = torch.nn.Parameter(torch.randn(2, Cin, 3, 3, device="cuda") / (9 * Cin) ** 0.5)
+    w2 = ops.pack_weight(wparam, False, torch.bfloat16)
+    wf = ops._derive(wparam, ("up2f", torch.bfloat16))
+    assert torch.equal(wf, ops.fused_up2_weights(w2, Cin))
+    rs = torch.rand(N, 2, device="cuda") + 0.5
+    bias = torch.randn(2, device="cuda")
+    outs = []
+    for fused in (None, wf):
+        before = dict(_lib.counts)
+        y = ops.empty_cl(N, 2, 2 * H, 2 * W, torch.float32, "cuda").fill_(float("nan"))
+        ops.tapconv(x, w2, y, plan, rs, bias, None, slope=0.2, gain=1.4, bias_scale=0.5, acc_scale=0.7, up2f=fused)
+        key = "lcgan_tapconv_tc_blocked" if fused is not None else "lcgan_tapconv_up2_thin"
+        assert _lib.counts.get(key, 0) == before.get(key, 0) + 1
+        outs.append(y)
+    torch.cuda.synchronize()
+    assert torch.isfinite(outs[1]).all()
+    assert rel_l2(outs[1], outs[0]) < 1e-5, f"{case}: {rel_l2(outs[1], outs[0])}"
