@@ -113,6 +113,15 @@ int lcgan_tapconv_wgrad_tc(const lcgan_tapconv* d, const void* x, const void* g,
 int lcgan_box3(const void* a, const void* mask, void* out, int dt, int N, int H, int W, int C,
                float pre_slope, float pre_gain, float post_slope, float post_gain, void* stream);
 
+/* lcgan_box3 with the NEXT layer's style modulation (custom_layers.py:62-64) folded in; cs [N,C] f32:
+ *   mask == NULL:  out = post(box3(a)) * cs[b,c]
+ *   mask != NULL:  out = box3(a * cs[b,c] * (mask*cs > 0 ? pre_gain : pre_gain*pre_slope)),
+ *                  red[b,c] += sum_p a*mask   (f32, caller-zeroed, may be NULL)
+ * Shapes the tiled kernel takes only: C % 32 == 0 (bf16) / 16 (f32), W >= 32, H >= 16. */
+int lcgan_box3_cs(const void* a, const void* mask, void* out, const float* cs, float* red, int dt, int N,
+                  int H, int W, int C, float pre_slope, float pre_gain, float post_slope, float post_gain,
+                  void* stream);
+
 /* y[b,i,j,c] = scale * sum_{2x2} x[b,2i+a,2j+b,c]   (F.avg_pool2d(2,2), custom_layers.py:202; scale=.25) */
 int lcgan_pool2(const void* x, void* y, int dt, int N, int H, int W, int C, float scale, void* stream);
 /* y[b,2i+a,2j+b,c] = scale * x[b,i,j,c]   (F.interpolate nearest x2, custom_layers.py:146; adjoint of pool2) */

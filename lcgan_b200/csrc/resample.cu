@@ -151,7 +151,11 @@ constexpr int kBoxTW = 32, kBoxTH = 16, kBoxWW = kBoxTW + 2;   // tile height: 1
 template <typename T, bool MASK, int TH>
 __global__ void __launch_bounds__(kThreads)
 box3_tile_kernel(const T* __restrict__ a, const T* __restrict__ mask, T* __restrict__ out, int H, int W, int C,
-                 float pre_slope, float pre_gain, float post_slope, float post_gain) {
+                 float pre_slope, float pre_gain, float post_slope, float post_gain,
+                 const float* __restrict__ cs = nullptr, float* __restrict__ red = nullptr) {
+  // cs [N,C] (optional): per-(image, channel) scale - the style modulation of the NEXT layer folded into this
+  // pass: forward out = post(box3(a)) * cs; backward (MASK) pre(a) = a * cs * lrelu'(mask * cs), and
+  // red[b,c] += sum over the tile's own pixels of a * mask (the style gradient, divided by cs on the host)
   constexpr int E = 16 / sizeof(T);
   constexpr int kBoxWH = TH + 2, SR = TH / 2;               // window height, rows per thread
   constexpr int kWin = kBoxWW * kBoxWH * 64;
@@ -173,7 +177,11 @@ box3_tile_kernel(const T* __restrict__ a, const T* __restrict__ mask, T* __restr
   __syncthreads();
   const int v = threadIdx.x & 3, xq = (threadIdx.x >> 2) & 31, strip = threadIdx.x >> 7;
   const int ox = tx * kBoxTW + xq;
-  if (ox >= W) return;
+  float csv[E], racc[E];
+#pragma unroll
+  for (int i = 0; i < E; ++i) { csv[i] = cs ? cs[(int64_t)b * C + c0 + v * E + i] : 1.f; racc[i] = 0.f; }
+  const bool col_live = ox < W;
+  if (!col_live && !(MASK && red)) return;                  // (with a reduction every thread reaches the barrier below)
   const float neg = pre_gain * pre_slope;
   float h0[E], h1[E], h2[E];
 #pragma unroll
@@ -190,24 +198,46 @@ box3_tile_kernel(const T* __restrict__ a, const T* __restrict__ mask, T* __restr
         float mf[E];
         m.v = *reinterpret_cast<const decltype(m.v)*>(p + kWin + 64 * k);
         m.unpack(mf);
+        if (red && k == 1 && rr >= 1 && rr <= SR && col_live) {      // the tile's own pixels: centre column, own rows
 #pragma unroll
-        for (int i = 0; i < E; ++i) f[k][i] *= (mf[i] > 0.f ? pre_gain : neg);
+          for (int i = 0; i < E; ++i) racc[i] = fmaf(f[k][i], mf[i], racc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < E; ++i) f[k][i] *= csv[i] * (mf[i] * csv[i] > 0.f ? pre_gain : neg);
       }
     }
 #pragma unroll
     for (int i = 0; i < E; ++i) { h0[i] = h1[i]; h1[i] = h2[i]; h2[i] = f[0][i] + f[1][i] + f[2][i]; }
     if (rr >= 2) {
       const int oy = ty * TH + strip * SR + rr - 2;
-      if (oy < H) {
+      if (oy < H && col_live) {
         float o[E];
 #pragma unroll
         for (int i = 0; i < E; ++i) {
           const float sv = (h0[i] + h1[i] + h2[i]) * (1.f / 9.f);
           o[i] = (sv > 0.f ? sv : sv * post_slope) * post_gain;
+          if constexpr (!MASK) o[i] *= csv[i];
         }
         Vec16<T> w;
         w.pack(o);
         w.store(out + (((int64_t)b * H + oy) * W + ox) * C + c0 + v * E);
+      }
+    }
+  }
+  if constexpr (MASK) {
+    if (red) {
+      // rows of the window beyond the image contribute zeros (zero-filled window), columns beyond it were skipped;
+      // sum the 64 threads (32 columns x 2 strips) that share a channel vector, one atomic per channel and CTA
+      __syncthreads();                                        // the windows are no longer read: reuse them
+      float* rs = reinterpret_cast<float*>(sm);
+#pragma unroll
+      for (int i = 0; i < E; ++i) rs[threadIdx.x * E + i] = racc[i];
+      __syncthreads();
+      if (threadIdx.x < 4 * E) {
+        const int vv = threadIdx.x / E, i = threadIdx.x % E;
+        float t = 0.f;
+        for (int j = 0; j < kThreads / 4; ++j) t += rs[(j * 4 + vv) * E + i];
+        atomicAdd(red + (int64_t)b * C + c0 + vv * E + i, t);
       }
     }
   }
@@ -572,6 +602,28 @@ extern "C" int lcgan_box3(const void* a, const void* mask, void* out, int dt, in
     DISPATCH_TV(dt, C, CALL);
 #undef CALL
   }
+  LCGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+// Box filter with the next layer's style folded in (see box3_tile_kernel): tile shapes only.
+extern "C" int lcgan_box3_cs(const void* a, const void* mask, void* out, const float* cs, float* red, int dt, int N,
+                             int H, int W, int C, float pre_slope, float pre_gain, float post_slope, float post_gain,
+                             void* stream) {
+  LCGAN_CHECK(a && out && cs && N > 0 && H > 0 && W > 0 && C > 0, "box3_cs: bad arguments");
+  LCGAN_CHECK(!red || mask, "box3_cs: the reduction needs the mask tensor");
+  const int cc = dt == LCGAN_BF16 ? 32 : 16;
+  LCGAN_CHECK((dt == LCGAN_BF16 || dt == LCGAN_F32) && C % cc == 0 && W >= kBoxTW && H >= kBoxTH,
+              "box3_cs: needs C %% %d == 0, W >= %d, H >= %d (use lcgan_box3 + lcgan_modulate otherwise)", cc, kBoxTW, kBoxTH);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int th = mask ? 8 : kBoxTH;
+  const dim3 grid(N * ((H + th - 1) / th) * ((W + kBoxTW - 1) / kBoxTW) * (C / cc));
+#define BT(T, M, THH)                                                                                     \
+  box3_tile_kernel<T, M, THH><<<grid, kThreads, 0, s>>>((const T*)a, (const T*)mask, (T*)out, H, W, C,       \
+                                                        pre_slope, pre_gain, post_slope, post_gain, cs, red)
+  if (dt == LCGAN_BF16) { if (mask) BT(bf16, true, 8); else BT(bf16, false, 16); }
+  else { if (mask) BT(float, true, 8); else BT(float, false, 16); }
+#undef BT
   LCGAN_LAUNCH_CHECK();
   return 0;
 }

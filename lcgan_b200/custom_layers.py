@@ -93,9 +93,10 @@ class ModulatedConv2d(nn.Module):
         self.lr_mul = lr_mul
         self.eps = eps
 
-    def forward(self, x, s, slope=1.0, gain=1.0, out_dtype=None, out_nchw=False, noise=None):
+    def forward(self, x, s, slope=1.0, gain=1.0, out_dtype=None, out_nchw=False, noise=None, premodulated=False):
         """noise: optional f32 [H_out, W_out] plane added between the conv (+bias) and the activation
-        (SynthesisLayer's noise injection, fused into the conv epilogue)."""
+        (SynthesisLayer's noise injection, fused into the conv epilogue).  premodulated: x is already x * s (its
+        producer folded the style in, ops.Box3ActMod)."""
         w = self.weight.weight
         c = float(self.weight.c)
         # demodulation coefficients, fp32: d[b,o] = rsqrt(s^2 @ Wsq^T + eps), Wsq cached per weight version
@@ -109,7 +110,7 @@ class ModulatedConv2d(nn.Module):
         if noise is not None:
             noise = noise.float().contiguous()
         return ops.ModConvAct.apply(_as_act(x), s, w, self.bias, d, noise, c, plan, slope,
-                                    gain, float(self.lr_mul), out_dtype or ops.act_dtype(), out_nchw)
+                                    gain, float(self.lr_mul), out_dtype or ops.act_dtype(), out_nchw, premodulated)
 
 
 class SynthesisLayer(nn.Module):
@@ -129,15 +130,20 @@ class SynthesisLayer(nn.Module):
             self.noise_strength = nn.Parameter(torch.zeros([]))
             self.register_buffer("noise_const", torch.randn([self.resolution, self.resolution]))
 
-    def forward(self, x, latent, slope=1.0, gain=1.0, out_dtype=None, out_nchw=False):
-        s = self.linear(latent.float())
+    def style(self, latent):
+        """The per-sample channel scales of this layer (custom_layers.py:105): [b, in_features] f32."""
+        return self.linear(latent.float()).float().contiguous()
+
+    def forward(self, x, latent, slope=1.0, gain=1.0, out_dtype=None, out_nchw=False, style=None):
+        """style: the result of self.style(latent) when the caller already folded it into x (x = activation * style)."""
+        s = self.linear(latent.float()) if style is None else style
         if not self.use_noise:
-            return self.modulated_conv(x, s, slope, gain, out_dtype, out_nchw)
+            return self.modulated_conv(x, s, slope, gain, out_dtype, out_nchw, premodulated=style is not None)
         # custom_layers.py:108-110: x + noise_const * noise_strength * noise_gain, between the conv and any
         # activation -> a [res, res] plane (a weight-sized torch op, differentiable w.r.t. noise_strength)
         # that the conv epilogue adds before the leaky-relu.  cnn.py never enables it (use_noise=False).
         plane = self.noise_const * self.noise_strength * self.noise_gain
-        return self.modulated_conv(x, s, slope, gain, out_dtype, out_nchw, noise=plane)
+        return self.modulated_conv(x, s, slope, gain, out_dtype, out_nchw, noise=plane, premodulated=style is not None)
 
 
 class SynthesisBlock(nn.Module):
@@ -175,8 +181,14 @@ class SynthesisBlock(nn.Module):
         flow = self.flow_layer(x, g_lat, out_dtype=torch.float32)                # fp32: sub-pixel offsets
         flow = ops.Box3.apply(flow)
         t = self.modulated_conv0(x, a_lat0)                                       # x2 up-conv + bias
-        t = ops.Box3Act.apply(t, 0.2, float(self.gain))                           # box -> lrelu * sqrt2
-        t = self.modulated_conv1(t, a_lat1, slope=0.2)                            # conv -> lrelu
+        if ops.box3_mod_eligible(t):
+            # box -> lrelu * sqrt2 -> * style of the next conv, one pass; the conv reads the modulated tensor
+            s1 = self.modulated_conv1.style(a_lat1)
+            t = ops.Box3ActMod.apply(t, s1, 0.2, float(self.gain))
+            t = self.modulated_conv1(t, a_lat1, slope=0.2, style=s1)              # conv -> lrelu
+        else:
+            t = ops.Box3Act.apply(t, 0.2, float(self.gain))                       # box -> lrelu * sqrt2
+            t = self.modulated_conv1(t, a_lat1, slope=0.2)                        # conv -> lrelu
         y = ops.Up2BoxAdd.apply(skip_lo, t)                                       # box(up2(skip)) + t
         return ops.Warp.apply(y, flow, float(self.max_flow_scale))                # tanh + grid + bicubic
 

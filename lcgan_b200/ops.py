@@ -746,6 +746,52 @@ class Box3Act(torch.autograd.Function):
         return dx, None, None
 
 
+def box3_mod_eligible(x) -> bool:
+    """Shapes the tiled box kernel with a folded style scale takes (lcgan_box3_cs)."""
+    n, c, h, w = x.shape
+    return x.is_cuda and w >= 32 and h >= 16 and c % (32 if x.dtype == torch.bfloat16 else 16) == 0 and _FOLD_STYLE
+
+
+_FOLD_STYLE = os.environ.get("LCGAN_NO_FOLD_STYLE", "0") != "1"
+
+
+class Box3ActMod(torch.autograd.Function):
+    """y = lrelu(box3(x), slope) * gain * s[b,c]: Box3Act with the style modulation of the FOLLOWING modulated
+    conv (custom_layers.py:62-64, shared-weight form) folded into the same pass - the conv then reads y directly
+    (ModConvAct with premodulated=True), so neither x*s nor its recomputation in backward ever makes a pass over
+    HBM, and the style gradient ds = sum_p dy * a (a = y / s) is reduced inside the backward box pass."""
+
+    @staticmethod
+    def forward(ctx, x, s, slope, gain):
+        _need_cuda(x, s)
+        x = _cl(x)
+        n, c, h, w = x.shape
+        assert s.dtype == torch.float32 and s.is_contiguous() and tuple(s.shape) == (n, c)
+        y = torch.empty_like(x)
+        _lib.call("lcgan_box3_cs", _ptr(x), None, _ptr(y), _ptr(s), None, _dt(x), n, h, w, c,
+                  C.c_float(1.0), C.c_float(1.0), C.c_float(slope), C.c_float(gain), _stream(x),
+                  nbytes=2 * x.numel() * x.element_size(), tag="box3_act")
+        ctx.save_for_backward(y, s)
+        ctx.cfg = (slope, gain)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        y, s = ctx.saved_tensors
+        slope, gain = ctx.cfg
+        dy = _cl(dy, y.dtype)
+        n, c, h, w = y.shape
+        dx = torch.empty_like(y)
+        red = torch.zeros_like(s) if ctx.needs_input_grad[1] else None
+        _lib.call("lcgan_box3_cs", _ptr(dy), _ptr(y), _ptr(dx), _ptr(s), _ptr(red), _dt(y), n, h, w, c,
+                  C.c_float(slope), C.c_float(gain), C.c_float(1.0), C.c_float(1.0), _stream(y),
+                  nbytes=3 * y.numel() * y.element_size(), tag="box3_act_bwd")
+        # ds = sum_p dy * a with a = y / s (a style that is exactly zero gives no gradient here; measure zero)
+        ds = None if red is None else torch.where(s != 0, red / s, torch.zeros_like(red))
+        return dx, ds, None, None
+
+
 class Up2BoxAdd(torch.autograd.Function):
     """out = box3(nearest_up2(s)) + t   (custom_layers.py:146-147,159)."""
 
@@ -843,11 +889,15 @@ class ModConvAct(torch.autograd.Function):
     First order only (the generator is never on the R1 path)."""
 
     @staticmethod
-    def forward(ctx, x, s, w, bias, d, noise, wscale, plan, slope, gain, bias_scale, out_dtype, out_nchw):
+    def forward(ctx, x, s, w, bias, d, noise, wscale, plan, slope, gain, bias_scale, out_dtype, out_nchw,
+                premodulated=False):
+        """premodulated: x already IS x*s (its producer folded the style in - Box3ActMod); s is then ignored here
+        and gets its gradient from that producer."""
         _need_cuda(x, s, w)
         assert _is_cl(x) and s.is_contiguous() and d.is_contiguous() and s.dtype == d.dtype == torch.float32
         compute = torch.float32 if x.dtype == torch.float32 else torch.bfloat16
-        xs = _modulate_raw(x, s)
+        ctx.premod = bool(premodulated)
+        xs = x if premodulated else _modulate_raw(x, s)
         w2 = pack_weight(w, False, compute)
         y = _alloc_out(x.shape[0], w2.shape[0], plan.OH, plan.OW, out_dtype, x.device, out_nchw)
         up2f = None
@@ -876,26 +926,36 @@ class ModConvAct(torch.autograd.Function):
             # d noise[h,w] = sum_{b,o} dz, dz = g / d[b,o]: a torch reduction, only on noise-enabled layers
             # (cnn.py never enables them; custom_layers.py:98-101 keeps the option)
             dnz = (g.float() / d[:, :, None, None]).sum(dim=(0, 1))
-        if need_x or need_s:
-            t = empty_cl(x.shape[0], x.shape[1], x.shape[2], x.shape[3], x.dtype, x.device)
-            tapconv(g, pack_weight(w, True, compute), t, plans.adjoint(plan), acc_scale=wscale)
-            dx = torch.empty_like(x)
-            ds = torch.zeros_like(s)
-            n, c, h, wd = x.shape
-            _lib.call("lcgan_modulate_bwd", _ptr(x), _ptr(t), _ptr(s), _ptr(dx), _ptr(ds), _dt(x), n, h * wd, c,
-                      _stream(x), nbytes=3 * x.numel() * x.element_size())
-            del t
-        if need_w and _wgrad_enabled():
-            xs = _modulate_raw(x, s)
-            dw2 = tapconv_wgrad(xs, g, plan, x.shape[1], w.shape[0], scale=wscale)
-            dw = unpack_wgrad(dw2, tuple(w.shape), False).contiguous()
-            del xs
+        if ctx.premod:
+            # x is the modulated activation itself: the data gradient w.r.t. it is the plain adjoint conv, the
+            # weight gradient reads it as is, and the style gradient belongs to the producer of x
+            if need_x:
+                dx = empty_cl(x.shape[0], x.shape[1], x.shape[2], x.shape[3], x.dtype, x.device)
+                tapconv(g, pack_weight(w, True, compute), dx, plans.adjoint(plan), acc_scale=wscale)
+            if need_w and _wgrad_enabled():
+                dw2 = tapconv_wgrad(x, g, plan, x.shape[1], w.shape[0], scale=wscale)
+                dw = unpack_wgrad(dw2, tuple(w.shape), False).contiguous()
+        else:
+            if need_x or need_s:
+                t = empty_cl(x.shape[0], x.shape[1], x.shape[2], x.shape[3], x.dtype, x.device)
+                tapconv(g, pack_weight(w, True, compute), t, plans.adjoint(plan), acc_scale=wscale)
+                dx = torch.empty_like(x)
+                ds = torch.zeros_like(s)
+                n, c, h, wd = x.shape
+                _lib.call("lcgan_modulate_bwd", _ptr(x), _ptr(t), _ptr(s), _ptr(dx), _ptr(ds), _dt(x), n, h * wd, c,
+                          _stream(x), nbytes=3 * x.numel() * x.element_size())
+                del t
+            if need_w and _wgrad_enabled():
+                xs = _modulate_raw(x, s)
+                dw2 = tapconv_wgrad(xs, g, plan, x.shape[1], w.shape[0], scale=wscale)
+                dw = unpack_wgrad(dw2, tuple(w.shape), False).contiguous()
+                del xs
         if need_b or need_d:
             # r1 = sum_p dz * z with z = d*acc + bias (+ noise): remove the additive terms to get sum_p dz * acc
             if need_d and ctx.has_noise:
                 r1 = r1 - (g.float() * ctx.noise[None, None]).sum(dim=(2, 3)) / d
             db, dd = _epilogue_grads(r0, r1, bias, d, bias_scale, need_b, need_d)
-        return dx, ds, dw, db, dd, dnz, None, None, None, None, None, None, None
+        return dx, ds, dw, db, dd, dnz, None, None, None, None, None, None, None, None
 
 
 class Demod(torch.autograd.Function):

@@ -57,20 +57,28 @@ class MaskRecorder:
         self.masks, self._handles, self._ops, self._orig = [], [], ops, None
         for m in modules:
             self._handles.append(m.register_forward_hook(lambda mod, inp, out: self.masks.append((out > 0).detach())))
+        self._orig_mod = None
         if box3act:
-            self._orig = ops.Box3Act.apply
+            self._orig, self._orig_mod = ops.Box3Act.apply, ops.Box3ActMod.apply
 
             def apply(*a):
                 out = self._orig(*a)
                 self.masks.append((out > 0).detach())
                 return out
-            ops.Box3Act.apply = apply
+
+            def apply_mod(x, s, *a):          # output = lrelu(box(x)) * gain * s: the mask is the sign of output / s
+                out = self._orig_mod(x, s, *a)
+                self.masks.append(((out.float() * s[:, :, None, None]) > 0).detach())
+                return out
+            ops.Box3Act.apply, ops.Box3ActMod.apply = apply, apply_mod
 
     def close(self):
         for h in self._handles:
             h.remove()
         if self._orig is not None:
             self._ops.Box3Act.apply = self._orig
+        if self._orig_mod is not None:
+            self._ops.Box3ActMod.apply = self._orig_mod
 
     def __enter__(self):
         return self
