@@ -56,6 +56,10 @@ typedef struct lcgan_tapconv {
                                       + noise[oy][ox] * noise_scale - the noise injection of
                                       custom_layers.py:108-110; NULL = none */
   float noise_scale;
+  const float* colscale;           /* optional f32 [N][Cin] (device): X[b,..,c] is multiplied by colscale[b,c] as it is
+                                      read - the style modulation of custom_layers.py:62-64 in the prologue.  Only the
+                                      pointwise thin kernels implement it (lcgan_tapconv_simt with Cin 32, 1x1,
+                                      Cout <= 4); every other path rejects a non-NULL value */
 } lcgan_tapconv;
 
 const char* lcgan_last_error(void);
@@ -94,6 +98,11 @@ int lcgan_tapconv_simt(const lcgan_tapconv* d, const void* x, const void* w2, vo
  * (bf16 channels-last X, bf16 W2, Cin % 64 == 0).  Y may be bf16 or f32 channels-last. */
 int lcgan_tapconv_tc(const lcgan_tapconv* d, const void* x, const void* w2, void* y,
                      const float* rowscale, const float* bias, const void* residual, void* stream);
+
+/* Per-image weight gradient of a pointwise (1x1) layer with 32 input channels and Cout <= 4 (the to-RGB conv,
+ * cnn.py:87): dwp[b][o][c] += sum_p G[b,p,o] * X[b,p,c], f32 [N][Cout][32], caller-zeroed.  With the unmodulated X
+ * this one pass yields both gradients of the modulated layer: dW = sum_b s[b,c] dwp[b], ds[b,c] = sum_o w[o,c] dwp[b]. */
+int lcgan_pw_wgrad32(const lcgan_tapconv* d, const void* x, const void* g, float* dwp, void* stream);
 
 /* Weight gradient of the same contraction (autograd of custom_layers.py:41,43,78,83,25):
  *   dW2[o][wtap[t]*Cin + c] += scale * sum_{b,m,n} G[b, m*os+py, n*os+px, o] * X[b, m*is+dy[t], n*is+dx[t], c]
@@ -147,6 +156,11 @@ int lcgan_modulate_bwd(const void* x, const void* t, const float* s, void* dx, f
  * (pre-tanh). */
 int lcgan_warp_fwd(const void* x, const float* flow, void* out, int dt, int N, int H, int W, int C,
                    float flow_scale, void* stream);
+/* the same with out = warp(x) * cs[b,c] (cs [N,C] f32): the style modulation of the to-RGB conv that consumes the
+ * warped features (custom_layers.py:62-64), folded into the warp pass.  Tiled shapes only (W >= 32, H >= 16,
+ * C % 32 == 0 for bf16 / 16 for f32). */
+int lcgan_warp_fwd_cs(const void* x, const float* flow, void* out, const float* cs, int dt, int N, int H, int W,
+                      int C, float flow_scale, void* stream);
 /* dx_acc [N,H,W,C] f32 (caller-zeroed, atomically accumulated); dflow [N,H,W,2] f32 (written). */
 int lcgan_warp_bwd(const void* x, const float* flow, const void* dout, float* dx_acc, float* dflow,
                    int dt, int N, int H, int W, int C, float flow_scale, void* stream);

@@ -37,6 +37,7 @@ class TapConvDesc(C.Structure):
         ("w_ld", C.c_int64),
         ("acc_scale", C.c_float), ("bias_scale", C.c_float), ("slope", C.c_float), ("gain", C.c_float),
         ("noise", C.c_void_p), ("noise_scale", C.c_float),
+        ("colscale", C.c_void_p),
     ]
 
 
@@ -103,6 +104,7 @@ _SIGS = {
                                   _VOIDP], C.c_int),
     "lcgan_tapconv_simt": ([C.POINTER(TapConvDesc), _VOIDP, _VOIDP, _VOIDP, _FP, _FP, _VOIDP, _VOIDP], C.c_int),
     "lcgan_tapconv_tc": ([C.POINTER(TapConvDesc), _VOIDP, _VOIDP, _VOIDP, _FP, _FP, _VOIDP, _VOIDP], C.c_int),
+    "lcgan_pw_wgrad32": ([C.POINTER(TapConvDesc), _VOIDP, _VOIDP, _FP, _VOIDP], C.c_int),
     "lcgan_tapconv_wgrad_simt": ([C.POINTER(TapConvDesc), _VOIDP, _VOIDP, _FP, C.c_float, _VOIDP], C.c_int),
     "lcgan_tapconv_wgrad_tc": ([C.POINTER(TapConvDesc), _VOIDP, _VOIDP, _FP, C.c_float, _VOIDP], C.c_int),
     "lcgan_box3": ([_VOIDP, _VOIDP, _VOIDP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -117,6 +119,7 @@ _SIGS = {
     "lcgan_modulate": ([_VOIDP, _FP, _VOIDP, C.c_int, C.c_int, C.c_int, C.c_int, _VOIDP], C.c_int),
     "lcgan_modulate_bwd": ([_VOIDP, _VOIDP, _FP, _VOIDP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, _VOIDP], C.c_int),
     "lcgan_warp_fwd": ([_VOIDP, _FP, _VOIDP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _VOIDP], C.c_int),
+    "lcgan_warp_fwd_cs": ([_VOIDP, _FP, _VOIDP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _VOIDP], C.c_int),
     "lcgan_warp_bwd": ([_VOIDP, _FP, _VOIDP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                         C.c_float, _VOIDP], C.c_int),
     "lcgan_warp_bwd_tiled": ([_VOIDP, _FP, _VOIDP, _VOIDP, _FP, _FP, _VOIDP, C.c_int, C.c_int, C.c_int, C.c_int,

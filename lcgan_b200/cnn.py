@@ -118,6 +118,15 @@ class Generator(torch.nn.Module):
         g_codes = geometry_code.unsqueeze(1)
         a_codes = appearance_code.unsqueeze(1).expand(-1, 2, -1)
         x = self.const.unsqueeze(0).expand(batch_size, -1, -1, -1)
-        for block in self.model:
+        blocks = list(self.model)
+        for block in blocks[:-1]:
             x = block(x, g_codes, a_codes)
-        return self.rgb_layer(x, a_codes)
+        # the to-RGB block is the only reader of the last block's output: its first style is folded into that
+        # block's warp pass (x * s never makes a pass of its own over HBM)
+        last = blocks[-1]
+        res, c = last.resolution, self.rgb_layer.modulated_conv0.modulated_conv.in_features
+        style0 = None
+        if ops.fold_style_eligible(res, res, c, x.is_cuda):
+            style0 = self.rgb_layer.modulated_conv0.style(a_codes[:, 0])
+        x = last(x, g_codes, a_codes, out_style=style0)
+        return self.rgb_layer(x, a_codes, style0=style0)

@@ -253,6 +253,7 @@ extern "C" int lcgan_tapconv_simt(const lcgan_tapconv* d, const void* x, const v
     const int e = lcgan_thin_forward(*d, x, w2, y, rowscale, bias, residual, s);
     if (e >= 0) return e;
   }
+  LCGAN_CHECK(d->colscale == nullptr, "tapconv_simt: colscale is only implemented by the pointwise thin kernel");
   if (d->x_dtype == LCGAN_F32) return dispatch_w<float>(*d, x, w2, y, rowscale, bias, residual, s);
   return dispatch_w<bf16>(*d, x, w2, y, rowscale, bias, residual, s);
 }

@@ -1135,6 +1135,7 @@ static int tapconv_tc_launch(const lcgan_tapconv* d, const void* x, const void* 
                              int cperiod) {
   LCGAN_CHECK(tc_eligible(d, cblk == 4), "tapconv_tc: descriptor not eligible for the tensor-core path");
   LCGAN_CHECK(d->w_dtype == LCGAN_BF16, "tapconv_tc: weights must be bf16");
+  LCGAN_CHECK(d->colscale == nullptr, "tapconv_tc: colscale is only implemented by the pointwise thin kernel");
   LCGAN_CHECK(x && w2 && y, "tapconv_tc: null tensor pointer");
   LCGAN_CHECK(((uintptr_t)x % 16 == 0) && ((uintptr_t)w2 % 16 == 0) && ((uintptr_t)y % 16 == 0) &&
               (d->w_ld % 8 == 0), "tapconv_tc: operands must be 16-byte aligned");

@@ -637,6 +637,7 @@ pw_out32_kernel(const lcgan_tapconv d, const bf16* __restrict__ x, const void* _
   for (uint32_t r = blockIdx.x * kThreads + threadIdx.x; r < rows; r += gridDim.x * kThreads) {
     const uint32_t b = r / hw, p = r - b * hw, m = p / MW, n = p - m * MW;
     const uint4* xp = reinterpret_cast<const uint4*>(x + (int64_t)r * 32);     // dense channels-last: pixel r
+    const float4* cp = d.colscale ? reinterpret_cast<const float4*>(d.colscale + (int64_t)b * 32) : nullptr;
     float acc[CO];
 #pragma unroll
     for (int o = 0; o < CO; ++o) acc[o] = 0.f;
@@ -645,6 +646,13 @@ pw_out32_kernel(const lcgan_tapconv d, const bf16* __restrict__ x, const void* _
       const uint4 u = xp[v];
       float f[8];
       unpack_raw16<bf16>(u, f);
+      if (cp) {
+        // the modulated activation as the tensor-core path would have read it: x * s rounded to bf16
+        const float4 c0 = __ldg(cp + 2 * v), c1 = __ldg(cp + 2 * v + 1);
+        const float cs8[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = __bfloat162float(__float2bfloat16_rn(f[i] * cs8[i]));
+      }
 #pragma unroll
       for (int o = 0; o < CO; ++o)
 #pragma unroll
@@ -712,6 +720,53 @@ pw_in32_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const void* __re
   }
 }
 
+// per-image weight gradient of the pointwise 32 -> CO layer: dwp[b][o][c] += sum_p g[b,p,o] x[b,p,c]
+template <typename TG, int CO>
+__global__ void __launch_bounds__(kThreads)
+pw_wgrad32_kernel(const lcgan_tapconv d, const bf16* __restrict__ x, const TG* __restrict__ g, float* __restrict__ dwp) {
+  const int b = blockIdx.y;
+  const uint32_t hw = (uint32_t)d.MH * d.MW, MW = d.MW;
+  float acc[CO][32];
+#pragma unroll
+  for (int o = 0; o < CO; ++o)
+#pragma unroll
+    for (int c = 0; c < 32; ++c) acc[o][c] = 0.f;
+  for (uint32_t p = blockIdx.x * kThreads + threadIdx.x; p < hw; p += gridDim.x * kThreads) {
+    const uint32_t m = p / MW, n = p - m * MW;
+    const uint4* xp = reinterpret_cast<const uint4*>(x + ((int64_t)b * hw + p) * 32);
+    const TG* gp = g + (int64_t)b * d.ys_n + (int64_t)m * d.ys_h + (int64_t)n * d.ys_w;
+    float gv[CO];
+#pragma unroll
+    for (int o = 0; o < CO; ++o) gv[o] = o < d.Cout ? ldf(gp + o * d.ys_c) : 0.f;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      float f[8];
+      unpack_raw16<bf16>(xp[v], f);
+#pragma unroll
+      for (int o = 0; o < CO; ++o)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[o][v * 8 + i] = fmaf(gv[o], f[i], acc[o][v * 8 + i]);
+    }
+  }
+  // warp reduction, then the 8 warps of the block through shared memory, one atomic per element and block
+  __shared__ float red[kThreads / 32][CO * 32];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+#pragma unroll
+  for (int o = 0; o < CO; ++o)
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      const float t = warp_sum(acc[o][c]);
+      if (lane == c) red[warp][o * 32 + c] = t;
+    }
+  __syncthreads();
+  for (int e = threadIdx.x; e < d.Cout * 32; e += kThreads) {
+    float t = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < kThreads / 32; ++w8) t += red[w8][e];
+    atomicAdd(dwp + (int64_t)b * d.Cout * 32 + e, t);
+  }
+}
+
 // 1x1, unit strides, no offset
 static bool is_pointwise(const lcgan_tapconv& d) {
   return d.ntaps == 1 && d.dy[0] == 0 && d.dx[0] == 0 && d.is == 1 && d.os == 1 && d.py == 0 && d.px == 0 &&
@@ -760,6 +815,10 @@ int lcgan_thin_forward(const lcgan_tapconv& d, const void* x, const void* w, voi
       LCGAN_LAUNCH_CHECK();
       return 0;
     }
+  }
+  if (d.colscale) {
+    lcgan_set_error("tapconv: colscale is only implemented by the pointwise 32-channel thin kernel");
+    return 1;
   }
   if (rows * (d.Cin <= kMaxThin ? d.Cout : 1) >= (1LL << 31) - (1 << 20)) return -1;   // 32-bit indices below
   // ---- thin-out --------------------------------------------------------------------------
@@ -918,6 +977,24 @@ extern "C" int lcgan_tapconv_up2_thin_wgrad(const lcgan_tapconv* d, const void* 
   } while (0)
   if (xf && gf) UW(float, float); else if (xf) UW(float, bf16); else if (gf) UW(bf16, float); else UW(bf16, bf16);
 #undef UW
+  LCGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int lcgan_pw_wgrad32(const lcgan_tapconv* d, const void* x, const void* g, float* dwp, void* stream) {
+  LCGAN_CHECK(d && x && g && dwp, "pw_wgrad32: null argument");
+  LCGAN_CHECK(is_pointwise(*d) && d->Cin == 32 && d->Cout >= 1 && d->Cout <= kMaxThin && d->x_dtype == LCGAN_BF16 &&
+              (uintptr_t)x % 16 == 0 && d->xs_c == 1 && d->xs_w == 32 && (d->MH == 1 || d->xs_h == (int64_t)d->MW * 32) &&
+              (d->N == 1 || d->xs_n == (int64_t)d->MH * d->MW * 32) && d->N <= 65535,
+              "pw_wgrad32: needs a 1x1 layer, 32 dense channels-last bf16 input channels, Cout <= %d", kMaxThin);
+  const int64_t hw = (int64_t)d->MH * d->MW;
+  int gx = (int)((hw + kThreads * 16 - 1) / (kThreads * 16));       // >= 16 pixels per thread
+  const int cap = (148 * 4 + d->N - 1) / d->N;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (d->y_dtype == LCGAN_F32) pw_wgrad32_kernel<float, kMaxThin><<<dim3(gx, d->N), kThreads, 0, s>>>(*d, (const bf16*)x, (const float*)g, dwp);
+  else pw_wgrad32_kernel<bf16, kMaxThin><<<dim3(gx, d->N), kThreads, 0, s>>>(*d, (const bf16*)x, (const bf16*)g, dwp);
   LCGAN_LAUNCH_CHECK();
   return 0;
 }

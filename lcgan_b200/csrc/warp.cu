@@ -489,7 +489,10 @@ __device__ __forceinline__ void store_chunk(T* dst, const float* acc) {
 template <typename T, bool BWD>
 __global__ void __launch_bounds__(kTileThreads, 2)
 warp_tile_gather_kernel(const T* __restrict__ x, const float* __restrict__ flow, const T* __restrict__ g,
-                        T* __restrict__ out, float* __restrict__ dflow, int H, int W, int C, float scale) {
+                        T* __restrict__ out, float* __restrict__ dflow, int H, int W, int C, float scale,
+                        const float* __restrict__ cs = nullptr) {
+  // cs [N,C] (forward only, optional): out = warp(x) * cs[b,c] - the style of the modulated conv that consumes
+  // the warped features (the to-RGB block), folded into this pass
   constexpr int CC = 64 / sizeof(T);
   extern __shared__ __align__(16) unsigned char smem[];
   const int tiles_x = (W + kTW - 1) / kTW, tiles_y = (H + kTH - 1) / kTH;
@@ -586,7 +589,17 @@ warp_tile_gather_kernel(const T* __restrict__ x, const float* __restrict__ flow,
         dy0 = dy1; dy1 = dy2; dy2 = dy3;
       }
     }
-    if constexpr (!BWD) store_chunk<T>(out + pix * C + c0, acc);
+    if constexpr (!BWD) {
+      if (cs) {
+        const float4* cp = reinterpret_cast<const float4*>(cs + (int64_t)b * C + c0);
+#pragma unroll
+        for (int i = 0; i < CC / 4; ++i) {
+          const float4 c4 = __ldg(cp + i);
+          acc[4 * i] *= c4.x; acc[4 * i + 1] *= c4.y; acc[4 * i + 2] *= c4.z; acc[4 * i + 3] *= c4.w;
+        }
+      }
+      store_chunk<T>(out + pix * C + c0, acc);
+    }
   }
   if (BWD && live) {
     const float d0 = gix * (0.5f * (float)W) * scale * (1.f - pc.th0 * pc.th0);
@@ -803,6 +816,25 @@ extern "C" int lcgan_warp_fwd(const void* x, const float* flow, void* out, int d
   if (dt == LCGAN_F32) { if (C % 4 == 0) CALL(float, 4); else CALL(float, 1); }
   else { if (C % 8 == 0) CALL(bf16, 8); else CALL(bf16, 1); }
 #undef CALL
+  LCGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+// Forward warp with a per-(image, channel) output scale (tiled shapes only: W >= 32, H >= 16, C % 32 (bf16) / 16).
+extern "C" int lcgan_warp_fwd_cs(const void* x, const float* flow, void* out, const float* cs, int dt, int N, int H,
+                                 int W, int C, float flow_scale, void* stream) {
+  LCGAN_CHECK(x && flow && out && cs && N > 0 && H > 1 && W > 1 && C > 0, "warp_fwd_cs: bad arguments");
+  LCGAN_CHECK((dt == LCGAN_F32 || dt == LCGAN_BF16) && tile_eligible(dt, H, W, C) && C % 4 == 0,
+              "warp_fwd_cs: shape not eligible for the tiled kernel (use lcgan_warp_fwd + lcgan_modulate)");
+  LCGAN_CHECK(tile_kernels_ready() == 0, "warp_fwd_cs: cannot opt in to %d bytes of shared memory", kDxSmem);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int tiles = N * ((H + kTH - 1) / kTH) * ((W + kTW - 1) / kTW);
+  if (dt == LCGAN_BF16)
+    warp_tile_gather_kernel<bf16, false><<<tiles, kTileThreads, kFwdSmem, s>>>(
+        (const bf16*)x, flow, nullptr, (bf16*)out, nullptr, H, W, C, flow_scale, cs);
+  else
+    warp_tile_gather_kernel<float, false><<<tiles, kTileThreads, kFwdSmem, s>>>(
+        (const float*)x, flow, nullptr, (float*)out, nullptr, H, W, C, flow_scale, cs);
   LCGAN_LAUNCH_CHECK();
   return 0;
 }

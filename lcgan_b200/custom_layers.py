@@ -173,7 +173,10 @@ class SynthesisBlock(nn.Module):
     def box_filter(self, x):
         return ops.Box3.apply(x)
 
-    def forward(self, x, g_latent, a_latent):
+    def forward(self, x, g_latent, a_latent, out_style=None):
+        """out_style [b, out_features] (optional): the style of the ONE modulated conv that consumes this block's
+        output (the to-RGB block after the last synthesis block); it is then folded into the warp pass and the block
+        returns the modulated features."""
         g_lat = g_latent[:, 0]
         a_lat0, a_lat1 = a_latent[:, 0], a_latent[:, 1]
         x = _as_act(x)
@@ -190,6 +193,8 @@ class SynthesisBlock(nn.Module):
             t = ops.Box3Act.apply(t, 0.2, float(self.gain))                       # box -> lrelu * sqrt2
             t = self.modulated_conv1(t, a_lat1, slope=0.2)                        # conv -> lrelu
         y = ops.Up2BoxAdd.apply(skip_lo, t)                                       # box(up2(skip)) + t
+        if out_style is not None:
+            return ops.WarpMod.apply(y, flow, out_style, float(self.max_flow_scale))
         return ops.Warp.apply(y, flow, float(self.max_flow_scale))                # tanh + grid + bicubic
 
 
@@ -205,8 +210,9 @@ class ToRGBBlock(nn.Module):
         self.modulated_conv1 = SynthesisLayer(in_features, out_features, a_latent_dim, resolution, kernel_size=1,
                                               use_noise=False)
 
-    def forward(self, x, a_latent):
-        x = self.modulated_conv0(_as_act(x), a_latent[:, 0], slope=0.2)
+    def forward(self, x, a_latent, style0=None):
+        """style0: self.modulated_conv0.style(...) when x already carries it (SynthesisBlock(out_style=...))."""
+        x = self.modulated_conv0(_as_act(x), a_latent[:, 0], slope=0.2, style=style0)
         # the image leaves the generator as NCHW fp32, like the reference's
         return self.modulated_conv1(x, a_latent[:, 1], out_dtype=torch.float32, out_nchw=True)
 

@@ -298,7 +298,7 @@ def unpack_wgrad(dw2: torch.Tensor, wshape, transposed: bool) -> torch.Tensor:
 # raw launches
 # ------------------------------------------------------------------------------------------
 def _fill_desc(d: TapConvDesc, l: plans.Launch, x, y, cin, cout, w2, slope, gain, bias_scale, acc_scale=1.0,
-               noise=None):
+               noise=None, colscale=None):
     n = x.shape[0]
     d.N, d.IH, d.IW, d.Cin = n, x.shape[2], x.shape[3], cin
     d.OH, d.OW, d.Cout = y.shape[2], y.shape[3], cout
@@ -313,6 +313,7 @@ def _fill_desc(d: TapConvDesc, l: plans.Launch, x, y, cin, cout, w2, slope, gain
     d.w_ld = w2.shape[1] if w2 is not None else len(l.taps) * cin
     d.acc_scale, d.bias_scale, d.slope, d.gain = acc_scale, bias_scale, slope, gain
     d.noise, d.noise_scale = (noise.data_ptr(), 1.0) if noise is not None else (None, 0.0)
+    d.colscale = colscale.data_ptr() if colscale is not None else None
 
 
 _PROFILE_SHAPES = os.environ.get("LCGAN_PROFILE_SHAPES", "0") == "1"
@@ -400,7 +401,7 @@ def _tapconv_up2_fused(lib, d, x, w2, y, plan, rowscale, bias, slope, gain, bias
 
 
 def tapconv(x, w2, y, plan: plans.Plan, rowscale=None, bias=None, residual=None, slope=1.0, gain=1.0,
-            bias_scale=1.0, acc_scale=1.0, noise=None, up2f=None):
+            bias_scale=1.0, acc_scale=1.0, noise=None, up2f=None, colscale=None):
     """y = epilogue(tapconv(x, w2)) for every launch of the plan; x, y logical NCHW.  noise: optional
     contiguous f32 [OH, OW] plane added before the activation (custom_layers.py:108-110)."""
     _need_cuda(x, w2, y)
@@ -436,8 +437,9 @@ def tapconv(x, w2, y, plan: plans.Plan, rowscale=None, bias=None, residual=None,
                       nbytes=x.numel() * x.element_size() + y.numel() * y.element_size())
             return y
     for l in plan.launches:
-        _fill_desc(d, l, x, y, cin, cout, w2, slope, gain, bias_scale, acc_scale, noise)
-        fn = "lcgan_tapconv_tc" if (_USE_TC and lib.lcgan_tapconv_tc_eligible(C.byref(d))) else "lcgan_tapconv_simt"
+        _fill_desc(d, l, x, y, cin, cout, w2, slope, gain, bias_scale, acc_scale, noise, colscale)
+        fn = "lcgan_tapconv_tc" if (_USE_TC and colscale is None and lib.lcgan_tapconv_tc_eligible(C.byref(d))) \
+            else "lcgan_tapconv_simt"
         rows = x.shape[0] * l.MH * l.MW
         _lib.call(fn, C.byref(d), _ptr(x), _ptr(w2), _ptr(y), _ptr(rowscale), _ptr(bias), _ptr(residual), st,
                   tag=_shape_tag(fn, d),
@@ -755,6 +757,11 @@ def box3_mod_eligible(x) -> bool:
 _FOLD_STYLE = os.environ.get("LCGAN_NO_FOLD_STYLE", "0") != "1"
 
 
+def fold_style_eligible(h, w, c, is_cuda=True) -> bool:
+    """Shapes for which the tiled box / warp kernels can fold a style scale into their pass."""
+    return bool(is_cuda and _FOLD_STYLE and w >= 32 and h >= 16 and c % (32 if _ACT_DTYPE == torch.bfloat16 else 16) == 0)
+
+
 class Box3ActMod(torch.autograd.Function):
     """y = lrelu(box3(x), slope) * gain * s[b,c]: Box3Act with the style modulation of the FOLLOWING modulated
     conv (custom_layers.py:62-64, shared-weight form) folded into the same pass - the conv then reads y directly
@@ -897,14 +904,20 @@ class ModConvAct(torch.autograd.Function):
         assert _is_cl(x) and s.is_contiguous() and d.is_contiguous() and s.dtype == d.dtype == torch.float32
         compute = torch.float32 if x.dtype == torch.float32 else torch.bfloat16
         ctx.premod = bool(premodulated)
-        xs = x if premodulated else _modulate_raw(x, s)
+        # pointwise 32 -> (<= 4) layer (to-RGB 1x1 at 1024^2): the thin kernel multiplies by the style as it reads x,
+        # and one per-image weight-gradient pass yields dW and ds - no modulate / modulate_bwd passes at all
+        ctx.pwmod = bool(not premodulated and _FOLD_STYLE and plan.k == 1 and len(plan.launches) == 1
+                         and plan.launches[0].is_ == 1 and x.shape[1] == 32 and w.shape[0] <= 4
+                         and x.dtype == torch.bfloat16 and _is_cl_dense(x) and noise is None)
+        xs = x if (premodulated or ctx.pwmod) else _modulate_raw(x, s)
         w2 = pack_weight(w, False, compute)
         y = _alloc_out(x.shape[0], w2.shape[0], plan.OH, plan.OW, out_dtype, x.device, out_nchw)
         up2f = None
         if (w.shape[0] == 2 and len(plan.launches) == 4 and compute == torch.bfloat16 and _FLOW_TC and _USE_TC
                 and out_dtype == torch.float32 and not out_nchw):
             up2f = _derive(w, ("up2f", compute))
-        tapconv(xs, w2, y, plan, d, bias, None, slope, gain, bias_scale, wscale, noise, up2f)
+        tapconv(xs, w2, y, plan, d, bias, None, slope, gain, bias_scale, wscale, noise, up2f,
+                colscale=s if ctx.pwmod else None)
         del xs
         ctx.save_for_backward(x, s, w, bias, d, y)
         ctx.cfg = (wscale, plan, slope, gain, bias_scale)
@@ -926,7 +939,23 @@ class ModConvAct(torch.autograd.Function):
             # d noise[h,w] = sum_{b,o} dz, dz = g / d[b,o]: a torch reduction, only on noise-enabled layers
             # (cnn.py never enables them; custom_layers.py:98-101 keeps the option)
             dnz = (g.float() / d[:, :, None, None]).sum(dim=(0, 1))
-        if ctx.premod:
+        if ctx.pwmod:
+            if need_x:
+                dx = torch.empty_like(x)
+                tapconv(g, pack_weight(w, True, compute), dx, plans.adjoint(plan), rowscale=s, acc_scale=wscale)
+            if (need_w and _wgrad_enabled()) or need_s:
+                n, cin, cout = x.shape[0], x.shape[1], w.shape[0]
+                dwp = torch.zeros((n, cout, cin), dtype=torch.float32, device=x.device)
+                dsc = TapConvDesc()
+                _fill_desc(dsc, plan.launches[0], x, g, cin, cout, None, 1.0, 1.0, 1.0)
+                _lib.call("lcgan_pw_wgrad32", C.byref(dsc), _ptr(x), _ptr(g), _ptr(dwp), _stream(x), tag="pw_wgrad32",
+                          nbytes=x.numel() * x.element_size() + g.numel() * g.element_size())
+                if need_w and _wgrad_enabled():
+                    dw = ((dwp * s[:, None, :]).sum(0) * wscale).reshape(w.shape)
+                if need_s:
+                    wq = pack_weight(w, False, compute).float()
+                    ds = (dwp * wq[None]).sum(1) * wscale
+        elif ctx.premod:
             # x is the modulated activation itself: the data gradient w.r.t. it is the plain adjoint conv, the
             # weight gradient reads it as is, and the style gradient belongs to the producer of x
             if need_x:
@@ -1026,6 +1055,47 @@ class Warp(torch.autograd.Function):
                   _ptr(ws_bounds), _dt(x), n, h, w, c, C.c_float(ctx.scale), _stream(x), tag="warp_bwd",
                   nbytes=3 * x.numel() * x.element_size() + 2 * flow.numel() * 4)
         return dx, dflow, None
+
+
+class WarpMod(torch.autograd.Function):
+    """out = warp(x, flow) * s[b,c]: the flow warp with the style of the modulated conv that consumes its output
+    folded in (the to-RGB block reads the last synthesis block's output and nothing else does).  Backward: one
+    pass turns the incoming gradient t into dout = t * s and the style gradient ds = sum_p t * out / s, then the
+    plain warp backward runs on dout."""
+
+    @staticmethod
+    def forward(ctx, x, flow, s, scale):
+        _need_cuda(x, flow, s)
+        x = _cl(x)
+        flow = _cl(flow, torch.float32)
+        n, c, h, w = x.shape
+        assert s.dtype == torch.float32 and s.is_contiguous() and tuple(s.shape) == (n, c)
+        out = torch.empty_like(x)
+        _lib.call("lcgan_warp_fwd_cs", _ptr(x), _ptr(flow), _ptr(out), _ptr(s), _dt(x), n, h, w, c, C.c_float(scale),
+                  _stream(x), nbytes=2 * x.numel() * x.element_size() + flow.numel() * 4, tag="warp_fwd")
+        ctx.save_for_backward(x, flow, s, out)
+        ctx.scale = scale
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, t):
+        x, flow, s, out = ctx.saved_tensors
+        t = _cl(t, x.dtype)
+        n, c, h, w = x.shape
+        dout = torch.empty_like(x)
+        ds = torch.zeros_like(s)
+        _lib.call("lcgan_modulate_bwd", _ptr(out), _ptr(t), _ptr(s), _ptr(dout), _ptr(ds), _dt(x), n, h * w, c,
+                  _stream(x), nbytes=3 * x.numel() * x.element_size())
+        ds = torch.where(s != 0, ds / s, torch.zeros_like(ds))
+        dflow = torch.empty_like(flow)
+        dx = torch.empty_like(x)
+        ws_acc = None if x.dtype == torch.float32 else torch.empty(x.numel(), dtype=torch.float32, device=x.device)
+        ws_bounds = torch.empty(4 * n * ((h + 15) // 16) * ((w + 31) // 32) + 4, dtype=torch.int32, device=x.device)
+        _lib.call("lcgan_warp_bwd_tiled", _ptr(x), _ptr(flow), _ptr(dout), _ptr(dx), _ptr(dflow), _ptr(ws_acc),
+                  _ptr(ws_bounds), _dt(x), n, h, w, c, C.c_float(ctx.scale), _stream(x), tag="warp_bwd",
+                  nbytes=3 * x.numel() * x.element_size() + 2 * flow.numel() * 4)
+        return dx, dflow, ds, None
 
 
 # ------------------------------------------------------------------------------------------
