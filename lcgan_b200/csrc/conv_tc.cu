@@ -255,7 +255,25 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
       const uint32_t leader = elect_one();
       const uint32_t tx_bytes = p.rowshare ? (uint32_t)p.a_bytes + 3 * wtile : (kTileM + p.BN) * p.kc * 2;
       int g = 0;                                            // k-block counter across tiles
-      if (p.rowshare == 3) {
+      if (p.rowshare == 4) {
+        // x2 transposed conv, haloed: ONE (wt+1) x (ht+1) box of the input lattice per tile; the four taps
+        // (dy, dx in {0,1}) are descriptor offsets into it, the nine live (tap, phase) weight blocks stay resident
+        const uint32_t wblk = (uint32_t)p.cperiod * p.kc * 2;
+        mbar_expect_tx(s.wfull, 9 * wblk, leader);
+        int idx = 0;
+        for (int t = 0; t < 4; ++t)
+          for (int py = t >> 1; py < 2; ++py)
+            for (int px = t & 1; px < 2; ++px, ++idx)
+              tma_load_2d(s.wres + idx * wblk, &tmw, s.wfull, t * p.Cin, (py * 2 + px) * p.cperiod, leader);
+        const uint32_t box_bytes = (uint32_t)(p.wt + 1) * (p.ht + 1) * p.kc * 2;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++g) {
+          const int tw = tile & (p.tiles_w - 1), th = (tile >> p.lw) & (p.tiles_h - 1), tb = tile >> (p.lw + p.lh);
+          const int st = g % p.stages, ph = (g / p.stages) & 1;
+          mbar_wait(&s.empty[st], ph ^ 1);
+          mbar_expect_tx(&s.full[st], box_bytes, leader);
+          tma_load_4d(s.a(st), &tmx, &s.full[st], 0, tw * p.wt, th * p.ht, tb, leader);
+        }
+      } else if (p.rowshare == 3) {
         // haloed small-channel mode: resident weights, and ONE TMA box per tile - the (wt+2) x (ht+2) pixel
         // neighbourhood of the 8 x 16 lattice tile.  Tap (dy, dx) is read by the MMA straight out of that
         // box through its descriptor start offset (rows (dy*(wt+2) + dx) further on, SBO = one stored row of
@@ -330,7 +348,44 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
       const uint32_t leader = elect_one();
       const uint32_t idesc = make_idesc(p.BN, false, false);
       int g = 0, li = 0;
-      if (p.rowshare == 3) {
+      if (p.rowshare == 4) {
+        mbar_wait(s.wfull, 0);
+        const uint32_t row16 = (uint32_t)(p.kc * 2) >> 4, pitch = (uint32_t)(p.wt + 1) * row16;
+        const uint32_t w_tl = ((uint32_t)p.cperiod * p.kc * 2) >> 4;
+        const uint32_t idesc4 = make_idesc(p.cperiod, false, false);          // N = Cout per (tap, phase) block
+        const uint64_t bd0 = make_desc(smem_u32(s.wres), 16, 16 * p.kc, p.kc);
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li, ++g) {
+          if ((li & 1) != mine) continue;
+          const int as = li % kAccStages, aph = (li / kAccStages) & 1;
+          mbar_wait(&s.acc_empty[as], aph ^ 1);
+          const int st = g % p.stages, ph = (g / p.stages) & 1;
+          mbar_wait(&s.full[st], ph);
+          tc_fence_after();
+          const uint32_t tacc = tmem_base + (uint32_t)(as * kMaxBN);
+          const uint64_t ad0 = make_desc(smem_u32(s.a(st)), 16, (uint32_t)(p.wt + 1) * p.kc * 2, p.kc);
+          int idx = 0;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const uint64_t ad = ad0 + (uint32_t)((t >> 1) * pitch + (t & 1) * row16);
+#pragma unroll
+            for (int py = t >> 1; py < 2; ++py)
+#pragma unroll
+              for (int px = t & 1; px < 2; ++px, ++idx) {
+                const uint32_t tcol = tacc + (uint32_t)((py * 2 + px) * p.cperiod);
+                const uint64_t bd = bd0 + (uint32_t)(idx * w_tl);
+                // tap (0,0) reaches every phase first: it initialises the four accumulators
+                umma_f16(tcol, ad, bd, idesc4, t != 0, leader);
+                umma_f16(tcol, ad + 2, bd + 2, idesc4, 1, leader);
+                if (p.kc == 64) {
+                  umma_f16(tcol, ad + 4, bd + 4, idesc4, 1, leader);
+                  umma_f16(tcol, ad + 6, bd + 6, idesc4, 1, leader);
+                }
+              }
+          }
+          umma_commit(&s.empty[st], leader);
+          umma_commit(&s.done[as], leader);
+        }
+      } else if (p.rowshare == 3) {
         mbar_wait(s.wfull, 0);
         const uint32_t row16 = (uint32_t)(p.kc * 2) >> 4;               // one stored pixel, in 16-byte units
         const uint32_t pitch = (uint32_t)(p.wt + 2) * row16;              // one stored row of wt+2 pixels
@@ -455,14 +510,18 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
     const float asg = p.acc_scale * p.gain, bsg = p.bias_scale * p.gain;
     // one 16-column chunk per thread and tile (BN <= 32, a single channel tile): its bias and the current
     // image's row scales stay in registers
-    const bool cache = p.BN <= 32 && p.n_tiles == 1 && p.cblk == 0;
+    // (also the blocked x2 form with 16 / 32 real channels: a thread's chunks, 32 columns apart, all map to the
+    // same 16 channels)
+    const bool cache = p.n_tiles == 1 && ((p.cblk == 0 && p.BN <= 32) || (p.cblk >= 16 && (p.cperiod == 16 || p.cperiod == 32)));
+    const int co = p.cblk ? (half * 16) % p.cperiod : half * 16;       // first channel of this thread's chunks
+    const int crow_c = p.cblk ? p.cperiod : p.Cout;
     float csc[16], cbi[16];
     int cached_b = -1;
     if (cache) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const int o = half * 16 + i;
-        cbi[i] = (bias && o < p.Cout) ? bias[o] * bsg : 0.f;
+        const int o = co + i;
+        cbi[i] = (bias && o < crow_c) ? bias[o] * bsg : 0.f;
         csc[i] = asg;
       }
     }
@@ -480,10 +539,10 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
       const float nzg = (p.noise && live) ? p.noise[(long long)((m0 + mi) * p.os + p.py) * p.OW + (n0 + ni) * p.os + p.px] *
                                             p.noise_scale * p.gain : 0.f;
       if (cache && rowscale && live && b != cached_b) {
-        const float4* rs = reinterpret_cast<const float4*>(rowscale + (long long)b * p.Cout + half * 16);
+        const float4* rs = reinterpret_cast<const float4*>(rowscale + (long long)b * crow_c + co);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          if (half * 16 + 4 * i < p.Cout) {
+          if (co + 4 * i < crow_c) {
             const float4 sc = rs[i];
             csc[4 * i] = sc.x * asg; csc[4 * i + 1] = sc.y * asg; csc[4 * i + 2] = sc.z * asg; csc[4 * i + 3] = sc.w * asg;
           }
@@ -1174,7 +1233,23 @@ static int tapconv_tc_launch(const lcgan_tapconv* d, const void* x, const void* 
   p.wres_bytes = 0;
   int smem_bytes = fwd_smem_bytes();
   const int budget = 3 * (20 * 1024 + 3 * kBBytes);        // bytes available for the operand ring
-  if (full3x3 && (d->Cin == 32 || d->Cin == 64) && d->Cout <= kMaxBN && d->MW % 8 == 0 && d->MH % 16 == 0 &&
+  bool up2_taps = cblk > 4 && d->ntaps == 4 && d->is == 1 && d->os == 1;
+  for (int t = 0; up2_taps && t < 4; ++t) up2_taps = d->dy[t] == (t >> 1) && d->dx[t] == (t & 1) && d->wtap[t] == t;
+  if (up2_taps && (d->Cin == 32 || d->Cin == 64) && d->Cout <= kMaxBN && d->Cout == 4 * cperiod && cblk == 2 * cperiod &&
+      d->MW % 8 == 0 && d->MH % 16 == 0 && getenv("LCGAN_NO_UP2_HALO") == nullptr) {
+    // x2 transposed conv in the blocked form, haloed: 8 x 16 input-lattice tiles, one (8+1) x (16+1) box per tile,
+    // the 9 live (tap, phase) weight blocks resident, 4 phase accumulators of Cout columns each
+    p.rowshare = 4;
+    p.wt = 8; p.ht = 16; p.nt = 1;
+    p.tiles_w = d->MW / p.wt; p.tiles_h = d->MH / p.ht;
+    p.wres_bytes = (9 * cperiod * d->Cin * 2 + 1023) & ~1023;
+    p.a_bytes = ((p.wt + 1) * (p.ht + 1) * p.kc * 2 + 1023) & ~1023;
+    p.b_bytes = 0;
+    p.stages = (kMaxSmem - 2048 - p.wres_bytes) / p.a_bytes;
+    if (p.stages > 12) p.stages = 12;
+    p.stages &= ~1;
+    smem_bytes = 1024 + p.wres_bytes + p.stages * p.a_bytes + 256;
+  } else if (full3x3 && (d->Cin == 32 || d->Cin == 64) && d->Cout <= kMaxBN && d->MW % 8 == 0 && d->MH % 16 == 0 &&
       9 * p.BN * d->Cin * 2 <= 80 * 1024 && getenv("LCGAN_NO_HALO") == nullptr) {
     // haloed small-channel mode: 8-wide x 16-tall lattice tiles, ONE (8+2) x (16+2) pixel box per tile serves all
     // nine taps, weights resident; stage stride padded to the swizzle period
@@ -1217,9 +1292,9 @@ static int tapconv_tc_launch(const lcgan_tapconv* d, const void* x, const void* 
   for (p.lw = 0; (1 << p.lw) < p.tiles_w; ++p.lw) {}
   for (p.lh = 0; (1 << p.lh) < p.tiles_h; ++p.lh) {}
   CUtensorMap tmx, tmw;
-  if (int e = make_act_map(&tmx, x, d->N, d->IH, d->IW, d->Cin, p.wt, p.ht, p.nt, d->is, p.kc, p.rowshare ? 2 : 0,
-                           p.rowshare == 3 ? 2 : 0)) return e;
-  if (int e = make_w_map(&tmw, w2, d->Cout, d->w_ld, p.BN, p.kc)) return e;
+  if (int e = make_act_map(&tmx, x, d->N, d->IH, d->IW, d->Cin, p.wt, p.ht, p.nt, d->is, p.kc,
+                           p.rowshare == 4 ? 1 : (p.rowshare ? 2 : 0), p.rowshare == 4 ? 1 : (p.rowshare == 3 ? 2 : 0))) return e;
+  if (int e = make_w_map(&tmw, w2, d->Cout, d->w_ld, p.rowshare == 4 ? cperiod : p.BN, p.kc)) return e;
 
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;

@@ -369,6 +369,12 @@ def fused_up2_weights(w2: torch.Tensor, cin: int) -> torch.Tensor:
 
 
 _FLOW_TC = os.environ.get("LCGAN_NO_FLOW_TC", "0") != "1"
+_UP2_HALO = os.environ.get("LCGAN_NO_UP2_HALO", "0") != "1"
+
+
+def up2_halo_eligible(cin, cout, h, w) -> bool:
+    """x2 transposed convs the haloed single-launch tensor-core form takes (conv_tc.cu, rowshare 4)."""
+    return bool(_UP2_HALO and cin in (32, 64) and cout % 16 == 0 and cout <= 32 and h % 16 == 0 and w % 8 == 0)
 
 
 def _tapconv_up2_fused(lib, d, x, w2, y, plan, rowscale, bias, slope, gain, bias_scale, acc_scale, st, wf=None):
@@ -416,10 +422,13 @@ def tapconv(x, w2, y, plan: plans.Plan, rowscale=None, bias=None, residual=None,
     lib = _lib.lib()
     st = _stream(x)
     d = TapConvDesc()
-    if (_UP2_FUSED and _USE_TC and len(plan.launches) == 4 and plan.launches[0].os == 2 and residual is None
-            and noise is None and cout % 16 == 0 and cin % 32 == 0 and cin <= _UP2_FUSED_MAX_CIN and x.dtype == torch.bfloat16
-            and w2.dtype == torch.bfloat16 and _is_cl_dense(x) and _is_cl_dense(y)):
-        _tapconv_up2_fused(lib, d, x, w2, y, plan, rowscale, bias, slope, gain, bias_scale, acc_scale, st)
+    if (_USE_TC and len(plan.launches) == 4 and plan.launches[0].os == 2 and residual is None
+            and noise is None and cout % 16 == 0 and cin % 32 == 0 and x.dtype == torch.bfloat16
+            and w2.dtype == torch.bfloat16 and _is_cl_dense(x) and _is_cl_dense(y)
+            and ((_UP2_FUSED and cin <= _UP2_FUSED_MAX_CIN) or up2_halo_eligible(cin, cout, plan.IH, plan.IW))):
+        # one launch over the input lattice; with 32 / 64 input channels the haloed form (one box per tile, resident
+        # weights, no zero blocks)
+        _tapconv_up2_fused(lib, d, x, w2, y, plan, rowscale, bias, slope, gain, bias_scale, acc_scale, st, wf=up2f)
         return y
     if (up2f is not None and _USE_TC and _FLOW_TC and cout == 2 and len(plan.launches) == 4 and plan.launches[0].os == 2
             and residual is None and noise is None and cin % 32 == 0 and x.dtype == torch.bfloat16
@@ -612,9 +621,12 @@ class ConvAct(torch.autograd.Function):
         wg = _wgrad_enabled()
         need_w, need_b = need_w and wg, need_b and wg
         dres = dy if (has_res and need_res) else None
-        trivial = slope == 1.0 and gain == 1.0 and rowscale is None
+        # no activation, no row scale, no bias gradient (the 1x1 skip convs): the epilogue was y = acc * gain, so the
+        # gain moves into the scale of the data- and weight-gradient kernels and no pass over dy is needed at all
+        trivial = slope == 1.0 and rowscale is None
         if trivial and not need_b:
             g, r0, r1 = dy, None, None
+            wscale = wscale * gain
         else:
             ycl = y if _is_cl(y) else _cl(y)
             if has_res:
@@ -913,8 +925,9 @@ class ModConvAct(torch.autograd.Function):
         w2 = pack_weight(w, False, compute)
         y = _alloc_out(x.shape[0], w2.shape[0], plan.OH, plan.OW, out_dtype, x.device, out_nchw)
         up2f = None
-        if (w.shape[0] == 2 and len(plan.launches) == 4 and compute == torch.bfloat16 and _FLOW_TC and _USE_TC
-                and out_dtype == torch.float32 and not out_nchw):
+        if len(plan.launches) == 4 and compute == torch.bfloat16 and _USE_TC and not out_nchw and (
+                (w.shape[0] == 2 and _FLOW_TC and out_dtype == torch.float32)
+                or up2_halo_eligible(x.shape[1], w.shape[0], plan.IH, plan.IW)):
             up2f = _derive(w, ("up2f", compute))
         tapconv(xs, w2, y, plan, d, bias, None, slope, gain, bias_scale, wscale, noise, up2f,
                 colscale=s if ctx.pwmod else None)

@@ -28,6 +28,12 @@ for w in which:
         else:
             ms = timeit(lambda: ops.tapconv_wgrad(x, g, plan, C, C))
         print(f"{w:8s} {ms:8.3f} ms  {flops/ms/1e9:8.1f} TF/s  {nbytes/ms/1e6:8.0f} GB/s (algorithmic)")
+    elif w == "up64":
+        x = cl(torch.randn(N, 64, 512, 512, device=dev).bfloat16()); wp = torch.nn.Parameter(torch.randn(32, 64, 3, 3, device=dev))
+        w2 = ops.pack_weight(wp, False, torch.bfloat16); wf = ops._derive(wp, ("up2f", torch.bfloat16)); plan = plans.conv_transpose_up2(3, 512, 512)
+        y = ops.empty_cl(N, 32, 1024, 1024, torch.bfloat16, dev); bias = torch.randn(32, device=dev); rs = torch.rand(N, 32, device=dev)
+        ms = timeit(lambda: ops.tapconv(x, w2, y, plan, rs, bias, None, up2f=wf)); tr = x.numel() * 2 + y.numel() * 2
+        print(f"{w:8s} {ms:8.3f} ms  {tr/ms/1e6:8.0f} GB/s (algorithmic)")
     elif w in ("rgbout", "rgbin"):
         R = 1024
         if w == "rgbout":

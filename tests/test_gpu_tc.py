@@ -22,6 +22,7 @@ def _setup():
     ops.set_wgrad_tensor_cores(True)
     ops.set_up2_fused(False)
     ops._UP2_FUSED_MAX_CIN = 64
+    ops._UP2_HALO = True
 
 
 def _cl(x):
@@ -105,6 +106,8 @@ def test_tc_wgrad_matches_simt(case):
 
 @pytest.mark.parametrize("case", [  # N, Cin, Cout, H, W
     (2, 64, 32, 16, 16), (1, 128, 64, 8, 16), (3, 32, 16, 16, 8), (2, 64, 32, 64, 64), (5, 32, 32, 4, 4),
+    # haloed form (Cin 32 / 64, Cout <= 32, H % 16 == 0, W % 8 == 0): many tiles, many images, non-square
+    (3, 64, 32, 128, 64), (33, 32, 16, 16, 8), (2, 64, 16, 32, 32),
 ])
 @pytest.mark.parametrize("out_f32", [False, True])
 def test_fused_up2_matches_four_phase_path(case, out_f32):
@@ -121,6 +124,7 @@ def test_fused_up2_matches_four_phase_path(case, out_f32):
     outs = []
     for fused in (False, True):
         ops.set_up2_fused(fused)
+        ops._UP2_HALO = fused                 # the four-phase reference path must not take the haloed form either
         ops._UP2_FUSED_MAX_CIN = 128          # exercise the two-n-tile case as well
         before = _lib.launches
         y = ops.empty_cl(N, Cout, 2 * H, 2 * W, dt, "cuda").fill_(float("nan"))
