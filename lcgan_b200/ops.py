@@ -625,7 +625,7 @@ class ConvAct(torch.autograd.Function):
         # gain moves into the scale of the data- and weight-gradient kernels and no pass over dy is needed at all
         trivial = slope == 1.0 and rowscale is None
         if trivial and not need_b:
-            g, r0, r1 = dy, None, None
+            g, r0, r1 = (dy if (dy.dtype == y.dtype and _is_cl(dy)) else _cl(dy, y.dtype)), None, None
             wscale = wscale * gain
         else:
             ycl = y if _is_cl(y) else _cl(y)
