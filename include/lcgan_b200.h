@@ -122,6 +122,12 @@ int lcgan_tapconv_wgrad_tc(const lcgan_tapconv* d, const void* x, const void* g,
 int lcgan_box3(const void* a, const void* mask, void* out, int dt, int N, int H, int W, int C,
                float pre_slope, float pre_gain, float post_slope, float post_gain, void* stream);
 
+/* out = box3(a) * (y > 0 ? gain : gain*slope);  r0[b,c] += sum_p out (f32 [N,C], caller-zeroed, may be NULL):
+ * the backward of F.avg_pool2d(3,1,1) (custom_layers.py:197) fused with the backward of the leaky-relu*gain of the conv
+ * in front of it (:205), whose stored output is y.  Tile shapes only (C % 32 (bf16) / 16 (f32), W >= 32, H >= 16). */
+int lcgan_box3_postmask(const void* a, const void* y, void* out, float* r0, int dt, int N, int H, int W, int C,
+                        float slope, float gain, void* stream);
+
 /* lcgan_box3 with the NEXT layer's style modulation (custom_layers.py:62-64) folded in; cs [N,C] f32:
  *   mask == NULL:  out = post(box3(a)) * cs[b,c]
  *   mask != NULL:  out = box3(a * cs[b,c] * (mask*cs > 0 ? pre_gain : pre_gain*pre_slope)),

@@ -109,6 +109,8 @@ _SIGS = {
     "lcgan_tapconv_wgrad_tc": ([C.POINTER(TapConvDesc), _VOIDP, _VOIDP, _FP, C.c_float, _VOIDP], C.c_int),
     "lcgan_box3": ([_VOIDP, _VOIDP, _VOIDP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                     C.c_float, C.c_float, C.c_float, C.c_float, _VOIDP], C.c_int),
+    "lcgan_box3_postmask": ([_VOIDP, _VOIDP, _VOIDP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                             C.c_float, C.c_float, _VOIDP], C.c_int),
     "lcgan_box3_cs": ([_VOIDP, _VOIDP, _VOIDP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                        C.c_float, C.c_float, C.c_float, C.c_float, _VOIDP], C.c_int),
     "lcgan_pool2": ([_VOIDP, _VOIDP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _VOIDP], C.c_int),

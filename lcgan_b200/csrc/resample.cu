@@ -152,7 +152,11 @@ template <typename T, bool MASK, int TH>
 __global__ void __launch_bounds__(kThreads)
 box3_tile_kernel(const T* __restrict__ a, const T* __restrict__ mask, T* __restrict__ out, int H, int W, int C,
                  float pre_slope, float pre_gain, float post_slope, float post_gain,
-                 const float* __restrict__ cs = nullptr, float* __restrict__ red = nullptr) {
+                 const float* __restrict__ cs = nullptr, float* __restrict__ red = nullptr,
+                 const T* __restrict__ post_mask = nullptr) {
+  // post_mask (MASK == false only): out = box3(a) * (post_mask > 0 ? post_gain : post_gain * post_slope) - the box
+  // filter's backward followed by the backward of the leaky-relu of the conv BEFORE it (y = post_mask), one pass;
+  // red[b,c] += sum_p out then is that conv's bias gradient
   // cs [N,C] (optional): per-(image, channel) scale - the style modulation of the NEXT layer folded into this
   // pass: forward out = post(box3(a)) * cs; backward (MASK) pre(a) = a * cs * lrelu'(mask * cs), and
   // red[b,c] += sum over the tile's own pixels of a * mask (the style gradient, divided by cs on the host)
@@ -181,7 +185,7 @@ box3_tile_kernel(const T* __restrict__ a, const T* __restrict__ mask, T* __restr
 #pragma unroll
   for (int i = 0; i < E; ++i) { csv[i] = cs ? cs[(int64_t)b * C + c0 + v * E + i] : 1.f; racc[i] = 0.f; }
   const bool col_live = ox < W;
-  if (!col_live && !(MASK && red)) return;                  // (with a reduction every thread reaches the barrier below)
+  if (!col_live && !red) return;                            // (with a reduction every thread reaches the barrier below)
   const float neg = pre_gain * pre_slope;
   float h0[E], h1[E], h2[E];
 #pragma unroll
@@ -212,11 +216,24 @@ box3_tile_kernel(const T* __restrict__ a, const T* __restrict__ mask, T* __restr
       const int oy = ty * TH + strip * SR + rr - 2;
       if (oy < H && col_live) {
         float o[E];
+        const int64_t oidx = (((int64_t)b * H + oy) * W + ox) * C + c0 + v * E;
+        if (!MASK && post_mask) {
+          Vec16<T> m;
+          float mf[E];
+          m.load(post_mask + oidx);
+          m.unpack(mf);
 #pragma unroll
-        for (int i = 0; i < E; ++i) {
-          const float sv = (h0[i] + h1[i] + h2[i]) * (1.f / 9.f);
-          o[i] = (sv > 0.f ? sv : sv * post_slope) * post_gain;
-          if constexpr (!MASK) o[i] *= csv[i];
+          for (int i = 0; i < E; ++i) {
+            o[i] = (h0[i] + h1[i] + h2[i]) * (1.f / 9.f) * (mf[i] > 0.f ? post_gain : post_gain * post_slope);
+            racc[i] += o[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < E; ++i) {
+            const float sv = (h0[i] + h1[i] + h2[i]) * (1.f / 9.f);
+            o[i] = (sv > 0.f ? sv : sv * post_slope) * post_gain;
+            if constexpr (!MASK) o[i] *= csv[i];
+          }
         }
         Vec16<T> w;
         w.pack(o);
@@ -224,7 +241,7 @@ box3_tile_kernel(const T* __restrict__ a, const T* __restrict__ mask, T* __restr
       }
     }
   }
-  if constexpr (MASK) {
+  {
     if (red) {
       // rows of the window beyond the image contribute zeros (zero-filled window), columns beyond it were skipped;
       // sum the 64 threads (32 columns x 2 strips) that share a channel vector, one atomic per channel and CTA
@@ -602,6 +619,26 @@ extern "C" int lcgan_box3(const void* a, const void* mask, void* out, int dt, in
     DISPATCH_TV(dt, C, CALL);
 #undef CALL
   }
+  LCGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+// out = box3(a) * lrelu'(y) * gain and r0[b,c] += sum_p out: the backward of "conv -> lrelu*gain -> box filter" from the
+// gradient of the box filter's output to the gradient of the conv's pre-activation, in one pass.  Tile shapes only.
+extern "C" int lcgan_box3_postmask(const void* a, const void* y, void* out, float* r0, int dt, int N, int H, int W,
+                                   int C, float slope, float gain, void* stream) {
+  LCGAN_CHECK(a && y && out && N > 0 && H > 0 && W > 0 && C > 0, "box3_postmask: bad arguments");
+  const int cc = dt == LCGAN_BF16 ? 32 : 16;
+  LCGAN_CHECK((dt == LCGAN_BF16 || dt == LCGAN_F32) && C % cc == 0 && W >= kBoxTW && H >= kBoxTH,
+              "box3_postmask: needs C %% %d == 0, W >= %d, H >= %d (use lcgan_box3 + lcgan_act_bwd otherwise)", cc, kBoxTW, kBoxTH);
+  cudaStream_t s = (cudaStream_t)stream;
+  const dim3 grid(N * ((H + kBoxTH - 1) / kBoxTH) * ((W + kBoxTW - 1) / kBoxTW) * (C / cc));
+  if (dt == LCGAN_BF16)
+    box3_tile_kernel<bf16, false, 16><<<grid, kThreads, 0, s>>>((const bf16*)a, nullptr, (bf16*)out, H, W, C, 1.f, 1.f, slope,
+                                                               gain, nullptr, r0, (const bf16*)y);
+  else
+    box3_tile_kernel<float, false, 16><<<grid, kThreads, 0, s>>>((const float*)a, nullptr, (float*)out, H, W, C, 1.f, 1.f,
+                                                                slope, gain, nullptr, r0, (const float*)y);
   LCGAN_LAUNCH_CHECK();
   return 0;
 }

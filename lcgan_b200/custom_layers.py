@@ -68,9 +68,14 @@ class EqualizedConv2d(nn.Module):
         self.stride = stride
         self.lr_mul = lr_mul
 
-    def forward(self, x, slope=1.0, gain=1.0, residual=None):
-        """slope/gain/residual: fused epilogue  lrelu(conv + bias, slope)*gain + residual."""
+    def forward(self, x, slope=1.0, gain=1.0, residual=None, box=False):
+        """slope/gain/residual: fused epilogue  lrelu(conv + bias, slope)*gain + residual.  box: follow with the 3x3
+        box filter inside the same autograd node (DiscriminatorBlock: conv0 -> lrelu -> box_filter)."""
         plan = plans.conv(self.kernel_size, self.stride, x.shape[2], x.shape[3])
+        if box:
+            assert residual is None and not self.no_bias
+            return ops.ConvActBox.apply(x, self.weight.weight, self.bias, float(self.weight.c), plan, slope, gain,
+                                        float(self.lr_mul))
         return ops.conv_act(x, self.weight.weight, None if self.no_bias else self.bias, None, residual,
                             wscale=float(self.weight.c), plan=plan, slope=slope, gain=gain,
                             bias_scale=float(self.lr_mul))
@@ -236,8 +241,7 @@ class DiscriminatorBlock(nn.Module):
     def forward(self, x):
         x = _as_act(x)
         if self.skip:
-            t = self.conv0(x, slope=0.2, gain=float(self.gain))
-            t = ops.Box3.apply(t)
+            t = self.conv0(x, slope=0.2, gain=float(self.gain), box=True)      # conv -> lrelu * sqrt2 -> box filter
             t = self.conv1(t, slope=0.2)
             pooled = ops.Pool2.apply(x, 0.25)
             # skip*sqrt(.5) + t, with the add fused into the (activation-free) skip conv epilogue

@@ -654,6 +654,101 @@ def _epilogue_grads(r0, r1, bias, d, bias_scale, want_db, want_dd):
     return db, dd
 
 
+class BoxMask(torch.autograd.Function):
+    """g = box3(dt) * lrelu'(y) * gain, r0 = sum_p g: from the gradient of a box filter's OUTPUT to the gradient of
+    the pre-activation of the conv in front of it (y = that conv's stored output), one pass instead of Box3 + ActBwd.
+    Linear in dt; its adjoint is MaskBox, so R1's create_graph pass builds a graph of our kernels again."""
+
+    @staticmethod
+    def forward(ctx, dt, y, slope, gain, want_r0):
+        _need_cuda(dt, y)
+        assert _is_cl(y)
+        dt = _cl(dt, y.dtype)
+        n, c, h, w = y.shape
+        r0 = torch.zeros((n, c), dtype=torch.float32, device=y.device) if want_r0 else None
+        if box3_mod_eligible(y):
+            g = torch.empty_like(y)
+            _lib.call("lcgan_box3_postmask", _ptr(dt), _ptr(y), _ptr(g), _ptr(r0), _dt(y), n, h, w, c,
+                      C.c_float(slope), C.c_float(gain), _stream(y), nbytes=3 * y.numel() * y.element_size(),
+                      tag="box3_act_bwd")
+        else:                                   # small maps: the two separate kernels
+            tmp = torch.empty_like(y)
+            _lib.call("lcgan_box3", _ptr(dt), None, _ptr(tmp), _dt(y), n, h, w, c, C.c_float(1.0), C.c_float(1.0),
+                      C.c_float(1.0), C.c_float(1.0), _stream(y), nbytes=2 * y.numel() * y.element_size())
+            g = torch.empty_like(y)
+            _lib.call("lcgan_act_bwd", _ptr(tmp), _ptr(y), _ptr(g), None, _ptr(r0), None, _dt(y), n, h * w, c,
+                      C.c_float(slope), C.c_float(gain), _stream(y), nbytes=3 * y.numel() * y.element_size())
+        ctx.save_for_backward(y)
+        ctx.cfg = (slope, gain)
+        outs = (g, r0 if want_r0 else _placeholder(y.device))
+        ctx.mark_non_differentiable(outs[1])
+        return outs
+
+    @staticmethod
+    def backward(ctx, gg, _g0):
+        (y,) = ctx.saved_tensors
+        return MaskBox.apply(gg, y, *ctx.cfg), None, None, None, None
+
+
+class MaskBox(torch.autograd.Function):
+    """h = box3(gg * lrelu'(y) * gain): the adjoint of BoxMask (the box filter is self-adjoint)."""
+
+    @staticmethod
+    def forward(ctx, gg, y, slope, gain):
+        _need_cuda(gg, y)
+        gg = _cl(gg, y.dtype)
+        n, c, h, w = y.shape
+        out = torch.empty_like(y)
+        _lib.call("lcgan_box3", _ptr(gg), _ptr(y), _ptr(out), _dt(y), n, h, w, c, C.c_float(slope), C.c_float(gain),
+                  C.c_float(1.0), C.c_float(1.0), _stream(y), nbytes=3 * y.numel() * y.element_size(), tag="box3_act_bwd")
+        ctx.save_for_backward(y)
+        ctx.cfg = (slope, gain)
+        return out
+
+    @staticmethod
+    def backward(ctx, hgrad):
+        (y,) = ctx.saved_tensors
+        return BoxMask.apply(hgrad, y, ctx.cfg[0], ctx.cfg[1], False)[0], None, None, None
+
+
+class ConvActBox(torch.autograd.Function):
+    """t = box3(lrelu(tapconv(x, w*wscale) + bias*bias_scale, slope) * gain): the first conv of a discriminator block
+    with the box filter that follows it (custom_layers.py:204-206) as ONE autograd node, so that backward can run the
+    box filter's and the activation's backward as one pass (BoxMask).  Twice differentiable like ConvAct."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, wscale, plan, slope, gain, bias_scale):
+        compute = torch.float32 if x.dtype == torch.float32 else torch.bfloat16
+        w2 = pack_weight(w, False, compute)
+        y = _alloc_out(x.shape[0], w2.shape[0], plan.OH, plan.OW, _ACT_DTYPE, x.device, False)
+        tapconv(x, w2, y, plan, None, bias, None, slope, gain, bias_scale, wscale)
+        n, c, h, wd = y.shape
+        t = torch.empty_like(y)
+        _lib.call("lcgan_box3", _ptr(y), None, _ptr(t), _dt(y), n, h, wd, c, C.c_float(1.0), C.c_float(1.0),
+                  C.c_float(1.0), C.c_float(1.0), _stream(y), nbytes=2 * y.numel() * y.element_size())
+        ctx.save_for_backward(x, w, bias, y)
+        ctx.cfg = (wscale, plan, slope, gain, bias_scale)
+        ctx.x_fmt = (x.dtype, x.is_contiguous() and not _is_cl(x))
+        return t
+
+    @staticmethod
+    def backward(ctx, dt):
+        x, w, bias, y = ctx.saved_tensors
+        wscale, plan, slope, gain, bias_scale = ctx.cfg
+        need_x, need_w, need_b = ctx.needs_input_grad[:3]
+        wg = _wgrad_enabled()
+        need_w, need_b = need_w and wg, need_b and wg
+        g, r0 = BoxMask.apply(dt, y, slope, gain, bool(need_b))
+        dx = dw = db = None
+        if need_x:
+            dx = ConvFwd.apply(g, w, wscale, plans.adjoint(plan), True, *ctx.x_fmt)
+        if need_w:
+            dw = ConvWgrad.apply(x, g, plan, False, tuple(w.shape), wscale)
+        if need_b:
+            db, _ = _epilogue_grads(r0, None, bias, None, bias_scale, True, False)
+        return dx, dw, db, None, None, None, None, None
+
+
 def conv_act(x, w, bias=None, rowscale=None, residual=None, *, wscale=1.0, plan, slope=1.0, gain=1.0,
              bias_scale=1.0, out_dtype=None, out_nchw=False):
     return ConvAct.apply(x, w, bias, rowscale, residual, wscale, plan, slope, gain, bias_scale,
@@ -763,15 +858,21 @@ class Box3Act(torch.autograd.Function):
 def box3_mod_eligible(x) -> bool:
     """Shapes the tiled box kernel with a folded style scale takes (lcgan_box3_cs)."""
     n, c, h, w = x.shape
-    return x.is_cuda and w >= 32 and h >= 16 and c % (32 if x.dtype == torch.bfloat16 else 16) == 0 and _FOLD_STYLE
+    return (x.is_cuda and w >= 32 and h >= 16 and c % (32 if x.dtype == torch.bfloat16 else 16) == 0 and _FOLD_STYLE
+            and not _DET)
 
 
 _FOLD_STYLE = os.environ.get("LCGAN_NO_FOLD_STYLE", "0") != "1"
+# deterministic mode (set_deterministic): the fused passes whose reductions finish with atomics (style gradient in the
+# box pass, bias gradient in BoxMask, the per-image pointwise weight gradient) fall back to the separate kernels, whose
+# reductions take ordered turns
+_DET = False
 
 
 def fold_style_eligible(h, w, c, is_cuda=True) -> bool:
     """Shapes for which the tiled box / warp kernels can fold a style scale into their pass."""
-    return bool(is_cuda and _FOLD_STYLE and w >= 32 and h >= 16 and c % (32 if _ACT_DTYPE == torch.bfloat16 else 16) == 0)
+    return bool(is_cuda and _FOLD_STYLE and not _DET and w >= 32 and h >= 16
+                and c % (32 if _ACT_DTYPE == torch.bfloat16 else 16) == 0)
 
 
 class Box3ActMod(torch.autograd.Function):
@@ -918,7 +1019,7 @@ class ModConvAct(torch.autograd.Function):
         ctx.premod = bool(premodulated)
         # pointwise 32 -> (<= 4) layer (to-RGB 1x1 at 1024^2): the thin kernel multiplies by the style as it reads x,
         # and one per-image weight-gradient pass yields dW and ds - no modulate / modulate_bwd passes at all
-        ctx.pwmod = bool(not premodulated and _FOLD_STYLE and plan.k == 1 and len(plan.launches) == 1
+        ctx.pwmod = bool(not premodulated and _FOLD_STYLE and not _DET and plan.k == 1 and len(plan.launches) == 1
                          and plan.launches[0].is_ == 1 and x.shape[1] == 32 and w.shape[0] <= 4
                          and x.dtype == torch.bfloat16 and _is_cl_dense(x) and noise is None)
         xs = x if (premodulated or ctx.pwmod) else _modulate_raw(x, s)
@@ -1220,4 +1321,6 @@ def set_deterministic(flag: bool) -> bool:
     on the same inputs are bit-identical.  Returns the previous setting.  (The rough-flow scatter
     fallback of the warp backward stays atomic; smooth flows - everything at and near initialisation -
     take the gather path, which is deterministic by construction.)"""
+    global _DET
+    _DET = bool(flag)
     return bool(_lib.lib().lcgan_set_deterministic(1 if flag else 0))

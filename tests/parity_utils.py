@@ -49,36 +49,35 @@ def masked_oracle(O, masks=None):
 
 
 class MaskRecorder:
-    """Collects the sign masks of our fused activations, in forward order: forward hooks on the modules whose
-    output is a leaky-relu'd tensor, plus a wrapper around ops.Box3Act (box filter + lrelu, one kernel)."""
+    """Collects the sign masks of our fused activations, in forward order.  Every leaky-relu of the CUDA path lives in
+    a kernel epilogue, so the recorder wraps the two entry points that apply one: ops.tapconv (conv epilogue, recorded
+    when the call has slope != 1) and ops.Box3Act / ops.Box3ActMod (box filter + lrelu [* style])."""
 
-    def __init__(self, modules=(), box3act=False):
+    def __init__(self, modules=(), box3act=True):
         from lcgan_b200 import ops
-        self.masks, self._handles, self._ops, self._orig = [], [], ops, None
-        for m in modules:
-            self._handles.append(m.register_forward_hook(lambda mod, inp, out: self.masks.append((out > 0).detach())))
-        self._orig_mod = None
-        if box3act:
-            self._orig, self._orig_mod = ops.Box3Act.apply, ops.Box3ActMod.apply
+        self.masks, self._ops = [], ops
+        self._tapconv, self._box, self._boxmod = ops.tapconv, ops.Box3Act.apply, ops.Box3ActMod.apply
 
-            def apply(*a):
-                out = self._orig(*a)
-                self.masks.append((out > 0).detach())
-                return out
+        def tapconv(*a, **k):
+            out = self._tapconv(*a, **k)
+            slope = k.get("slope", a[7] if len(a) > 7 else 1.0)
+            if slope != 1.0:
+                self.masks.append((a[2] > 0).detach())
+            return out
 
-            def apply_mod(x, s, *a):          # output = lrelu(box(x)) * gain * s: the mask is the sign of output / s
-                out = self._orig_mod(x, s, *a)
-                self.masks.append(((out.float() * s[:, :, None, None]) > 0).detach())
-                return out
-            ops.Box3Act.apply, ops.Box3ActMod.apply = apply, apply_mod
+        def box(*a):
+            out = self._box(*a)
+            self.masks.append((out > 0).detach())
+            return out
+
+        def boxmod(x, s, *a):                 # output = lrelu(box(x)) * gain * s: the mask is the sign of output * s
+            out = self._boxmod(x, s, *a)
+            self.masks.append(((out.float() * s[:, :, None, None]) > 0).detach())
+            return out
+        ops.tapconv, ops.Box3Act.apply, ops.Box3ActMod.apply = tapconv, box, boxmod
 
     def close(self):
-        for h in self._handles:
-            h.remove()
-        if self._orig is not None:
-            self._ops.Box3Act.apply = self._orig
-        if self._orig_mod is not None:
-            self._ops.Box3ActMod.apply = self._orig_mod
+        self._ops.tapconv, self._ops.Box3Act.apply, self._ops.Box3ActMod.apply = self._tapconv, self._box, self._boxmod
 
     def __enter__(self):
         return self
