@@ -87,6 +87,12 @@ int lcgan_tapconv_up2_thin(const lcgan_tapconv* d, const void* x, const void* w2
 int lcgan_tapconv_up2_thin_wgrad(const lcgan_tapconv* d, const void* x, const void* g, float* dw2,
                                  float scale, void* stream);
 
+/* Gather for the flow layers' weight gradient on the tensor cores: g [N,2H,2W,2] f32 channels-last (the gradient of a
+ * C -> 2 conv_transpose2d(k3,s2,p1,op1), custom_layers.py:78,150) -> out [N,H,W,32] bf16 channels-last with
+ * out[b,m,n, (ki*3+kj)*2 + o] = g[b, 2m-1+ki, 2n-1+kj, o] (0 outside the image; channels 18..31 zero).  The weight
+ * gradient is then the pointwise lcgan_tapconv_wgrad_tc of X against this tensor. */
+int lcgan_flow_grad_im2col(const float* g, void* out, int N, int H, int W, void* stream);
+
 /* Forward-type tap conv on CUDA cores (any strides/dtypes; fp32 accumulate).
  * Replaces F.conv2d / F.conv_transpose2d / F.linear call sites (custom_layers.py:25,41,43,78,83)
  * and their autograd data-gradients.  rowscale [N,Cout] f32, bias [Cout] f32, residual like Y;

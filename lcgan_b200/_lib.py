@@ -104,6 +104,7 @@ _SIGS = {
                                   _VOIDP], C.c_int),
     "lcgan_tapconv_simt": ([C.POINTER(TapConvDesc), _VOIDP, _VOIDP, _VOIDP, _FP, _FP, _VOIDP, _VOIDP], C.c_int),
     "lcgan_tapconv_tc": ([C.POINTER(TapConvDesc), _VOIDP, _VOIDP, _VOIDP, _FP, _FP, _VOIDP, _VOIDP], C.c_int),
+    "lcgan_flow_grad_im2col": ([_FP, _VOIDP, C.c_int, C.c_int, C.c_int, _VOIDP], C.c_int),
     "lcgan_pw_wgrad32": ([C.POINTER(TapConvDesc), _VOIDP, _VOIDP, _FP, _VOIDP], C.c_int),
     "lcgan_tapconv_wgrad_simt": ([C.POINTER(TapConvDesc), _VOIDP, _VOIDP, _FP, C.c_float, _VOIDP], C.c_int),
     "lcgan_tapconv_wgrad_tc": ([C.POINTER(TapConvDesc), _VOIDP, _VOIDP, _FP, C.c_float, _VOIDP], C.c_int),

@@ -468,6 +468,25 @@ def tapconv_wgrad(x, g, plan: plans.Plan, cin, cout, scale=1.0):
     st = _stream(x)
     d = TapConvDesc()
     cv4 = cin // 4
+    if (_FLOW_TC and _USE_TC and _USE_WGRAD_TC and not _DET and len(plan.launches) == 4 and cout == 2
+            and plan.launches[0].os == 2 and cin % 32 == 0 and x.dtype == torch.bfloat16 and g.dtype == torch.float32
+            and _is_cl_dense(x) and _is_cl_dense(g) and plan.IH * plan.IW >= 128
+            and plan.IH & (plan.IH - 1) == 0 and plan.IW & (plan.IW - 1) == 0):
+        # flow layer: gather the 9 x 2 gradient taps into a 32-channel bf16 tensor, then a pointwise tensor-core wgrad
+        n = x.shape[0]
+        g18 = empty_cl(n, 32, plan.IH, plan.IW, torch.bfloat16, x.device)
+        _lib.call("lcgan_flow_grad_im2col", _ptr(g), _ptr(g18), n, plan.IH, plan.IW, st, tag="flow_grad_im2col",
+                  nbytes=g.numel() * 4 + g18.numel() * 2)
+        p1 = plans.conv(1, 1, plan.IH, plan.IW)
+        l = p1.launches[0]
+        t = torch.zeros((32, cin), dtype=torch.float32, device=x.device)
+        _fill_desc(d, l, x, g18, cin, 32, None, 1.0, 1.0, 1.0)
+        d.w_ld = cin
+        _lib.call("lcgan_tapconv_wgrad_tc", C.byref(d), _ptr(x), _ptr(g18), _ptr(t), C.c_float(scale), st,
+                  tag=_shape_tag("lcgan_tapconv_wgrad_tc", d), flops=2.0 * n * plan.IH * plan.IW * 18 * cin,
+                  nbytes=x.numel() * 2 + g18.numel() * 2)
+        # rows (tap, o) -> dW2[o][tap*cin + c]
+        return t[:18].view(9, 2, cin).permute(1, 0, 2).reshape(2, 9 * cin).contiguous()
     if (len(plan.launches) == 4 and cout <= 2 and plan.launches[0].os == 2 and cin % 4 == 0 and cv4 <= 256
             and 256 % cv4 == 0):
         # x2 transposed conv of a flow layer: one fused pass for all 9 taps

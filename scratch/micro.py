@@ -61,6 +61,7 @@ for w in which:
             ms = timeit(lambda: ops.tapconv(g, w2, y, plans.adjoint(plan))); tr = y.numel() * 2 + g.numel() * 4
         else:
             g = cl(torch.randn(N, 2, 2 * R, 2 * R, device=dev))
+            ops._FLOW_TC = os.environ.get("LCGAN_NO_FLOW_TC") != "1"
             ms = timeit(lambda: ops.tapconv_wgrad(x, g, plan, C, 2)); tr = x.numel() * 2 + g.numel() * 4
         print(f"{w:8s} {ms:8.3f} ms  {tr/ms/1e6:8.0f} GB/s (algorithmic)")
     else:

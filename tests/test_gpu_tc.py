@@ -163,3 +163,24 @@ def test_flow_layer_on_tensor_cores_matches_thin_kernel(case):
     torch.cuda.synchronize()
     assert torch.isfinite(outs[1]).all()
     assert rel_l2(outs[1], outs[0]) < 1e-5, f"{case}: {rel_l2(outs[1], outs[0])}"
+
+
+@pytest.mark.parametrize("case", [(2, 64, 16, 16), (3, 128, 8, 16), (1, 32, 64, 32), (4, 64, 32, 32)])   # N, Cin, H, W
+def test_flow_layer_wgrad_on_tensor_cores_matches_thin_kernel(case):
+    """Weight gradient of the flow layers (C -> 2, x2 transposed, fp32 gradient): gather of the 9 x 2 gradient taps +
+    a pointwise tensor-core wgrad against the CUDA-core all-tap kernel (the gather rounds the gradient to bf16)."""
+    from lcgan_b200 import ops, plans, _lib
+    N, Cin, H, W = case
+    plan = plans.conv_transpose_up2(3, H, W)
+    x = _cl(torch.randn(N, Cin, H, W, device="cuda").bfloat16())
+    g = _cl(torch.randn(N, 2, 2 * H, 2 * W, device="cuda"))
+    outs = []
+    for tc in (False, True):
+        ops._FLOW_TC = tc
+        before = _lib.counts.get("lcgan_flow_grad_im2col", 0)
+        outs.append(ops.tapconv_wgrad(x, g if tc else g.bfloat16().float(), plan, Cin, 2, scale=0.37))
+        assert _lib.counts.get("lcgan_flow_grad_im2col", 0) == before + (1 if tc else 0)
+    ops._FLOW_TC = True
+    torch.cuda.synchronize()
+    assert outs[1].shape == outs[0].shape == (2, 9 * Cin)
+    assert rel_l2(outs[1], outs[0]) < 1e-5, f"{case}: {rel_l2(outs[1], outs[0])}"
