@@ -6,6 +6,7 @@
 // reduction over channels) in one pass.  A group of G lanes (G = min(32, C/V)) owns one pixel and
 // strides over its 16-byte channel vectors, so every gather tap is a contiguous run.
 #include "common.cuh"
+#include "tma_window.cuh"
 #include <stdlib.h>
 #include <limits.h>
 #include <mutex>
@@ -109,6 +110,7 @@ constexpr int kFW = 44, kFH = 28;                        // footprint window (fw
 constexpr int kBW = 48, kBH = 32;                        // contributor window (dx): tile + 16
 constexpr int kMaxWindows = 6;                           // dx: windows per source tile before giving up
 constexpr int kFwdSmem = kFW * kFH * kPixB + 16;                     //  78 864 B (2 CTAs / SM)
+constexpr int kFwdSmem8 = kFW * (8 + 12) * kPixB + 16;                //  56 336 B (4 CTAs / SM, 8-row tiles)
 constexpr int kDxSmem = kBW * kBH * (kPixB + 8) + 32;                // 110 624 B (2 CTAs / SM)
 
 // the scatter (atomic) kernels run only when the tiled dx kernel raised the flag
@@ -399,46 +401,61 @@ warp_bwd_run_kernel(const T* __restrict__ x, const float* __restrict__ flow, con
 }
 
 
-template <typename T> __device__ __forceinline__ void unpack16(const uint4& u, float* f);
-template <> __device__ __forceinline__ void unpack16<bf16>(const uint4& u, float* f) {
-  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    f[2 * i] = __uint_as_float(w[i] << 16);
-    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+// Mixed-precision FMA of sm_100 (PTX fma.rn.f32.bf16 -> SASS FHFMA.BF16 with .H0/.H1 operand selects): both factors are
+// bf16 halves of packed registers, the product is exact and the accumulate is fp32 - so a packed bf16 pair needs no
+// unpack instructions (ncu on the unpack + FFMA form: 54 % ALU-pipe, 31 % FMA-pipe, issue-bound).
+//   acc0 += lo(x) * lo(w),  acc1 += hi(x) * lo(w)
+__device__ __forceinline__ void fhfma_pair(uint32_t x, uint32_t w, float& acc0, float& acc1) {
+  asm("{\n\t.reg .b16 xl, xh, wl, wh;\n\t"
+      "mov.b32 {xl, xh}, %2;\n\tmov.b32 {wl, wh}, %3;\n\t"
+      "fma.rn.f32.bf16 %0, xl, wl, %0;\n\tfma.rn.f32.bf16 %1, xh, wl, %1;\n\t}"
+      : "+f"(acc0), "+f"(acc1) : "r"(x), "r"(w));
+}
+//   acc += lo(x) * lo(g) + hi(x) * hi(g)
+__device__ __forceinline__ void fhfma_dot(uint32_t x, uint32_t g, float& acc) {
+  asm("{\n\t.reg .b16 xl, xh, gl, gh;\n\t"
+      "mov.b32 {xl, xh}, %1;\n\tmov.b32 {gl, gh}, %2;\n\t"
+      "fma.rn.f32.bf16 %0, xl, gl, %0;\n\tfma.rn.f32.bf16 %0, xh, gh, %0;\n\t}"
+      : "+f"(acc) : "r"(x), "r"(g));
+}
+// A tap weight as the bf16 operand of fhfma_pair.  Rounding the 16 bicubic weights to bf16 (2^-9 relative each)
+// perturbs the result by less than the bf16 rounding of the stored output does (sum w^2 < 1); fp32 mode is untouched.
+__device__ __forceinline__ uint32_t bf16_weight(float w) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(w)); }
+
+template <typename T>
+__device__ __forceinline__ void fma_vec(const uint4& u, float w, uint32_t wb, float* acc) {
+  if constexpr (sizeof(T) == 2) {
+    fhfma_pair(u.x, wb, acc[0], acc[1]); fhfma_pair(u.y, wb, acc[2], acc[3]);
+    fhfma_pair(u.z, wb, acc[4], acc[5]); fhfma_pair(u.w, wb, acc[6], acc[7]);
+  } else {
+    acc[0] = fmaf(__uint_as_float(u.x), w, acc[0]); acc[1] = fmaf(__uint_as_float(u.y), w, acc[1]);
+    acc[2] = fmaf(__uint_as_float(u.z), w, acc[2]); acc[3] = fmaf(__uint_as_float(u.w), w, acc[3]);
   }
 }
-template <> __device__ __forceinline__ void unpack16<float>(const uint4& u, float* f) {
-  f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y); f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w);
+template <typename T>
+__device__ __forceinline__ void dot_vec(const uint4& u, const uint4& g, float& dot) {
+  if constexpr (sizeof(T) == 2) {
+    fhfma_dot(u.x, g.x, dot); fhfma_dot(u.y, g.y, dot); fhfma_dot(u.z, g.z, dot); fhfma_dot(u.w, g.w, dot);
+  } else {
+    dot = fmaf(__uint_as_float(u.x), __uint_as_float(g.x), dot); dot = fmaf(__uint_as_float(u.y), __uint_as_float(g.y), dot);
+    dot = fmaf(__uint_as_float(u.z), __uint_as_float(g.z), dot); dot = fmaf(__uint_as_float(u.w), __uint_as_float(g.w), dot);
+  }
 }
 
 // acc[0..CC) += w * (64-byte pixel chunk at p)
 template <typename T>
 __device__ __forceinline__ void fma_chunk(const unsigned char* p, float w, float* acc) {
   constexpr int E = 16 / sizeof(T);
+  const uint32_t wb = sizeof(T) == 2 ? bf16_weight(w) : 0u;
 #pragma unroll
-  for (int v = 0; v < 4; ++v) {
-    const uint4 u = *reinterpret_cast<const uint4*>(p + v * 16);
-    float f[E];
-    unpack16<T>(u, f);
-#pragma unroll
-    for (int i = 0; i < E; ++i) acc[v * E + i] = fmaf(f[i], w, acc[v * E + i]);
-  }
+  for (int v = 0; v < 4; ++v) fma_vec<T>(*reinterpret_cast<const uint4*>(p + v * 16), w, wb, acc + v * E);
 }
 // <chunk at p, chunk g> with g kept packed (4 x uint4)
 template <typename T>
 __device__ __forceinline__ float dot_chunk(const unsigned char* p, const uint4* g) {
-  constexpr int E = 16 / sizeof(T);
   float dot = 0.f;
 #pragma unroll
-  for (int v = 0; v < 4; ++v) {
-    const uint4 u = *reinterpret_cast<const uint4*>(p + v * 16);
-    float f[E], h[E];
-    unpack16<T>(u, f);
-    unpack16<T>(g[v], h);
-#pragma unroll
-    for (int i = 0; i < E; ++i) dot = fmaf(f[i], h[i], dot);
-  }
+  for (int v = 0; v < 4; ++v) dot_vec<T>(*reinterpret_cast<const uint4*>(p + v * 16), g[v], dot);
   return dot;
 }
 // the same on a swizzled window pixel (win = window base, pq = pixel index in the window)
@@ -447,30 +464,17 @@ __device__ __forceinline__ void fma_chunk_win(const unsigned char* win, int pq, 
   constexpr int E = 16 / sizeof(T);
   const unsigned char* p = win + pq * kPixB;
   const int x = (pq >> 1) & 3;
+  const uint32_t wb = sizeof(T) == 2 ? bf16_weight(w) : 0u;
 #pragma unroll
-  for (int v = 0; v < 4; ++v) {
-    const uint4 u = *reinterpret_cast<const uint4*>(p + ((v ^ x) << 4));
-    float f[E];
-    unpack16<T>(u, f);
-#pragma unroll
-    for (int i = 0; i < E; ++i) acc[v * E + i] = fmaf(f[i], w, acc[v * E + i]);
-  }
+  for (int v = 0; v < 4; ++v) fma_vec<T>(*reinterpret_cast<const uint4*>(p + ((v ^ x) << 4)), w, wb, acc + v * E);
 }
 template <typename T>
 __device__ __forceinline__ float dot_chunk_win(const unsigned char* win, int pq, const uint4* g) {
-  constexpr int E = 16 / sizeof(T);
   const unsigned char* p = win + pq * kPixB;
   const int x = (pq >> 1) & 3;
   float dot = 0.f;
 #pragma unroll
-  for (int v = 0; v < 4; ++v) {
-    const uint4 u = *reinterpret_cast<const uint4*>(p + ((v ^ x) << 4));
-    float f[E], h[E];
-    unpack16<T>(u, f);
-    unpack16<T>(g[v], h);
-#pragma unroll
-    for (int i = 0; i < E; ++i) dot = fmaf(f[i], h[i], dot);
-  }
+  for (int v = 0; v < 4; ++v) dot_vec<T>(*reinterpret_cast<const uint4*>(p + ((v ^ x) << 4)), g[v], dot);
   return dot;
 }
 template <typename T>
@@ -486,26 +490,78 @@ __device__ __forceinline__ void store_chunk(T* dst, const float* acc) {
 
 // BWD = false: out[p] = sum_taps w x[tap]          (the forward warp)
 // BWD = true : dflow[p] from <x[tap], g[p]> and the derivative weights
-template <typename T, bool BWD>
-__global__ void __launch_bounds__(kTileThreads, 2)
-warp_tile_gather_kernel(const T* __restrict__ x, const float* __restrict__ flow, const T* __restrict__ g,
-                        T* __restrict__ out, float* __restrict__ dflow, int H, int W, int C, float scale,
-                        const float* __restrict__ cs = nullptr) {
+// Pre-pass: per SOURCE tile, the bounding box of the output pixels whose 4x4 footprint touches it.
+// bbox[tile] = {max(-p.x), max(p.x), max(-p.y), max(p.y)}, pre-set very negative (memset 0x80).  A warp
+// (32 pixels of a row) aggregates by source tile before the atomics.
+// (called by all 32 lanes; live = this lane holds an output pixel (w, h) of image b with footprint origin x0, y0)
+__device__ __forceinline__ void bbox_update(int* __restrict__ bbox, bool live, int b, int h, int w, int x0, int y0, int H,
+                                            int W, int tiles_x, int tiles_y) {
+  int fx0 = 1, fx1 = 0, fy0 = 1, fy1 = 0;                              // empty footprint
+  if (live) {
+    fx0 = max(x0 - 1, 0); fx1 = min(x0 + 2, W - 1);
+    fy0 = max(y0 - 1, 0); fy1 = min(y0 + 2, H - 1);
+  }
+  const bool any = fx0 <= fx1 && fy0 <= fy1;
+  const int tx0 = fx0 / kTW, tx1 = fx1 / kTW, ty0 = fy0 / kTH, ty1 = fy1 / kTH;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int tx = (k & 1) ? tx1 : tx0, ty = (k & 2) ? ty1 : ty0;
+    const bool dup = ((k & 1) && tx1 == tx0) || ((k & 2) && ty1 == ty0);
+    const int id = (any && !dup) ? (b * tiles_y + ty) * tiles_x + tx : -1;
+    const unsigned grp = __match_any_sync(0xffffffffu, id);
+    const int a0 = __reduce_max_sync(grp, -w), a1 = __reduce_max_sync(grp, w);
+    const int a2 = __reduce_max_sync(grp, -h), a3 = __reduce_max_sync(grp, h);
+    if (id >= 0 && (int)(threadIdx.x & 31) == __ffs(grp) - 1) {
+      int* bb = bbox + (int64_t)id * 4;
+      atomicMax(bb + 0, a0); atomicMax(bb + 1, a1); atomicMax(bb + 2, a2); atomicMax(bb + 3, a3);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+warp_bbox_kernel(const float* __restrict__ flow, int N, int H, int W, float scale, int* __restrict__ bbox) {
+  const int tiles_x = (W + kTW - 1) / kTW, tiles_y = (H + kTH - 1) / kTH;
+  const int64_t npix = (int64_t)N * H * W;
+  const int64_t npix_pad = (npix + 31) / 32 * 32;
+  for (int64_t pix = blockIdx.x * 256LL + threadIdx.x; pix < npix_pad; pix += (int64_t)gridDim.x * 256) {
+    const bool live = pix < npix;
+    int w = 0, h = 0, b = 0, x0 = 0, y0 = 0;
+    if (live) {
+      w = (int)(pix % W); h = (int)((pix / W) % H); b = (int)(pix / ((int64_t)W * H));
+      const PixCoord pc = source_index(flow, pix, h, w, H, W, scale);
+      x0 = pc.x0; y0 = pc.y0;
+    }
+    bbox_update(bbox, live, b, h, w, x0, y0, H, W, tiles_x, tiles_y);
+  }
+}
+
+// TMA = true (bf16): the window arrives by one bulk tensor copy (tma_window.cuh) instead of per-thread cp.async
+// TH = tile height (a warp per row): 16 -> 2 CTAs of 512 threads per SM, 8 -> 4 CTAs of 256 (more independent
+// flow-load -> window-load -> gather latency chains in flight per SM)
+template <typename T, bool BWD, bool TMA = false, int TH = kTH>
+__global__ void __launch_bounds__(kTW * TH, 1024 / (kTW * TH))
+warp_tile_gather_kernel(const __grid_constant__ CUtensorMap tmx, const T* __restrict__ x, const float* __restrict__ flow,
+                        const T* __restrict__ g, T* __restrict__ out, float* __restrict__ dflow, int H, int W, int C,
+                        float scale, const float* __restrict__ cs = nullptr, int* __restrict__ bbox = nullptr) {
   // cs [N,C] (forward only, optional): out = warp(x) * cs[b,c] - the style of the modulated conv that consumes
   // the warped features (the to-RGB block), folded into this pass
   constexpr int CC = 64 / sizeof(T);
-  extern __shared__ __align__(16) unsigned char smem[];
-  const int tiles_x = (W + kTW - 1) / kTW, tiles_y = (H + kTH - 1) / kTH;
+  constexpr int FH = TH + 12;                              // window height
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tiles_x = (W + kTW - 1) / kTW, tiles_y = (H + TH - 1) / TH;
   int t = blockIdx.x;
   const int tx = t % tiles_x; t /= tiles_x;
   const int ty = t % tiles_y;
   const int b = t / tiles_y;
-  const int px = tx * kTW + (threadIdx.x & 31), py = ty * kTH + (threadIdx.x >> 5);
+  const int px = tx * kTW + (threadIdx.x & 31), py = ty * TH + (threadIdx.x >> 5);
   const bool live = px < W && py < H;
   const T* img = x + (int64_t)b * H * W * C;
   const int64_t pix = ((int64_t)b * H + py) * W + px;
-  int* org = reinterpret_cast<int*>(smem + kFW * kFH * kPixB);   // window origin (min x0, min y0 of the tile)
+  int* org = reinterpret_cast<int*>(smem + kFW * FH * kPixB);   // window origin (min x0, min y0 of the tile)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kFW * FH * kPixB + 8);
+  uint32_t phase = 0;
   if (threadIdx.x < 2) org[threadIdx.x] = INT_MAX;
+  if (TMA && threadIdx.x == 0) tmaw::bar_init(bar);
   __syncthreads();
   PixCoord pc{};
   float wx[4], wy[4], dwx[4], dwy[4];
@@ -518,23 +574,36 @@ warp_tile_gather_kernel(const T* __restrict__ x, const float* __restrict__ flow,
     // footprints entirely outside the image contribute nothing and must not drag the window away
     if (pc.x0 + 2 >= 0 && pc.x0 - 1 < W && pc.y0 + 2 >= 0 && pc.y0 - 1 < H) { mx = pc.x0; my = pc.y0; }
   }
+  if constexpr (BWD) {
+    // the dx kernel's per-source-tile contributor boxes, from the coordinates this pass computes anyway
+    if (bbox) bbox_update(bbox, live, b, py, px, pc.x0, pc.y0, H, W, (W + kTW - 1) / kTW, (H + kTH - 1) / kTH);
+  }
   mx = __reduce_min_sync(0xffffffffu, mx);
   my = __reduce_min_sync(0xffffffffu, my);
   if ((threadIdx.x & 31) == 0) { atomicMin(org + 0, mx); atomicMin(org + 1, my); }
   __syncthreads();
   const int wx0 = min(max(org[0] - 1, -4), W), wy0 = min(max(org[1] - 1, -4), H);
-  const bool inwin = live && pc.x0 - 1 >= wx0 && pc.x0 + 2 < wx0 + kFW && pc.y0 - 1 >= wy0 && pc.y0 + 2 < wy0 + kFH;
+  const bool inwin = live && pc.x0 - 1 >= wx0 && pc.x0 + 2 < wx0 + kFW && pc.y0 - 1 >= wy0 && pc.y0 + 2 < wy0 + FH;
   float gix = 0.f, giy = 0.f;
   for (int c0 = 0; c0 < C; c0 += CC) {
     if (c0) __syncthreads();                             // everyone is done with the previous chunk
-    load_window<T, kFW, kFH, kPixB, kTileThreads, true>(smem, img, H, W, C, c0, wy0, wx0);
+    if constexpr (TMA) {
+      if (threadIdx.x == 0) tmaw::load(smem, &tmx, bar, kFW * FH * kPixB, c0, wx0, wy0, b);
+    } else {
+      load_window<T, kFW, FH, kPixB, kTW * TH, true>(smem, img, H, W, C, c0, wy0, wx0);
+    }
     uint4 gv[4];
     if (BWD && live) {
 #pragma unroll
       for (int v = 0; v < 4; ++v) gv[v] = *reinterpret_cast<const uint4*>(g + pix * C + c0 + v * (16 / sizeof(T)));
     }
-    cp_async_wait_all();
-    __syncthreads();
+    if constexpr (TMA) {
+      tmaw::wait(bar, phase);
+      phase ^= 1;
+    } else {
+      cp_async_wait_all();
+      __syncthreads();
+    }
     if (!live) continue;
     float acc[CC];
 #pragma unroll
@@ -619,57 +688,31 @@ __device__ __forceinline__ float cubic_k(float d) {
   return fmaf(fmaf(fmaf(c3, d, c2), d, c1), d, c0);
 }
 
-// Pre-pass: per SOURCE tile, the bounding box of the output pixels whose 4x4 footprint touches it.
-// bbox[tile] = {max(-p.x), max(p.x), max(-p.y), max(p.y)}, pre-set very negative (memset 0x80).  A warp
-// (32 pixels of a row) aggregates by source tile before the atomics.
-__global__ void __launch_bounds__(256)
-warp_bbox_kernel(const float* __restrict__ flow, int N, int H, int W, float scale, int* __restrict__ bbox) {
-  const int tiles_x = (W + kTW - 1) / kTW, tiles_y = (H + kTH - 1) / kTH;
-  const int64_t npix = (int64_t)N * H * W;
-  const int64_t npix_pad = (npix + 31) / 32 * 32;
-  for (int64_t pix = blockIdx.x * 256LL + threadIdx.x; pix < npix_pad; pix += (int64_t)gridDim.x * 256) {
-    const bool live = pix < npix;
-    int w = 0, h = 0, b = 0, fx0 = 1, fx1 = 0, fy0 = 1, fy1 = 0;      // empty footprint
-    if (live) {
-      w = (int)(pix % W); h = (int)((pix / W) % H); b = (int)(pix / ((int64_t)W * H));
-      const PixCoord pc = source_index(flow, pix, h, w, H, W, scale);
-      fx0 = max(pc.x0 - 1, 0); fx1 = min(pc.x0 + 2, W - 1);
-      fy0 = max(pc.y0 - 1, 0); fy1 = min(pc.y0 + 2, H - 1);
-    }
-    const bool any = fx0 <= fx1 && fy0 <= fy1;
-    const int tx0 = fx0 / kTW, tx1 = fx1 / kTW, ty0 = fy0 / kTH, ty1 = fy1 / kTH;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int tx = (k & 1) ? tx1 : tx0, ty = (k & 2) ? ty1 : ty0;
-      const bool dup = ((k & 1) && tx1 == tx0) || ((k & 2) && ty1 == ty0);
-      const int id = (any && !dup) ? (b * tiles_y + ty) * tiles_x + tx : -1;
-      const unsigned grp = __match_any_sync(0xffffffffu, id);
-      const int a0 = __reduce_max_sync(grp, -w), a1 = __reduce_max_sync(grp, w);
-      const int a2 = __reduce_max_sync(grp, -h), a3 = __reduce_max_sync(grp, h);
-      if (id >= 0 && (int)(threadIdx.x & 31) == __ffs(grp) - 1) {
-        int* bb = bbox + (int64_t)id * 4;
-        atomicMax(bb + 0, a0); atomicMax(bb + 1, a1); atomicMax(bb + 2, a2); atomicMax(bb + 3, a3);
-      }
-    }
-  }
-}
-
-template <typename T>
+template <typename T, bool TMA = false>
 __global__ void __launch_bounds__(kTileThreads, 2)
-warp_tile_dx_kernel(const float* __restrict__ flow, const T* __restrict__ g, T* __restrict__ dx,
-                    const int* __restrict__ bbox, int* __restrict__ flag, int H, int W, int C, float scale) {
+warp_tile_dx_kernel(const __grid_constant__ CUtensorMap tmg, const float* __restrict__ flow, const T* __restrict__ g,
+                    T* __restrict__ dx, const int* __restrict__ bbox, int* __restrict__ flag, int H, int W, int C,
+                    float scale) {
   constexpr int CC = 64 / sizeof(T);
-  extern __shared__ __align__(16) unsigned char smem[];
+  extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* gwin = smem;
   float2* coord = reinterpret_cast<float2*>(smem + kBW * kBH * kPixB);
   int* lb = reinterpret_cast<int*>(smem + kBW * kBH * (kPixB + 8));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kBW * kBH * (kPixB + 8) + 16);
+  uint32_t phase = 0;
+  if (TMA && threadIdx.x == 0) tmaw::bar_init(bar);      // made visible by the first __syncthreads of the window loop
   const int tiles_x = (W + kTW - 1) / kTW, tiles_y = (H + kTH - 1) / kTH;
   int t = blockIdx.x;
   const int* bb = bbox + (int64_t)t * 4;
   const int tx = t % tiles_x; t /= tiles_x;
   const int ty = t % tiles_y;
   const int b = t / tiles_y;
-  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  // a warp owns an 8 x 4 patch, not 32 pixels of a row: its lanes walk the candidate offsets in lockstep and run the
+  // union of their hit sets, which grows with the spread of the displacement over the warp (ncu, 8 %-stretch flow:
+  // 33 hit iterations per warp for 16-20 per lane with row-shaped warps).  A quarter-warp is still 8 consecutive
+  // pixels of a row, so the swizzled 16-byte window reads stay conflict-free and the stores 512-byte runs.
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lx = (wid & 3) * 8 + (lane & 7), ly = (wid >> 2) * 4 + (lane >> 3);
   const int px = tx * kTW + lx, py = ty * kTH + ly;
   const bool live = px < W && py < H;
   const int64_t pix = ((int64_t)b * H + py) * W + px;
@@ -690,7 +733,11 @@ warp_tile_dx_kernel(const float* __restrict__ flow, const T* __restrict__ g, T* 
     for (int wi = 0; wi < nwx * nwy; ++wi) {
       const int wx0 = bx0 + (wi % nwx) * kBW, wy0 = by0 + (wi / nwx) * kBH;
       __syncthreads();                                       // previous window fully consumed
-      load_window<T, kBW, kBH, kPixB, kTileThreads, true>(gwin, gimg, H, W, C, c0, wy0, wx0);
+      if constexpr (TMA) {
+        if (threadIdx.x == 0) tmaw::load(gwin, &tmg, bar, kBW * kBH * kPixB, c0, wx0, wy0, b);
+      } else {
+        load_window<T, kBW, kBH, kPixB, kTileThreads, true>(gwin, gimg, H, W, C, c0, wy0, wx0);
+      }
       if (c0 == 0 || nwx * nwy > 1) {
         // sample positions of the window's output pixels + their integer displacement range
         if (threadIdx.x < 4) lb[threadIdx.x] = INT_MIN;
@@ -714,9 +761,14 @@ warp_tile_dx_kernel(const float* __restrict__ flow, const T* __restrict__ g, T* 
         }
         m0 = __reduce_max_sync(0xffffffffu, m0); m1 = __reduce_max_sync(0xffffffffu, m1);
         m2 = __reduce_max_sync(0xffffffffu, m2); m3 = __reduce_max_sync(0xffffffffu, m3);
-        if (lx == 0) { atomicMax(lb + 0, m0); atomicMax(lb + 1, m1); atomicMax(lb + 2, m2); atomicMax(lb + 3, m3); }
+        if (lane == 0) { atomicMax(lb + 0, m0); atomicMax(lb + 1, m1); atomicMax(lb + 2, m2); atomicMax(lb + 3, m3); }
       }
-      cp_async_wait_all();
+      if constexpr (TMA) {
+        tmaw::wait(bar, phase);
+        phase ^= 1;
+      } else {
+        cp_async_wait_all();
+      }
       __syncthreads();
       if (!live || lb[1] == INT_MIN) continue;               // no sample of this window reaches the tile
       // contributors of s: p in [s - e_max - 2, s - e_min + 1], clipped to the window
@@ -781,12 +833,37 @@ static int tile_kernels_ready() {
   std::call_once(once, [] {
     err |= opt_in_smem(warp_tile_gather_kernel<bf16, false>, kFwdSmem);
     err |= opt_in_smem(warp_tile_gather_kernel<bf16, true>, kFwdSmem);
+    err |= opt_in_smem(warp_tile_gather_kernel<bf16, false, true>, kFwdSmem);
+    err |= opt_in_smem(warp_tile_gather_kernel<bf16, true, true>, kFwdSmem);
+    err |= opt_in_smem(warp_tile_gather_kernel<bf16, false, true, 8>, kFwdSmem8);
+    err |= opt_in_smem(warp_tile_gather_kernel<bf16, true, true, 8>, kFwdSmem8);
+    err |= opt_in_smem(warp_tile_dx_kernel<bf16, true>, kDxSmem);
     err |= opt_in_smem(warp_tile_gather_kernel<float, false>, kFwdSmem);
     err |= opt_in_smem(warp_tile_gather_kernel<float, true>, kFwdSmem);
     err |= opt_in_smem(warp_tile_dx_kernel<bf16>, kDxSmem);
     err |= opt_in_smem(warp_tile_dx_kernel<float>, kDxSmem);
   });
   return err;
+}
+
+static bool tile8() { static const bool on = getenv("LCGAN_WARP_TH16") == nullptr; return on; }
+static bool use_tma() { static const bool on = getenv("LCGAN_WARP_NO_TMA") == nullptr; return on; }
+
+static void launch_tile_fwd(const void* x, const float* flow, void* out, const float* cs, int dt, int N, int H, int W,
+                            int C, float flow_scale, int tiles, cudaStream_t s) {
+  CUtensorMap tm{};
+  if (dt == LCGAN_BF16 && use_tma() && tile8() && tmaw::make_map(&tm, x, N, H, W, C, kFW, 20, true))
+    warp_tile_gather_kernel<bf16, false, true, 8><<<N * ((H + 7) / 8) * ((W + kTW - 1) / kTW), kTW * 8, kFwdSmem8, s>>>(
+        tm, (const bf16*)x, flow, nullptr, (bf16*)out, nullptr, H, W, C, flow_scale, cs);
+  else if (dt == LCGAN_BF16 && use_tma() && tmaw::make_map(&tm, x, N, H, W, C, kFW, kFH, true))
+    warp_tile_gather_kernel<bf16, false, true><<<tiles, kTileThreads, kFwdSmem, s>>>(
+        tm, (const bf16*)x, flow, nullptr, (bf16*)out, nullptr, H, W, C, flow_scale, cs);
+  else if (dt == LCGAN_BF16)
+    warp_tile_gather_kernel<bf16, false><<<tiles, kTileThreads, kFwdSmem, s>>>(
+        tm, (const bf16*)x, flow, nullptr, (bf16*)out, nullptr, H, W, C, flow_scale, cs);
+  else
+    warp_tile_gather_kernel<float, false><<<tiles, kTileThreads, kFwdSmem, s>>>(
+        tm, (const float*)x, flow, nullptr, (float*)out, nullptr, H, W, C, flow_scale, cs);
 }
 
 extern "C" int lcgan_warp_fwd(const void* x, const float* flow, void* out, int dt, int N, int H, int W, int C,
@@ -798,12 +875,7 @@ extern "C" int lcgan_warp_fwd(const void* x, const float* flow, void* out, int d
   if (tile_eligible(dt, H, W, C)) {
     LCGAN_CHECK(tile_kernels_ready() == 0, "warp_fwd: cannot opt in to %d bytes of shared memory", kDxSmem);
     const int tiles = N * ((H + kTH - 1) / kTH) * ((W + kTW - 1) / kTW);
-    if (dt == LCGAN_BF16)
-      warp_tile_gather_kernel<bf16, false><<<tiles, kTileThreads, kFwdSmem, s>>>(
-          (const bf16*)x, flow, nullptr, (bf16*)out, nullptr, H, W, C, flow_scale);
-    else
-      warp_tile_gather_kernel<float, false><<<tiles, kTileThreads, kFwdSmem, s>>>(
-          (const float*)x, flow, nullptr, (float*)out, nullptr, H, W, C, flow_scale);
+    launch_tile_fwd(x, flow, out, nullptr, dt, N, H, W, C, flow_scale, tiles, s);
     LCGAN_LAUNCH_CHECK();
     return 0;
   }
@@ -829,12 +901,7 @@ extern "C" int lcgan_warp_fwd_cs(const void* x, const float* flow, void* out, co
   LCGAN_CHECK(tile_kernels_ready() == 0, "warp_fwd_cs: cannot opt in to %d bytes of shared memory", kDxSmem);
   cudaStream_t s = (cudaStream_t)stream;
   const int tiles = N * ((H + kTH - 1) / kTH) * ((W + kTW - 1) / kTW);
-  if (dt == LCGAN_BF16)
-    warp_tile_gather_kernel<bf16, false><<<tiles, kTileThreads, kFwdSmem, s>>>(
-        (const bf16*)x, flow, nullptr, (bf16*)out, nullptr, H, W, C, flow_scale, cs);
-  else
-    warp_tile_gather_kernel<float, false><<<tiles, kTileThreads, kFwdSmem, s>>>(
-        (const float*)x, flow, nullptr, (float*)out, nullptr, H, W, C, flow_scale, cs);
+  launch_tile_fwd(x, flow, out, cs, dt, N, H, W, C, flow_scale, tiles, s);
   LCGAN_LAUNCH_CHECK();
   return 0;
 }
@@ -897,17 +964,30 @@ extern "C" int lcgan_warp_bwd_tiled(const void* x, const float* flow, const void
     LCGAN_CUDA(cudaMemsetAsync(flag, 0, 4 * sizeof(int), s));
     const int64_t npix = (int64_t)N * H * W;
     const int bgrid = (int)(npix / 256 + 1 < 148LL * 8 ? npix / 256 + 1 : 148LL * 8);
-    warp_bbox_kernel<<<bgrid, 256, 0, s>>>(flow, N, H, W, flow_scale, bbox);
-    if (dt == LCGAN_BF16) {
+    CUtensorMap tmx{}, tmg{};
+    const bool tma = dt == LCGAN_BF16 && use_tma() && tmaw::make_map(&tmx, x, N, H, W, C, kFW, tile8() ? 20 : kFH, true) &&
+                     tmaw::make_map(&tmg, dout, N, H, W, C, kBW, kBH, true);
+    // the contributor boxes come from the flow-gradient pass on the TMA path, from a pre-pass otherwise
+    if (!tma) warp_bbox_kernel<<<bgrid, 256, 0, s>>>(flow, N, H, W, flow_scale, bbox);
+    if (tma) {
+      if (tile8())
+        warp_tile_gather_kernel<bf16, true, true, 8><<<N * ((H + 7) / 8) * ((W + kTW - 1) / kTW), kTW * 8, kFwdSmem8, s>>>(
+            tmx, (const bf16*)x, flow, (const bf16*)dout, nullptr, dflow, H, W, C, flow_scale, nullptr, bbox);
+      else
+        warp_tile_gather_kernel<bf16, true, true><<<tiles, kTileThreads, kFwdSmem, s>>>(
+            tmx, (const bf16*)x, flow, (const bf16*)dout, nullptr, dflow, H, W, C, flow_scale, nullptr, bbox);
+      warp_tile_dx_kernel<bf16, true><<<tiles, kTileThreads, kDxSmem, s>>>(tmg, flow, (const bf16*)dout, (bf16*)dx, bbox,
+                                                                          flag, H, W, C, flow_scale);
+    } else if (dt == LCGAN_BF16) {
       warp_tile_gather_kernel<bf16, true><<<tiles, kTileThreads, kFwdSmem, s>>>(
-          (const bf16*)x, flow, (const bf16*)dout, nullptr, dflow, H, W, C, flow_scale);
-      warp_tile_dx_kernel<bf16><<<tiles, kTileThreads, kDxSmem, s>>>(flow, (const bf16*)dout, (bf16*)dx, bbox, flag,
+          tmx, (const bf16*)x, flow, (const bf16*)dout, nullptr, dflow, H, W, C, flow_scale);
+      warp_tile_dx_kernel<bf16><<<tiles, kTileThreads, kDxSmem, s>>>(tmg, flow, (const bf16*)dout, (bf16*)dx, bbox, flag,
                                                                     H, W, C, flow_scale);
     } else {
       warp_tile_gather_kernel<float, true><<<tiles, kTileThreads, kFwdSmem, s>>>(
-          (const float*)x, flow, (const float*)dout, nullptr, dflow, H, W, C, flow_scale);
-      warp_tile_dx_kernel<float><<<tiles, kTileThreads, kDxSmem, s>>>(flow, (const float*)dout, (float*)dx, bbox, flag,
-                                                                     H, W, C, flow_scale);
+          tmx, (const float*)x, flow, (const float*)dout, nullptr, dflow, H, W, C, flow_scale);
+      warp_tile_dx_kernel<float><<<tiles, kTileThreads, kDxSmem, s>>>(tmg, flow, (const float*)dout, (float*)dx, bbox,
+                                                                     flag, H, W, C, flow_scale);
     }
     LCGAN_LAUNCH_CHECK();
     skip = flag;                                          // the rest runs only if a tile gave up

@@ -49,9 +49,9 @@ for w in which:
             y = ops.empty_cl(N, 2, 1024, 1024, torch.float32, dev)
             ops.tapconv(x64, w2, y, plan, None, None, None)
         elif w == "warpf":
-            flow = cl(torch.randn(N, 2, R, R, device=dev) * 0.004); ops.Warp.apply(x, flow, 0.1)
+            flow = cl(torch.nn.functional.interpolate(torch.randn(N, 2, R // 64, R // 64, device=dev) * 0.1, size=(R, R), mode='bilinear')); ops.Warp.apply(x, flow, 0.1)
         elif w == "warpb":
-            flow = cl(torch.randn(N, 2, R, R, device=dev) * 0.004); xr = x.clone().requires_grad_(); fr = flow.clone().requires_grad_()
+            flow = cl(torch.nn.functional.interpolate(torch.randn(N, 2, R // 64, R // 64, device=dev) * 0.1, size=(R, R), mode='bilinear')); xr = x.clone().requires_grad_(); fr = flow.clone().requires_grad_()
             out = ops.Warp.apply(xr, fr, 0.1)
             torch.autograd.grad(out, (xr, fr), g)
         torch.cuda.synchronize()
