@@ -3,6 +3,7 @@
 // One thread handles one 16-byte channel vector of one pixel (V=1 fallback for odd C), so a warp
 // reads/writes contiguous 512-byte runs along the channel-innermost axis.
 #include "common.cuh"
+#include "tma_window.cuh"
 #include <stdlib.h>
 
 namespace {
@@ -148,9 +149,12 @@ box3_strip_kernel(const T* __restrict__ a, const T* __restrict__ mask, T* __rest
 // enough bytes are in flight regardless of instruction scheduling (the strip kernel's 30 dependent
 // vector loads per thread left it latency-bound at 2.2 TB/s).
 constexpr int kBoxTW = 32, kBoxTH = 16, kBoxWW = kBoxTW + 2;   // tile height: 16 (8 with the mask window, 48 KiB static limit)
-template <typename T, bool MASK, int TH>
+// TMA = true (bf16): the window(s) arrive by one bulk tensor copy each (tma_window.cuh; out-of-image pixels zero-filled by
+// the unit) instead of ~10 bounds-checked 16-byte cp.async per thread - about 40 % of this kernel's instructions.
+template <typename T, bool MASK, int TH, bool TMA = false>
 __global__ void __launch_bounds__(kThreads)
-box3_tile_kernel(const T* __restrict__ a, const T* __restrict__ mask, T* __restrict__ out, int H, int W, int C,
+box3_tile_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUtensorMap tmm,
+                 const T* __restrict__ a, const T* __restrict__ mask, T* __restrict__ out, int H, int W, int C,
                  float pre_slope, float pre_gain, float post_slope, float post_gain,
                  const float* __restrict__ cs = nullptr, float* __restrict__ red = nullptr,
                  const T* __restrict__ post_mask = nullptr) {
@@ -163,7 +167,8 @@ box3_tile_kernel(const T* __restrict__ a, const T* __restrict__ mask, T* __restr
   constexpr int E = 16 / sizeof(T);
   constexpr int kBoxWH = TH + 2, SR = TH / 2;               // window height, rows per thread
   constexpr int kWin = kBoxWW * kBoxWH * 64;
-  __shared__ __align__(16) unsigned char sm[MASK ? 2 * kWin : kWin];
+  __shared__ __align__(128) unsigned char sm[MASK ? 2 * kWin : kWin];
+  __shared__ __align__(8) uint64_t bar;
   const int tiles_x = (W + kBoxTW - 1) / kBoxTW, tiles_y = (H + TH - 1) / TH;
   // the channel chunks of a tile are neighbouring CTAs (chunk fastest): they run together and read
   // whole DRAM pages; chunk-major order swept the tensor once per chunk, 64 bytes of every pixel
@@ -173,12 +178,24 @@ box3_tile_kernel(const T* __restrict__ a, const T* __restrict__ mask, T* __restr
   const int tx = t % tiles_x; t /= tiles_x;
   const int ty = t % tiles_y;
   const int b = t / tiles_y;
-  load_window<T, kBoxWW, kBoxWH, 64, kThreads>(sm, a + (int64_t)b * H * W * C, H, W, C, c0, ty * TH - 1, tx * kBoxTW - 1);
-  if constexpr (MASK)   // the activation mask of the backward pass: a is scaled by the leaky-relu slope of mask
-    load_window<T, kBoxWW, kBoxWH, 64, kThreads>(sm + kWin, mask + (int64_t)b * H * W * C, H, W, C, c0,
-                                                 ty * TH - 1, tx * kBoxTW - 1);
-  cp_async_wait_all();
-  __syncthreads();
+  if constexpr (TMA) {
+    static_assert(kWin % 128 == 0, "the mask window must start 128-byte aligned");
+    if (threadIdx.x == 0) {
+      tmaw::bar_init(&bar);
+      tmaw::arm(&bar, MASK ? 2 * kWin : kWin);
+      tmaw::copy(sm, &tma, &bar, c0, tx * kBoxTW - 1, ty * TH - 1, b);
+      if constexpr (MASK) tmaw::copy(sm + kWin, &tmm, &bar, c0, tx * kBoxTW - 1, ty * TH - 1, b);
+    }
+    __syncthreads();                                          // the barrier is initialised
+    tmaw::wait(&bar, 0);
+  } else {
+    load_window<T, kBoxWW, kBoxWH, 64, kThreads>(sm, a + (int64_t)b * H * W * C, H, W, C, c0, ty * TH - 1, tx * kBoxTW - 1);
+    if constexpr (MASK)   // the activation mask of the backward pass: a is scaled by the leaky-relu slope of mask
+      load_window<T, kBoxWW, kBoxWH, 64, kThreads>(sm + kWin, mask + (int64_t)b * H * W * C, H, W, C, c0,
+                                                   ty * TH - 1, tx * kBoxTW - 1);
+    cp_async_wait_all();
+    __syncthreads();
+  }
   const int v = threadIdx.x & 3, xq = (threadIdx.x >> 2) & 31, strip = threadIdx.x >> 7;
   const int ox = tx * kBoxTW + xq;
   float csv[E], racc[E];
@@ -584,6 +601,30 @@ template <typename T> constexpr int vec_of() { return Vec16<T>::N; }
 
 }  // namespace
 
+// the tiled kernel for every flavour (mask / style / reduction / post-mask); bf16 windows arrive by TMA
+static void launch_box_tile(const void* a, const void* mask, void* out, int dt, int N, int H, int W, int C, float pre_slope,
+                            float pre_gain, float post_slope, float post_gain, const float* cs, float* red,
+                            const void* post_mask, cudaStream_t s) {
+  static const bool no_tma = getenv("LCGAN_BOX_NO_TMA") != nullptr;
+  const int cc = dt == LCGAN_BF16 ? 32 : 16;
+  const int th = mask ? 8 : kBoxTH;
+  const dim3 grid(N * ((H + th - 1) / th) * ((W + kBoxTW - 1) / kBoxTW) * (C / cc));
+  CUtensorMap ta{}, tm{};
+  const bool tma = dt == LCGAN_BF16 && !no_tma && tmaw::make_map(&ta, a, N, H, W, C, kBoxWW, th + 2, false) &&
+                   (!mask || tmaw::make_map(&tm, mask, N, H, W, C, kBoxWW, th + 2, false));
+#define BT(T, M, THH, TMA)                                                                                        \
+  box3_tile_kernel<T, M, THH, TMA><<<grid, kThreads, 0, s>>>(ta, tm, (const T*)a, (const T*)mask, (T*)out, H, W, C, \
+                                                             pre_slope, pre_gain, post_slope, post_gain, cs, red,  \
+                                                             (const T*)post_mask)
+  if (dt == LCGAN_BF16) {
+    if (tma) { if (mask) BT(bf16, true, 8, true); else BT(bf16, false, 16, true); }
+    else { if (mask) BT(bf16, true, 8, false); else BT(bf16, false, 16, false); }
+  } else {
+    if (mask) BT(float, true, 8, false); else BT(float, false, 16, false);
+  }
+#undef BT
+}
+
 extern "C" int lcgan_box3(const void* a, const void* mask, void* out, int dt, int N, int H, int W, int C,
                           float pre_slope, float pre_gain, float post_slope, float post_gain, void* stream) {
   LCGAN_CHECK(a && out && N > 0 && H > 0 && W > 0 && C > 0, "box3: bad arguments");
@@ -591,14 +632,7 @@ extern "C" int lcgan_box3(const void* a, const void* mask, void* out, int dt, in
   const int cc = dt == LCGAN_BF16 ? 32 : 16;
   if ((dt == LCGAN_BF16 || dt == LCGAN_F32) && C % cc == 0 && W >= kBoxTW && H >= kBoxTH &&
       getenv("LCGAN_BOX_NO_TILE") == nullptr) {
-    const int th = mask ? 8 : kBoxTH;
-    const dim3 grid(N * ((H + th - 1) / th) * ((W + kBoxTW - 1) / kBoxTW) * (C / cc));
-#define BT(T, M, THH)                                                                                     \
-  box3_tile_kernel<T, M, THH><<<grid, kThreads, 0, s>>>((const T*)a, (const T*)mask, (T*)out, H, W, C,       \
-                                                        pre_slope, pre_gain, post_slope, post_gain)
-    if (dt == LCGAN_BF16) { if (mask) BT(bf16, true, 8); else BT(bf16, false, 16); }
-    else { if (mask) BT(float, true, 8); else BT(float, false, 16); }
-#undef BT
+    launch_box_tile(a, mask, out, dt, N, H, W, C, pre_slope, pre_gain, post_slope, post_gain, nullptr, nullptr, nullptr, s);
   } else if (H % 8 == 0 && (int64_t)N * (H / 8) * W * (C / 8) >= 148LL * 64) {
 #define CALL(T, V)                                                                                   \
   do {                                                                                               \
@@ -632,13 +666,7 @@ extern "C" int lcgan_box3_postmask(const void* a, const void* y, void* out, floa
   LCGAN_CHECK((dt == LCGAN_BF16 || dt == LCGAN_F32) && C % cc == 0 && W >= kBoxTW && H >= kBoxTH,
               "box3_postmask: needs C %% %d == 0, W >= %d, H >= %d (use lcgan_box3 + lcgan_act_bwd otherwise)", cc, kBoxTW, kBoxTH);
   cudaStream_t s = (cudaStream_t)stream;
-  const dim3 grid(N * ((H + kBoxTH - 1) / kBoxTH) * ((W + kBoxTW - 1) / kBoxTW) * (C / cc));
-  if (dt == LCGAN_BF16)
-    box3_tile_kernel<bf16, false, 16><<<grid, kThreads, 0, s>>>((const bf16*)a, nullptr, (bf16*)out, H, W, C, 1.f, 1.f, slope,
-                                                               gain, nullptr, r0, (const bf16*)y);
-  else
-    box3_tile_kernel<float, false, 16><<<grid, kThreads, 0, s>>>((const float*)a, nullptr, (float*)out, H, W, C, 1.f, 1.f,
-                                                                slope, gain, nullptr, r0, (const float*)y);
+  launch_box_tile(a, nullptr, out, dt, N, H, W, C, 1.f, 1.f, slope, gain, nullptr, r0, y, s);
   LCGAN_LAUNCH_CHECK();
   return 0;
 }
@@ -653,14 +681,7 @@ extern "C" int lcgan_box3_cs(const void* a, const void* mask, void* out, const f
   LCGAN_CHECK((dt == LCGAN_BF16 || dt == LCGAN_F32) && C % cc == 0 && W >= kBoxTW && H >= kBoxTH,
               "box3_cs: needs C %% %d == 0, W >= %d, H >= %d (use lcgan_box3 + lcgan_modulate otherwise)", cc, kBoxTW, kBoxTH);
   cudaStream_t s = (cudaStream_t)stream;
-  const int th = mask ? 8 : kBoxTH;
-  const dim3 grid(N * ((H + th - 1) / th) * ((W + kBoxTW - 1) / kBoxTW) * (C / cc));
-#define BT(T, M, THH)                                                                                     \
-  box3_tile_kernel<T, M, THH><<<grid, kThreads, 0, s>>>((const T*)a, (const T*)mask, (T*)out, H, W, C,       \
-                                                        pre_slope, pre_gain, post_slope, post_gain, cs, red)
-  if (dt == LCGAN_BF16) { if (mask) BT(bf16, true, 8); else BT(bf16, false, 16); }
-  else { if (mask) BT(float, true, 8); else BT(float, false, 16); }
-#undef BT
+  launch_box_tile(a, mask, out, dt, N, H, W, C, pre_slope, pre_gain, post_slope, post_gain, cs, red, nullptr, s);
   LCGAN_LAUNCH_CHECK();
   return 0;
 }

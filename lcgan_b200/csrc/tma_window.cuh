@@ -18,13 +18,20 @@ __device__ __forceinline__ void bar_init(uint64_t* bar) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(bar)));
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-// called by ONE thread: arm the barrier with the box size and start the copy of box (c0, x0, y0, b)
-__device__ __forceinline__ void load(void* dst, const CUtensorMap* map, uint64_t* bar, uint32_t bytes, int c0, int x0, int y0,
-                                     int b) {
+// called by ONE thread: arm the barrier with the bytes of all the copies of this phase ...
+__device__ __forceinline__ void arm(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
+}
+// ... and start the copy of box (c0, x0, y0, b)
+__device__ __forceinline__ void copy(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int x0, int y0, int b) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(s32(dst)), "l"(map), "r"(s32(bar)), "r"(c0), "r"(x0), "r"(y0), "r"(b) : "memory");
+}
+__device__ __forceinline__ void load(void* dst, const CUtensorMap* map, uint64_t* bar, uint32_t bytes, int c0, int x0, int y0,
+                                     int b) {
+  arm(bar, bytes);
+  copy(dst, map, bar, c0, x0, y0, b);
 }
 __device__ __forceinline__ void wait(uint64_t* bar, uint32_t parity) {
   asm volatile(

@@ -1,5 +1,5 @@
 """Micro-benchmark of individual launches at real 1024^2 shapes (CUDA events, L2 flushed by size)."""
-import sys, torch
+import os, sys, torch
 sys.path.insert(0, '.')
 from lcgan_b200 import ops, plans, _lib
 ops.set_precision("bf16")
@@ -7,6 +7,13 @@ dev = 'cuda'
 def cl(x): return x.contiguous(memory_format=torch.channels_last)
 def timeit(fn, n=5):
     fn(); torch.cuda.synchronize()
+    if os.environ.get("PROF"):
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as pr:
+            for _ in range(n): fn()
+            torch.cuda.synchronize()
+        for e in sorted(pr.key_averages(), key=lambda e: -e.device_time_total)[:8]:
+            print(f"      {e.device_time_total / n / 1e3:8.3f} ms  x{e.count // n:3d}  {e.key[:90]}")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(n): fn()
