@@ -55,6 +55,8 @@ struct TcParams {
   const float* noise;                           // [OH][OW] f32 plane added before the activation (or null)
   float noise_scale;
   int OW;
+  int tiles_w_px;                               // rowshare == 5: output width (columns past it are not stored)
+  int dbg;                                    // LCGAN_TC_DEBUG timing experiments (1: no MMAs, 2: no TMA loads, 4: no stores)
 };
 
 struct WgParams {
@@ -222,6 +224,11 @@ __device__ __forceinline__ Smem carve(uint8_t* raw, int stages, int a_bytes, int
 // ---------------------------------------------------------------------------------------------
 // forward-type kernel
 // ---------------------------------------------------------------------------------------------
+// LEAN: the epilogue of the dominant HBM-bound shapes (one 32-channel tile, bf16 output, unit output stride, no
+// residual / noise / blocked layout, resident-weight modes) with everything per-tile hoisted: ncu had the generic
+// epilogue at ~300 instructions per thread and tile for 16 outputs (8 warps x 300 = 2 400 of the 2 575 warp
+// instructions a tile costs; 644 issue cycles per scheduler against the 690-cycle HBM budget of a tile).
+template <bool LEAN>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmw, const TcParams p,
                   void* __restrict__ y, const float* __restrict__ rowscale, const float* __restrict__ bias,
@@ -273,6 +280,24 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
           mbar_expect_tx(&s.full[st], box_bytes, leader);
           tma_load_4d(s.a(st), &tmx, &s.full[st], 0, tw * p.wt, th * p.ht, tb, leader);
         }
+      } else if (p.rowshare == 5) {
+        // dx-on-N mode (see the MMA issuer): a 16-pixel-wide, (8+2)-row box per tile, 14 output columns of it live;
+        // resident weights ordered [dy][dx] so that the three dx taps of one dy are ONE B operand of 3*Cout rows
+        mbar_expect_tx(s.wfull, 9 * wtile, leader);
+        for (int dyi = 0; dyi < 3; ++dyi)
+          for (int j = 0; j < 3; ++j)
+            tma_load_2d(s.wres + (dyi * 3 + j) * wtile, &tmw, s.wfull, p.grp_wtap[j][dyi] * p.Cin, 0, leader);
+        const uint32_t box_bytes = 16u * 10u * p.kc * 2;
+        const int per_img = p.tiles_w * p.tiles_h;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++g) {
+          const int tb = tile / per_img, tr = tile - tb * per_img;
+          const int th = tr / p.tiles_w, tw = tr - th * p.tiles_w;
+          const int st = g % p.stages, ph = (g / p.stages) & 1;
+          mbar_wait(&s.empty[st], ph ^ 1);
+          if (p.dbg & 2) { if (leader) mbar_arrive(&s.full[st]); continue; }
+          mbar_expect_tx(&s.full[st], box_bytes, leader);
+          tma_load_4d(s.a(st), &tmx, &s.full[st], 0, tw * 14 - 1, th * 8 - 1, tb, leader);
+        }
       } else if (p.rowshare == 3) {
         // haloed small-channel mode: resident weights, and ONE TMA box per tile - the (wt+2) x (ht+2) pixel
         // neighbourhood of the 8 x 16 lattice tile.  Tap (dy, dx) is read by the MMA straight out of that
@@ -290,6 +315,7 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
           const int tw = tile & (p.tiles_w - 1), th = (tile >> p.lw) & (p.tiles_h - 1), tb = tile >> (p.lw + p.lh);
           const int st = g % p.stages, ph = (g / p.stages) & 1;
           mbar_wait(&s.empty[st], ph ^ 1);
+          if (p.dbg & 2) { if (leader) mbar_arrive(&s.full[st]); continue; }
           mbar_expect_tx(&s.full[st], box_bytes, leader);
           tma_load_4d(s.a(st), &tmx, &s.full[st], 0, tw * p.wt - 1, th * p.ht - 1, tb, leader);
         }
@@ -385,6 +411,43 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
           umma_commit(&s.empty[st], leader);
           umma_commit(&s.done[as], leader);
         }
+      } else if (p.rowshare == 5) {
+        // dx-on-N: D'[(m, n'), (dx, o)] = sum_dy sum_c X[m + dy - 1, n', c] W[o, dy, dx, c] - one MMA per (dy, K step)
+        // with N = 3 * Cout; the epilogue adds the three dx column groups of neighbouring pixels.  Timing the haloed
+        // mode with its memory traffic switched off (LCGAN_TC_DEBUG) showed its 18 N = 32 MMAs per tile alone take the
+        // kernel's whole duration: ~64 cycles each, the cost of streaming the 4 KB A operand out of shared memory,
+        // not of the 16-cycle tensor work.  Here an A operand is read once per dy instead of once per tap.
+        mbar_wait(s.wfull, 0);
+        const uint32_t idesc5 = make_idesc(3 * p.BN, false, false);
+        const uint32_t a_dy = (uint32_t)(16 * p.kc * 2) >> 4;             // one stored row of 16 pixels, 16-byte units
+        const uint32_t w_dy = (3 * wtile) >> 4;
+        const uint64_t bd0 = make_desc(smem_u32(s.wres), 16, 16 * p.kc, p.kc);
+        const int nacc = 3 * p.BN <= kMaxBN ? kAccStages : 2;
+        const uint32_t acc_stride = (uint32_t)(kAccStages * kMaxBN / nacc);
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li, ++g) {
+          if ((li & 1) != mine) continue;
+          const int as = li % nacc, aph = (li / nacc) & 1;
+          mbar_wait(&s.acc_empty[as], aph ^ 1);
+          const int st = g % p.stages, ph = (g / p.stages) & 1;
+          mbar_wait(&s.full[st], ph);
+          tc_fence_after();
+          const uint32_t tacc = tmem_base + (uint32_t)as * acc_stride;
+          const uint64_t ad0 = make_desc(smem_u32(s.a(st)), 16, 16 * p.kc, p.kc);
+          if (!(p.dbg & 1))
+#pragma unroll
+          for (int dyi = 0; dyi < 3; ++dyi) {
+            const uint64_t ad = ad0 + (uint32_t)(dyi * a_dy);
+            const uint64_t bd = bd0 + (uint32_t)(dyi * w_dy);
+            umma_f16(tacc, ad, bd, idesc5, dyi != 0, leader);
+            umma_f16(tacc, ad + 2, bd + 2, idesc5, 1, leader);
+            if (p.kc == 64) {
+              umma_f16(tacc, ad + 4, bd + 4, idesc5, 1, leader);
+              umma_f16(tacc, ad + 6, bd + 6, idesc5, 1, leader);
+            }
+          }
+          umma_commit(&s.empty[st], leader);
+          umma_commit(&s.done[as], leader);
+        }
       } else if (p.rowshare == 3) {
         mbar_wait(s.wfull, 0);
         const uint32_t row16 = (uint32_t)(p.kc * 2) >> 4;               // one stored pixel, in 16-byte units
@@ -402,6 +465,7 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
           // 8-row core groups = the 8 pixels of one lattice row; consecutive groups one stored row apart
           const uint64_t ad0 = make_desc(smem_u32(s.a(st)), 16, (uint32_t)(p.wt + 2) * p.kc * 2, p.kc);
           uint32_t first = 0;
+          if (!(p.dbg & 1))
 #pragma unroll
           for (int j = 0; j < 3; ++j) {
 #pragma unroll
@@ -526,6 +590,129 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
       }
     }
     int li = 0;
+    if constexpr (LEAN) if (p.rowshare == 5) {
+      // accumulator row r = m * 16 + n' (8 rows of 16 stored pixels): lane n' = 1..14 owns output column n0 + n' - 1 and
+      // adds dx = 0 from its left neighbour's row, dx = 1 from its own, dx = 2 from its right neighbour's
+      const int m = r >> 4, np = r & 15;
+      const int nacc = 3 * p.BN <= kMaxBN ? kAccStages : 2;
+      const uint32_t acc_stride = (uint32_t)(kAccStages * kMaxBN / nacc);
+      const float slope = p.slope;
+      const int per_img = p.tiles_w * p.tiles_h;
+      const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li) {
+        if ((li & 1) != eg) continue;
+        const int b = tile / per_img, tr = tile - b * per_img;
+        const int th = tr / p.tiles_w, tw = tr - th * p.tiles_w;
+        const int n = tw * 14 + np - 1, mm = th * 8 + m;
+        const bool live = np >= 1 && np <= 14 && n < p.tiles_w_px;
+        bf16* const yp = reinterpret_cast<bf16*>(y) + (long long)b * p.ys_n + (long long)mm * p.ys_h + (long long)n * p.ys_w;
+        if (cache && rowscale && b != cached_b) {
+          const float4* rs = reinterpret_cast<const float4*>(rowscale + (long long)b * 32 + half * 16);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 sc = rs[i];
+            csc[4 * i] = sc.x * asg; csc[4 * i + 1] = sc.y * asg; csc[4 * i + 2] = sc.z * asg; csc[4 * i + 3] = sc.w * asg;
+          }
+          cached_b = b;
+        }
+        const int as = li % nacc, aph = (li / nacc) & 1;
+        mbar_wait(&s.done[as], aph);
+        tc_fence_after();
+        const uint32_t tcol = tlane + (uint32_t)as * acc_stride;
+        for (int c = half * 16; c < p.BN; c += 32) {
+          uint32_t v0[16], v1[16], v2[16];
+          tmem_ld16(tcol + (uint32_t)c, v0);
+          tmem_ld16(tcol + (uint32_t)(p.BN + c), v1);
+          tmem_ld16(tcol + (uint32_t)(2 * p.BN + c), v2);
+          tmem_ld_wait();
+          if (c + 32 >= p.BN) {
+            // last chunk is in registers: hand the accumulator back before the arithmetic and the stores
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s.acc_empty[as]);
+          }
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float lft = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[i]), 1);
+            const float rgt = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[i]), 1);
+            f[i] = lft + __uint_as_float(v1[i]) + rgt;
+          }
+          if (live) {
+            if (cache) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = fmaf(f[i], csc[i], cbi[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float4 sc = make_float4(asg, asg, asg, asg), bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (rowscale) {
+                  const float4 t4 = *reinterpret_cast<const float4*>(rowscale + (long long)b * p.Cout + c + 4 * i);
+                  sc = make_float4(t4.x * asg, t4.y * asg, t4.z * asg, t4.w * asg);
+                }
+                if (bias) {
+                  const float4 t4 = *reinterpret_cast<const float4*>(bias + c + 4 * i);
+                  bb = make_float4(t4.x * bsg, t4.y * bsg, t4.z * bsg, t4.w * bsg);
+                }
+                f[4 * i] = fmaf(f[4 * i], sc.x, bb.x); f[4 * i + 1] = fmaf(f[4 * i + 1], sc.y, bb.y);
+                f[4 * i + 2] = fmaf(f[4 * i + 2], sc.z, bb.z); f[4 * i + 3] = fmaf(f[4 * i + 3], sc.w, bb.w);
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], f[i] * slope);
+            Vec16<bf16> o0v, o1v;
+            o0v.pack(f); o1v.pack(f + 8);
+            if (!(p.dbg & 4)) { o0v.store(yp + c); o1v.store(yp + c + 8); }
+          }
+        }
+      }
+      li = -1;                                                // (done: skip the other forms below)
+    }
+    if (li < 0) {
+    } else if constexpr (LEAN) {
+      // per-thread constants: element offset of (row of the tile, 16-channel half), tile steps
+      bf16* const ybase = reinterpret_cast<bf16*>(y) + (long long)mi * p.ys_h + (long long)ni * p.ys_w + half * 16;
+      const long long wstep = (long long)p.wt * p.ys_w, hstep = (long long)p.ht * p.ys_h;
+      const float slope = p.slope;
+      const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 16);
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li) {
+        if ((li & 1) != eg) continue;
+        const int tw = tile & (p.tiles_w - 1), th = (tile >> p.lw) & (p.tiles_h - 1), tb = tile >> (p.lw + p.lh);
+        const int b = tb * p.nt + bi;
+        const bool live = b < p.N;
+        if (rowscale && live && b != cached_b) {
+          const float4* rs = reinterpret_cast<const float4*>(rowscale + (long long)b * 32 + half * 16);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 sc = rs[i];
+            csc[4 * i] = sc.x * asg; csc[4 * i + 1] = sc.y * asg; csc[4 * i + 2] = sc.z * asg; csc[4 * i + 3] = sc.w * asg;
+          }
+          cached_b = b;
+        }
+        const int as = li % kAccStages, aph = (li / kAccStages) & 1;
+        mbar_wait(&s.done[as], aph);
+        tc_fence_after();
+        uint32_t v[16];
+        tmem_ld16(tcol + (uint32_t)(as * kMaxBN), v);
+        tmem_ld_wait();
+        // the accumulator is in registers: hand the stage back before the arithmetic and the stores
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s.acc_empty[as]);
+        if (live) {
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float t = fmaf(__uint_as_float(v[i]), csc[i], cbi[i]);
+            f[i] = fmaxf(t, t * slope);
+          }
+          bf16* yp = ybase + (long long)b * p.ys_n + th * hstep + tw * wstep;
+          Vec16<bf16> o0v, o1v;
+          o0v.pack(f); o1v.pack(f + 8);
+          if (!(p.dbg & 4)) { o0v.store(yp); o1v.store(yp + 8); }
+        }
+      }
+    } else
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li) {
       if ((li & 1) != eg) continue;
       int nt_i = 0, t = tile;
@@ -947,6 +1134,7 @@ struct WhParams {
   long long w_ld;
   float scale;
   int* sems;
+  int dyn;                                      // dy on N: one MMA per K step covers the three dy taps too (see the kernel)
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -977,20 +1165,46 @@ tapconv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmg, const __grid_
 
   if (warp == 0) {
     const uint32_t leader = elect_one();
-    const uint32_t tx_bytes = (uint32_t)(WT + 2) * (HT + 2) * rowx + (uint32_t)WT * HT * rowg;
+    // dyn: the row halo moves from X to G (X box (WT+2) x HT, G box WT x (HT+2))
+    const uint32_t tx_bytes = p.dyn ? (uint32_t)(WT + 2) * HT * rowx + (uint32_t)WT * (HT + 2) * rowg
+                                    : (uint32_t)(WT + 2) * (HT + 2) * rowx + (uint32_t)WT * HT * rowg;
     for (int kb = 0; kb < nkb; ++kb) {
       const int st = kb % p.stages, ph = (kb / p.stages) & 1;
       mbar_wait(&s.empty[st], ph ^ 1);
       const int t = t_begin + kb;
       const int tw = t & (p.tiles_w - 1), th = (t >> p.lw) & (p.tiles_h - 1), tb = t >> (p.lw + p.lh);
       mbar_expect_tx(&s.full[st], tx_bytes, leader);
-      tma_load_4d(s.a(st), &tmx, &s.full[st], 0, tw * WT - 1, th * HT - 1, tb, leader);
-      tma_load_4d(s.b(st), &tmg, &s.full[st], 0, tw * WT, th * HT, tb, leader);
+      tma_load_4d(s.a(st), &tmx, &s.full[st], 0, tw * WT - 1, th * HT - (p.dyn ? 0 : 1), tb, leader);
+      tma_load_4d(s.b(st), &tmg, &s.full[st], 0, tw * WT, th * HT - (p.dyn ? 1 : 0), tb, leader);
     }
   } else if (warp == 1) {
     const uint32_t leader = elect_one();
     const uint32_t idesc = make_idesc(p.Cout, true, true);
     const uint32_t row16 = rowx >> 4, pitch16 = (uint32_t)(WT + 2) * row16;
+    if (p.dyn) {
+      // dW[o][dy,dx][c] = sum_q X[q + (0, dx-1), c] G[q - (dy-1, 0), o]: with q = the X row, the dy = 2, 1, 0 views of G
+      // start one stored lattice row (8 pixels) apart, so - like the dx views of X on M - they are the consecutive
+      // N blocks of ONE MN-major B operand (LBO = 8 pixels): D^T[(dx, c) x (2-dy, o)], 8 (16 for 64 channels) MMAs
+      // of N = 3 * Cout per tile instead of 24 (48) of N = Cout.  The N = Cout form ran at ~53-61 cycles per MMA
+      // whatever N was - streaming the 4 KB A operand out of shared memory - and bounded the kernel (1.31 ms for
+      // 32 -> 32 @1024^2 against 0.66 ms of HBM time).
+      const uint32_t idesc3 = make_idesc(3 * p.Cout, true, true);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int st = kb % p.stages, ph = (kb / p.stages) & 1;
+        mbar_wait(&s.full[st], ph);
+        tc_fence_after();
+        const uint64_t ad0 = make_desc(smem_u32(s.a(st)), rowx, (uint32_t)(WT + 2) * rowx, p.kcx);
+        const uint64_t bd0 = make_desc(smem_u32(s.b(st)), 8 * rowg, 8 * rowg, p.kcg);
+#pragma unroll
+        for (int k = 0; k < HT / 2; ++k) {
+          const uint64_t ad = ad0 + (uint32_t)(2 * k * pitch16);
+          const uint64_t bd = bd0 + (uint32_t)(k * 16 * (rowg >> 4));
+          umma_f16(tmem_base, ad, bd, idesc3, (kb | k) != 0, leader);
+          if (nh == 2) umma_f16(tmem_base + (uint32_t)(3 * p.Cout), ad + 2 * row16, bd, idesc3, (kb | k) != 0, leader);
+        }
+        umma_commit(&s.empty[st], leader);
+      }
+    } else
     for (int kb = 0; kb < nkb; ++kb) {
       const int st = kb % p.stages, ph = (kb / p.stages) & 1;
       mbar_wait(&s.full[st], ph);
@@ -1028,10 +1242,12 @@ tapconv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmg, const __grid_
         const int dxi = nh == 2 ? 2 * h + r / 64 : r / 32;
         const int c = nh == 2 ? r % 64 : r % 32;
         const bool live = dxi < 3 && nkb > 0;
+        // dyn: accumulator h holds the N blocks j = 2 - dy side by side
         float* col = dw + (long long)p.grp_wtap[live ? dxi : 0][dyi] * p.Cin + c;
+        const uint32_t acol = p.dyn ? (uint32_t)((h * 3 + (2 - dyi)) * p.Cout) : (uint32_t)((dyi * nh + h) * p.Cout);
         for (int o0 = 0; o0 < p.Cout; o0 += 16) {
           uint32_t v[16];
-          tmem_ld16(trow + (uint32_t)((dyi * nh + h) * p.Cout + o0), v);
+          tmem_ld16(trow + acol + (uint32_t)o0, v);
           tmem_ld_wait();
           if (live) {
 #pragma unroll
@@ -1202,7 +1418,6 @@ static int tapconv_tc_launch(const lcgan_tapconv* d, const void* x, const void* 
   p.N = d->N; p.Cin = d->Cin; p.Cout = d->Cout;
   lattice_tile(d->MW, d->MH, &p.wt, &p.ht, &p.nt);
   p.tiles_w = d->MW / p.wt; p.tiles_h = d->MH / p.ht;
-  const int tiles_b = (d->N + p.nt - 1) / p.nt;
   p.is = d->is; p.os = d->os; p.py = d->py; p.px = d->px;
   p.kc = d->Cin % 64 == 0 ? 64 : 32;
   p.ntaps = d->ntaps; p.kpt = d->Cin / p.kc;
@@ -1244,6 +1459,25 @@ static int tapconv_tc_launch(const lcgan_tapconv* d, const void* x, const void* 
     p.tiles_w = d->MW / p.wt; p.tiles_h = d->MH / p.ht;
     p.wres_bytes = (9 * cperiod * d->Cin * 2 + 1023) & ~1023;
     p.a_bytes = ((p.wt + 1) * (p.ht + 1) * p.kc * 2 + 1023) & ~1023;
+    p.b_bytes = 0;
+    p.stages = (kMaxSmem - 2048 - p.wres_bytes) / p.a_bytes;
+    if (p.stages > 12) p.stages = 12;
+    p.stages &= ~1;
+    smem_bytes = 1024 + p.wres_bytes + p.stages * p.a_bytes + 256;
+  } else if (full3x3 && (d->Cin == 32 || d->Cin == 64) && (d->Cout == 32 || d->Cout == 64) && d->MW >= 16 &&
+             d->MH % 8 == 0 && d->os == 1 && d->px == 0 && d->py == 0 && cblk == 0 && !p.y_f32 && !residual && !d->noise &&
+             getenv("LCGAN_DXN") != nullptr) {
+    // dx-on-N mode (OPT-IN, LCGAN_DXN=1): 16 stored x 8 rows per tile (14 live output columns), one (16) x (8+2) box per
+    // tile, weights resident as three [dx][Cout] x Cin operands (one per dy).  Measured on the B200 (32 -> 32 @1024^2,
+    // batch 32): its MMA chain costs 0.11 ms where the nine-tap haloed mode's costs 0.67 ms, but the epilogue's two
+    // shuffles per output and three TMEM loads per chunk make the epilogue skeleton alone 0.99 ms (0.43 ms there):
+    // 1.46 ms against 1.06 ms end to end.  Kept, tested, for the TMA-store epilogue that would make it pay.
+    p.rowshare = 5;
+    p.wt = 16; p.ht = 8; p.nt = 1;
+    p.tiles_w = (d->MW + 13) / 14; p.tiles_h = d->MH / 8;
+    p.tiles_w_px = d->MW;
+    p.wres_bytes = 9 * p.BN * d->Cin * 2;
+    p.a_bytes = 16 * 10 * p.kc * 2;
     p.b_bytes = 0;
     p.stages = (kMaxSmem - 2048 - p.wres_bytes) / p.a_bytes;
     if (p.stages > 12) p.stages = 12;
@@ -1294,18 +1528,29 @@ static int tapconv_tc_launch(const lcgan_tapconv* d, const void* x, const void* 
   CUtensorMap tmx, tmw;
   if (int e = make_act_map(&tmx, x, d->N, d->IH, d->IW, d->Cin, p.wt, p.ht, p.nt, d->is, p.kc,
                            p.rowshare == 4 ? 1 : (p.rowshare ? 2 : 0), p.rowshare == 4 ? 1 : (p.rowshare == 3 ? 2 : 0))) return e;
+  const int tiles_img = (d->N + p.nt - 1) / p.nt;          // (the small-channel modes reset nt to 1)
   if (int e = make_w_map(&tmw, w2, d->Cout, d->w_ld, p.rowshare == 4 ? cperiod : p.BN, p.kc)) return e;
 
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(tapconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    attr_err = cudaFuncSetAttribute(tapconv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(tapconv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
   });
   LCGAN_CHECK(attr_err == cudaSuccess, "tapconv_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(attr_err));
   p.n_tiles = (d->Cout + p.BN - 1) / p.BN;
-  p.total_tiles = p.tiles_w * p.tiles_h * tiles_b * p.n_tiles;
+  p.total_tiles = p.tiles_w * p.tiles_h * tiles_img * p.n_tiles;
   const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();   // persistent: one CTA per SM
-  tapconv_tc_kernel<<<grid, kFwdThreads, smem_bytes, (cudaStream_t)stream>>>(tmx, tmw, p, y, rowscale, bias, residual);
+  static const int dbg = getenv("LCGAN_TC_DEBUG") ? atoi(getenv("LCGAN_TC_DEBUG")) : 0;
+  p.dbg = dbg;
+  static const bool no_lean = getenv("LCGAN_TC_NO_LEAN") != nullptr;
+  const bool lean = p.rowshare == 5 || !no_lean && p.n_tiles == 1 && p.BN == 32 && d->Cout == 32 && p.cblk == 0 && p.rowshare >= 2 &&
+                    !p.y_f32 && !residual && !p.noise && p.os == 1 && p.px == 0 && p.py == 0;
+  if (lean)
+    tapconv_tc_kernel<true><<<grid, kFwdThreads, smem_bytes, (cudaStream_t)stream>>>(tmx, tmw, p, y, rowscale, bias, residual);
+  else
+    tapconv_tc_kernel<false><<<grid, kFwdThreads, smem_bytes, (cudaStream_t)stream>>>(tmx, tmw, p, y, rowscale, bias, residual);
   LCGAN_LAUNCH_CHECK();
   return 0;
 }
@@ -1368,16 +1613,17 @@ extern "C" int lcgan_tapconv_wgrad_tc(const lcgan_tapconv* d, const void* x, con
       h.tiles_per_split = (h.tiles_total + hs - 1) / hs;
       hs = (h.tiles_total + h.tiles_per_split - 1) / h.tiles_per_split;
       h.kcx = d->Cin; h.kcg = d->Cout;
-      h.x_bytes = (10 * 18 * h.kcx * 2 + 1023) & ~1023;
-      h.g_bytes = 8 * 16 * h.kcg * 2;
+      h.dyn = getenv("LCGAN_WG_NO_DYN") == nullptr;
+      h.x_bytes = ((h.dyn ? 10 * 16 : 10 * 18) * h.kcx * 2 + 1023) & ~1023;
+      h.g_bytes = ((h.dyn ? 8 * 18 : 8 * 16) * h.kcg * 2 + 1023) & ~1023;
       h.stages = (kMaxSmem - 2048) / (h.x_bytes + h.g_bytes);
       if (h.stages > kWhStagesMax) h.stages = kWhStagesMax;
       h.w_ld = d->w_ld; h.scale = scale; h.sems = nullptr;
       if (lcgan_det_enabled()) LCGAN_CUDA(cudaGetSymbolAddress((void**)&h.sems, g_sems));
       const int smem = 1024 + h.stages * (h.x_bytes + h.g_bytes) + 256;
       CUtensorMap tmgh, tmxh;
-      if (int e = make_act_map(&tmgh, g, d->N, d->OH, d->OW, d->Cout, 8, 16, 1, 1, h.kcg)) return e;
-      if (int e = make_act_map(&tmxh, x, d->N, d->IH, d->IW, d->Cin, 8, 16, 1, 1, h.kcx, 2, 2)) return e;
+      if (int e = make_act_map(&tmgh, g, d->N, d->OH, d->OW, d->Cout, 8, 16, 1, 1, h.kcg, h.dyn ? 2 : 0, 0)) return e;
+      if (int e = make_act_map(&tmxh, x, d->N, d->IH, d->IW, d->Cin, 8, 16, 1, 1, h.kcx, h.dyn ? 0 : 2, 2)) return e;
       static std::once_flag once3;
       static cudaError_t attr_err3 = cudaSuccess;
       std::call_once(once3, [] {

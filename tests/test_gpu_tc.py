@@ -57,6 +57,9 @@ CASES = [  # kind, k, N, Cin, Cout, H, W
     # side of a tile, one tile per image, 16 / 64 output channels, many images, non-square maps
     ("s1", 3, 3, 32, 16, 16, 8), ("s1", 3, 2, 32, 64, 32, 16), ("s1", 3, 33, 64, 64, 16, 32), ("s1", 3, 2, 32, 32, 256, 256),
     ("s1", 3, 2, 64, 48, 64, 128),
+    # widths that are not multiples of the tile width, a single row of tiles, mixed 32 / 64 channel counts
+    ("s1", 3, 3, 32, 32, 8, 24), ("s1", 3, 2, 64, 64, 24, 40), ("s1", 3, 1, 64, 32, 40, 72), ("s1", 3, 2, 32, 64, 8, 16),
+    ("s1", 3, 5, 32, 32, 64, 1024),
 ]
 
 
@@ -87,6 +90,24 @@ def test_tc_forward_matches_simt(case, out_f32):
     tol = 1e-5 if out_f32 else 4e-3
     assert rel_l2(b, a) < tol, f"{case}: {rel_l2(b, a)}"
     assert rel_l2(b2, a2) < tol, f"{case} residual: {rel_l2(b2, a2)}"
+
+
+@pytest.mark.parametrize("case", [("s1", 3, 2, 32, 32, 32, 32), ("s1", 3, 33, 64, 64, 16, 32), ("s1", 3, 2, 32, 32, 256, 256),
+                                  ("s1", 3, 3, 32, 32, 8, 24), ("s1", 3, 2, 64, 64, 24, 40), ("s1", 3, 1, 64, 32, 40, 72),
+                                  ("s1", 3, 2, 32, 64, 8, 16), ("s1", 3, 5, 32, 32, 64, 1024)])
+def test_tc_forward_dx_on_n_mode_matches(case, monkeypatch):
+    """The opt-in dx-on-N mode (LCGAN_DXN=1: one MMA per dy with N = 3 * Cout, the epilogue adds the dx column groups of
+    neighbouring pixels; conv_tc.cu explains why it is not the default) against the CUDA-core path."""
+    monkeypatch.setenv("LCGAN_DXN", "1")
+    test_tc_forward_matches_simt(case, False)
+
+
+@pytest.mark.parametrize("case", [("s1", 3, 2, 32, 32, 32, 32), ("s1", 3, 33, 64, 64, 16, 32), ("s1", 3, 2, 32, 64, 32, 16)])
+def test_tc_wgrad_halo_nine_view_form_still_matches(case, monkeypatch):
+    """The haloed weight gradient puts the dy taps on N by default (one MMA per K step); the older form with one MMA per
+    dy stays selectable (LCGAN_WG_NO_DYN=1) and must stay right."""
+    monkeypatch.setenv("LCGAN_WG_NO_DYN", "1")
+    test_tc_wgrad_matches_simt(case)
 
 
 @pytest.mark.parametrize("case", [c for c in CASES if c[4] % 32 == 0])
