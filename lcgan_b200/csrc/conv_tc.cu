@@ -265,13 +265,16 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
       if (p.rowshare == 4) {
         // x2 transposed conv, haloed: ONE (wt+1) x (ht+1) box of the input lattice per tile; the four taps
         // (dy, dx in {0,1}) are descriptor offsets into it, the nine live (tap, phase) weight blocks stay resident
+        // Resident weights: per tap the blocks of the phases it reaches, in ACCUMULATOR-COLUMN order.  The accumulator
+        // holds the phases in the order 0, 1, 3, 2 so that each tap's phases are contiguous columns: tap (0,0) -> all
+        // four (one N = 4*Cout MMA), tap (0,1) -> phases 1, 3, tap (1,0) -> phases 3, 2, tap (1,1) -> phase 3.
         const uint32_t wblk = (uint32_t)p.cperiod * p.kc * 2;
         mbar_expect_tx(s.wfull, 9 * wblk, leader);
-        int idx = 0;
-        for (int t = 0; t < 4; ++t)
-          for (int py = t >> 1; py < 2; ++py)
-            for (int px = t & 1; px < 2; ++px, ++idx)
-              tma_load_2d(s.wres + idx * wblk, &tmw, s.wfull, t * p.Cin, (py * 2 + px) * p.cperiod, leader);
+        {
+          const int order[9][2] = {{0, 0}, {0, 1}, {0, 3}, {0, 2}, {1, 1}, {1, 3}, {2, 3}, {2, 2}, {3, 3}};   // (tap, phase)
+          for (int idx = 0; idx < 9; ++idx)
+            tma_load_2d(s.wres + idx * wblk, &tmw, s.wfull, order[idx][0] * p.Cin, order[idx][1] * p.cperiod, leader);
+        }
         const uint32_t box_bytes = (uint32_t)(p.wt + 1) * (p.ht + 1) * p.kc * 2;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++g) {
           const int tw = tile & (p.tiles_w - 1), th = (tile >> p.lw) & (p.tiles_h - 1), tb = tile >> (p.lw + p.lh);
@@ -379,6 +382,7 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
         const uint32_t row16 = (uint32_t)(p.kc * 2) >> 4, pitch = (uint32_t)(p.wt + 1) * row16;
         const uint32_t w_tl = ((uint32_t)p.cperiod * p.kc * 2) >> 4;
         const uint32_t idesc4 = make_idesc(p.cperiod, false, false);          // N = Cout per (tap, phase) block
+        const uint32_t idesc_n2 = make_idesc(2 * p.cperiod, false, false), idesc_n4 = make_idesc(4 * p.cperiod, false, false);
         const uint64_t bd0 = make_desc(smem_u32(s.wres), 16, 16 * p.kc, p.kc);
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li, ++g) {
           if ((li & 1) != mine) continue;
@@ -389,24 +393,23 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
           tc_fence_after();
           const uint32_t tacc = tmem_base + (uint32_t)(as * kMaxBN);
           const uint64_t ad0 = make_desc(smem_u32(s.a(st)), 16, (uint32_t)(p.wt + 1) * p.kc * 2, p.kc);
-          int idx = 0;
+          // one MMA per (tap, K step) over all the phases the tap reaches (N = 4, 2, 2, 1 x Cout): 4 instead of 9
+          // MMAs per K step - an N <= 128 MMA costs ~60 cycles of operand streaming whatever N is
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const uint64_t ad = ad0 + (uint32_t)((t >> 1) * pitch + (t & 1) * row16);
-#pragma unroll
-            for (int py = t >> 1; py < 2; ++py)
-#pragma unroll
-              for (int px = t & 1; px < 2; ++px, ++idx) {
-                const uint32_t tcol = tacc + (uint32_t)((py * 2 + px) * p.cperiod);
-                const uint64_t bd = bd0 + (uint32_t)(idx * w_tl);
-                // tap (0,0) reaches every phase first: it initialises the four accumulators
-                umma_f16(tcol, ad, bd, idesc4, t != 0, leader);
-                umma_f16(tcol, ad + 2, bd + 2, idesc4, 1, leader);
-                if (p.kc == 64) {
-                  umma_f16(tcol, ad + 4, bd + 4, idesc4, 1, leader);
-                  umma_f16(tcol, ad + 6, bd + 6, idesc4, 1, leader);
-                }
-              }
+            const int first_blk = t == 0 ? 0 : (t == 1 ? 4 : (t == 2 ? 6 : 8));
+            const int first_col = t == 0 ? 0 : (t == 1 ? 1 : 2);          // accumulator position of the tap's first phase
+            const uint32_t idn = t == 0 ? idesc_n4 : (t == 3 ? idesc4 : idesc_n2);
+            const uint32_t tcol = tacc + (uint32_t)(first_col * p.cperiod);
+            const uint64_t bd = bd0 + (uint32_t)(first_blk * w_tl);
+            // tap (0,0) reaches every phase first: it initialises the four accumulators
+            umma_f16(tcol, ad, bd, idn, t != 0, leader);
+            umma_f16(tcol, ad + 2, bd + 2, idn, 1, leader);
+            if (p.kc == 64) {
+              umma_f16(tcol, ad + 4, bd + 4, idn, 1, leader);
+              umma_f16(tcol, ad + 6, bd + 6, idn, 1, leader);
+            }
           }
           umma_commit(&s.empty[st], leader);
           umma_commit(&s.done[as], leader);
@@ -746,7 +749,7 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
       const int g0 = li * nkb;
       const bool has0 = !ring || nkb > 1 || (g0 & 1) == 0, has1 = ring && (nkb > 1 || (g0 & 1) == 1);
       // 16 accumulator columns -> scale, bias, activation, residual, store
-      auto finish16 = [&](const uint32_t* v, int oc) {
+      auto finish16 = [&](const uint32_t* v, int oc) {   // oc: first accumulator column of the chunk
         if (live && p.cblk == 4) {
           // narrow blocked form (2-channel x2 transposed conv): columns 0..7 = (py, px, ch); each py half is one
           // float4 = the two horizontally adjacent output pixels x 2 channels
@@ -769,6 +772,8 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
         } else if (live && oc < p.Cout) {
           // o: channel whose rowscale / bias apply; yo: element offset of the chunk inside the pixel
           const int o = p.cblk ? oc % p.cperiod : oc;
+          // (haloed x2 form: accumulator columns hold the phases in the order 0, 1, 3, 2)
+          if (p.rowshare == 4 && oc >= 2 * p.cperiod) oc ^= p.cperiod;
           const long long yo = p.cblk ? (long long)(oc / p.cblk) * p.ys_blk + oc % p.cblk : oc;
           const int crow = p.cblk ? p.cperiod : p.Cout;
           float f[16];
@@ -1451,6 +1456,7 @@ static int tapconv_tc_launch(const lcgan_tapconv* d, const void* x, const void* 
   bool up2_taps = cblk > 4 && d->ntaps == 4 && d->is == 1 && d->os == 1;
   for (int t = 0; up2_taps && t < 4; ++t) up2_taps = d->dy[t] == (t >> 1) && d->dx[t] == (t & 1) && d->wtap[t] == t;
   if (up2_taps && (d->Cin == 32 || d->Cin == 64) && d->Cout <= kMaxBN && d->Cout == 4 * cperiod && cblk == 2 * cperiod &&
+      (cperiod & (cperiod - 1)) == 0 &&
       d->MW % 8 == 0 && d->MH % 16 == 0 && getenv("LCGAN_NO_UP2_HALO") == nullptr) {
     // x2 transposed conv in the blocked form, haloed: 8 x 16 input-lattice tiles, one (8+1) x (16+1) box per tile,
     // the 9 live (tap, phase) weight blocks resident, 4 phase accumulators of Cout columns each
