@@ -1,5 +1,6 @@
 // Shared helpers for the lcgan_b200 kernels (sm_100a).
 #pragma once
+#include <mutex>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -138,6 +139,21 @@ __device__ __forceinline__ void load_window(unsigned char* sm, const T* __restri
     cp_async16(sm + pq * PITCH + (SWZ ? swz_slot(pq, v) : v) * 16, src, ok);
   }
 }
+
+// One-time initialisation PER DEVICE (cudaFuncSetAttribute applies to the current device only): run(f) calls f() the first
+// time it is reached with each current device and returns f's result for that device afterwards.
+struct DeviceOnce {
+  std::mutex m;
+  bool done[64] = {};
+  int result[64] = {};
+  template <class F> int run(F f) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return f();
+    std::lock_guard<std::mutex> g(m);
+    if (!done[dev]) { result[dev] = f(); done[dev] = true; }
+    return result[dev];
+  }
+};
 
 // thin.cu: special-shape kernels tried before the generic tiled ones (-1 = not applicable)
 int lcgan_thin_forward(const lcgan_tapconv& d, const void* x, const void* w, void* y, const float* rowscale,

@@ -1537,12 +1537,13 @@ static int tapconv_tc_launch(const lcgan_tapconv* d, const void* x, const void* 
   const int tiles_img = (d->N + p.nt - 1) / p.nt;          // (the small-channel modes reset nt to 1)
   if (int e = make_w_map(&tmw, w2, d->Cout, d->w_ld, p.rowshare == 4 ? cperiod : p.BN, p.kc)) return e;
 
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
+  static DeviceOnce once;
+  const cudaError_t attr_err = (cudaError_t)once.run([] {
+    cudaError_t attr_err = cudaSuccess;
     attr_err = cudaFuncSetAttribute(tapconv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (attr_err == cudaSuccess)
       attr_err = cudaFuncSetAttribute(tapconv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    return (int)attr_err;
   });
   LCGAN_CHECK(attr_err == cudaSuccess, "tapconv_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(attr_err));
   p.n_tiles = (d->Cout + p.BN - 1) / p.BN;
@@ -1551,8 +1552,8 @@ static int tapconv_tc_launch(const lcgan_tapconv* d, const void* x, const void* 
   static const int dbg = getenv("LCGAN_TC_DEBUG") ? atoi(getenv("LCGAN_TC_DEBUG")) : 0;
   p.dbg = dbg;
   static const bool no_lean = getenv("LCGAN_TC_NO_LEAN") != nullptr;
-  const bool lean = p.rowshare == 5 || !no_lean && p.n_tiles == 1 && p.BN == 32 && d->Cout == 32 && p.cblk == 0 && p.rowshare >= 2 &&
-                    !p.y_f32 && !residual && !p.noise && p.os == 1 && p.px == 0 && p.py == 0;
+  const bool lean = p.rowshare == 5 || (!no_lean && p.n_tiles == 1 && p.BN == 32 && d->Cout == 32 && p.cblk == 0 && p.rowshare >= 2 &&
+                    !p.y_f32 && !residual && !p.noise && p.os == 1 && p.px == 0 && p.py == 0);
   if (lean)
     tapconv_tc_kernel<true><<<grid, kFwdThreads, smem_bytes, (cudaStream_t)stream>>>(tmx, tmw, p, y, rowscale, bias, residual);
   else
@@ -1630,10 +1631,11 @@ extern "C" int lcgan_tapconv_wgrad_tc(const lcgan_tapconv* d, const void* x, con
       CUtensorMap tmgh, tmxh;
       if (int e = make_act_map(&tmgh, g, d->N, d->OH, d->OW, d->Cout, 8, 16, 1, 1, h.kcg, h.dyn ? 2 : 0, 0)) return e;
       if (int e = make_act_map(&tmxh, x, d->N, d->IH, d->IW, d->Cin, 8, 16, 1, 1, h.kcx, h.dyn ? 0 : 2, 2)) return e;
-      static std::once_flag once3;
-      static cudaError_t attr_err3 = cudaSuccess;
-      std::call_once(once3, [] {
+      static DeviceOnce once3;
+      const cudaError_t attr_err3 = (cudaError_t)once3.run([] {
+        cudaError_t attr_err3 = cudaSuccess;
         attr_err3 = cudaFuncSetAttribute(tapconv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+        return (int)attr_err3;
       });
       LCGAN_CHECK(attr_err3 == cudaSuccess, "tapconv_wgrad_halo: cannot raise dynamic shared memory: %s",
                   cudaGetErrorString(attr_err3));
@@ -1653,10 +1655,11 @@ extern "C" int lcgan_tapconv_wgrad_tc(const lcgan_tapconv* d, const void* x, con
     CUtensorMap tmg2, tmx2;
     if (int e = make_act_map(&tmg2, g, d->N, d->OH, d->OW, d->Cout, p.wt, p.ht, p.nt, d->os, p.kcg)) return e;
     if (int e = make_act_map(&tmx2, x, d->N, d->IH, d->IW, d->Cin, p.wt, p.ht, p.nt, d->is, p.kcx)) return e;
-    static std::once_flag once2;
-    static cudaError_t attr_err2 = cudaSuccess;
-    std::call_once(once2, [] {
+    static DeviceOnce once2;
+    const cudaError_t attr_err2 = (cudaError_t)once2.run([] {
+      cudaError_t attr_err2 = cudaSuccess;
       attr_err2 = cudaFuncSetAttribute(tapconv_wgrad_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tn_smem_bytes());
+      return (int)attr_err2;
     });
     LCGAN_CHECK(attr_err2 == cudaSuccess, "tapconv_wgrad_tn: cannot raise dynamic shared memory: %s",
                 cudaGetErrorString(attr_err2));
@@ -1669,10 +1672,11 @@ extern "C" int lcgan_tapconv_wgrad_tc(const lcgan_tapconv* d, const void* x, con
   CUtensorMap tmg, tmx;
   if (int e = make_act_map(&tmg, g, d->N, d->OH, d->OW, d->Cout, p.wt, p.ht, p.nt, d->os, p.kcg)) return e;
   if (int e = make_act_map(&tmx, x, d->N, d->IH, d->IW, d->Cin, p.wt, p.ht, p.nt, d->is, p.kcx)) return e;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
+  static DeviceOnce once;
+  const cudaError_t attr_err = (cudaError_t)once.run([] {
+    cudaError_t attr_err = cudaSuccess;
     attr_err = cudaFuncSetAttribute(tapconv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem_bytes());
+    return (int)attr_err;
   });
   LCGAN_CHECK(attr_err == cudaSuccess, "tapconv_wgrad_tc: cannot raise dynamic shared memory: %s",
               cudaGetErrorString(attr_err));

@@ -828,9 +828,9 @@ static int opt_in_smem(K kernel, int bytes) {
 }
 
 static int tile_kernels_ready() {
-  static std::once_flag once;
-  static int err = 0;
-  std::call_once(once, [] {
+  static DeviceOnce once;
+  return once.run([] {
+    int err = 0;
     err |= opt_in_smem(warp_tile_gather_kernel<bf16, false>, kFwdSmem);
     err |= opt_in_smem(warp_tile_gather_kernel<bf16, true>, kFwdSmem);
     err |= opt_in_smem(warp_tile_gather_kernel<bf16, false, true>, kFwdSmem);
@@ -842,8 +842,8 @@ static int tile_kernels_ready() {
     err |= opt_in_smem(warp_tile_gather_kernel<float, true>, kFwdSmem);
     err |= opt_in_smem(warp_tile_dx_kernel<bf16>, kDxSmem);
     err |= opt_in_smem(warp_tile_dx_kernel<float>, kDxSmem);
+    return err;
   });
-  return err;
 }
 
 static bool tile8() { static const bool on = getenv("LCGAN_WARP_TH16") == nullptr; return on; }
