@@ -35,6 +35,11 @@ for w in which:
         else:
             ms = timeit(lambda: ops.tapconv_wgrad(x, g, plan, C, C))
         print(f"{w:8s} {ms:8.3f} ms  {flops/ms/1e9:8.1f} TF/s  {nbytes/ms/1e6:8.0f} GB/s (algorithmic)")
+    elif w == "res32":
+        x = cl(torch.randn(N, 32, 512, 512, device=dev).bfloat16()); w2 = torch.randn(64, 32, device=dev).bfloat16()
+        y = ops.empty_cl(N, 64, 512, 512, torch.bfloat16, dev); res = cl(torch.randn(N, 64, 512, 512, device=dev).bfloat16())
+        ms = timeit(lambda: ops.tapconv(x, w2, y, plans.conv(1, 1, 512, 512), None, None, res, gain=0.7)); tr = x.numel() * 2 + 2 * y.numel() * 2
+        print(f"{w:8s} {ms:8.3f} ms  {tr/ms/1e6:8.0f} GB/s (algorithmic)")
     elif w == "up64":
         x = cl(torch.randn(N, 64, 512, 512, device=dev).bfloat16()); wp = torch.nn.Parameter(torch.randn(32, 64, 3, 3, device=dev))
         w2 = ops.pack_weight(wp, False, torch.bfloat16); wf = ops._derive(wp, ("up2f", torch.bfloat16)); plan = plans.conv_transpose_up2(3, 512, 512)
