@@ -301,6 +301,24 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
           mbar_expect_tx(&s.full[st], box_bytes, leader);
           tma_load_4d(s.a(st), &tmx, &s.full[st], 0, tw * 14 - 1, th * 8 - 1, tb, leader);
         }
+      } else if (p.rowshare == 6) {
+        // haloed STRIDE-2 mode (3x3, 32 input channels): the input is seen as [N, H, W/2, 2*32] - a PAIR of pixels is one
+        // 128-byte swizzle row - and ONE unit-stride box of (8+1) pairs x (2*16+1) rows per 8 x 16 lattice tile replaces
+        // nine element-stride-2 boxes (which fetch 64-byte pieces at 128-byte stride: 0.42 of HBM).  Tap (dy, dx) of
+        // lattice point (m, n) is input pixel (2m+dy-1, 2n+dx-1) = box row 2m+dy, pair n + ((dx+1)>>1), half (dx != 1):
+        // a descriptor start offset, with consecutive 8-pair groups two box rows apart (SBO).
+        mbar_expect_tx(s.wfull, 9 * wtile, leader);
+        for (int j = 0; j < 3; ++j)
+          for (int dyi = 0; dyi < 3; ++dyi)
+            tma_load_2d(s.wres + (j * 3 + dyi) * wtile, &tmw, s.wfull, p.grp_wtap[j][dyi] * p.Cin, 0, leader);
+        const uint32_t box_bytes = 9u * 33u * 128u;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++g) {
+          const int tw = tile & (p.tiles_w - 1), th = (tile >> p.lw) & (p.tiles_h - 1), tb = tile >> (p.lw + p.lh);
+          const int st = g % p.stages, ph = (g / p.stages) & 1;
+          mbar_wait(&s.empty[st], ph ^ 1);
+          mbar_expect_tx(&s.full[st], box_bytes, leader);
+          tma_load_4d(s.a(st), &tmx, &s.full[st], 0, tw * 8 - 1, th * 32 - 1, tb, leader);
+        }
       } else if (p.rowshare == 3) {
         // haloed small-channel mode: resident weights, and ONE TMA box per tile - the (wt+2) x (ht+2) pixel
         // neighbourhood of the 8 x 16 lattice tile.  Tap (dy, dx) is read by the MMA straight out of that
@@ -446,6 +464,36 @@ tapconv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
             if (p.kc == 64) {
               umma_f16(tacc, ad + 4, bd + 4, idesc5, 1, leader);
               umma_f16(tacc, ad + 6, bd + 6, idesc5, 1, leader);
+            }
+          }
+          umma_commit(&s.empty[st], leader);
+          umma_commit(&s.done[as], leader);
+        }
+      } else if (p.rowshare == 6) {
+        mbar_wait(s.wfull, 0);
+        const uint32_t pitch16 = 9 * 8;                                   // one box row of 9 pixel pairs, 16-byte units
+        const uint32_t w_tl = wtile >> 4;
+        const uint64_t bd0 = make_desc(smem_u32(s.wres), 16, 16 * 32, 32);      // weights: 64-byte rows (K = 32)
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li, ++g) {
+          if ((li & 1) != mine) continue;
+          const int as = li % kAccStages, aph = (li / kAccStages) & 1;
+          mbar_wait(&s.acc_empty[as], aph ^ 1);
+          const int st = g % p.stages, ph = (g / p.stages) & 1;
+          mbar_wait(&s.full[st], ph);
+          tc_fence_after();
+          const uint32_t tacc = tmem_base + (uint32_t)(as * kMaxBN);
+          // A: 128-byte rows (pixel pairs, SWIZZLE_128B); the wanted pixel is one half of the row = two K steps of it
+          const uint64_t ad0 = make_desc(smem_u32(s.a(st)), 16, 2 * 9 * 128, 64);
+          uint32_t first = 0;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+#pragma unroll
+            for (int dyi = 0; dyi < 3; ++dyi) {
+              const uint64_t ad = ad0 + (uint32_t)(dyi * pitch16 + ((j + 1) >> 1) * 8 + (j != 1 ? 4 : 0));
+              const uint64_t bd = bd0 + (uint32_t)((j * 3 + dyi) * w_tl);
+              umma_f16(tacc, ad, bd, idesc, first, leader);
+              umma_f16(tacc, ad + 2, bd + 2, idesc, 1, leader);
+              first = 1;
             }
           }
           umma_commit(&s.empty[st], leader);
@@ -1449,6 +1497,18 @@ static int tapconv_tc_launch(const lcgan_tapconv* d, const void* x, const void* 
     }
     full3x3 = seen == 0x1FF;
   }
+  // full 3x3 stride-2 tap set (input offsets -1, 0, +1 around 2m, 2n)?
+  bool s2_3x3 = false;
+  if (d->ntaps == 9 && d->is == 2 && d->os == 1) {
+    int seen = 0;
+    for (int t = 0; t < 9; ++t) {
+      const int dy = d->dy[t], dx = d->dx[t];
+      if (dy < -1 || dy > 1 || dx < -1 || dx > 1) { seen = -1; break; }
+      p.grp_wtap[dx + 1][dy + 1] = d->wtap[t];
+      seen |= 1 << ((dy + 1) * 3 + dx + 1);
+    }
+    s2_3x3 = seen == 0x1FF;
+  }
   p.rowshare = 0;
   p.wres_bytes = 0;
   int smem_bytes = fwd_smem_bytes();
@@ -1465,6 +1525,19 @@ static int tapconv_tc_launch(const lcgan_tapconv* d, const void* x, const void* 
     p.tiles_w = d->MW / p.wt; p.tiles_h = d->MH / p.ht;
     p.wres_bytes = (9 * cperiod * d->Cin * 2 + 1023) & ~1023;
     p.a_bytes = ((p.wt + 1) * (p.ht + 1) * p.kc * 2 + 1023) & ~1023;
+    p.b_bytes = 0;
+    p.stages = (kMaxSmem - 2048 - p.wres_bytes) / p.a_bytes;
+    if (p.stages > 12) p.stages = 12;
+    p.stages &= ~1;
+    smem_bytes = 1024 + p.wres_bytes + p.stages * p.a_bytes + 256;
+  } else if (s2_3x3 && d->Cin == 32 && d->Cout <= kMaxBN && d->MW % 8 == 0 && d->MH % 16 == 0 && d->IW == 2 * d->MW &&
+             d->IH == 2 * d->MH && cblk == 0 && getenv("LCGAN_NO_S2_HALO") == nullptr) {
+    // haloed stride-2 mode (see the producer): pixel pairs as 128-byte rows, one (8+1) x (32+1) box per tile
+    p.rowshare = 6;
+    p.wt = 8; p.ht = 16; p.nt = 1;
+    p.tiles_w = d->MW / p.wt; p.tiles_h = d->MH / p.ht;
+    p.wres_bytes = 9 * p.BN * d->Cin * 2;
+    p.a_bytes = (9 * 33 * 128 + 1023) & ~1023;
     p.b_bytes = 0;
     p.stages = (kMaxSmem - 2048 - p.wres_bytes) / p.a_bytes;
     if (p.stages > 12) p.stages = 12;
@@ -1532,6 +1605,10 @@ static int tapconv_tc_launch(const lcgan_tapconv* d, const void* x, const void* 
   for (p.lw = 0; (1 << p.lw) < p.tiles_w; ++p.lw) {}
   for (p.lh = 0; (1 << p.lh) < p.tiles_h; ++p.lh) {}
   CUtensorMap tmx, tmw;
+  if (p.rowshare == 6) {
+    // [N, IH, IW/2, 64]: the same bytes with pixel pairs as the innermost 64 "channels"; box 64 x (8+1) x (32+1)
+    if (int e = make_act_map(&tmx, x, d->N, d->IH, d->IW / 2, 64, 8, 32, 1, 1, 64, 1, 1)) return e;
+  } else
   if (int e = make_act_map(&tmx, x, d->N, d->IH, d->IW, d->Cin, p.wt, p.ht, p.nt, d->is, p.kc,
                            p.rowshare == 4 ? 1 : (p.rowshare ? 2 : 0), p.rowshare == 4 ? 1 : (p.rowshare == 3 ? 2 : 0))) return e;
   const int tiles_img = (d->N + p.nt - 1) / p.nt;          // (the small-channel modes reset nt to 1)

@@ -35,6 +35,11 @@ for w in which:
         else:
             ms = timeit(lambda: ops.tapconv_wgrad(x, g, plan, C, C))
         print(f"{w:8s} {ms:8.3f} ms  {flops/ms/1e9:8.1f} TF/s  {nbytes/ms/1e6:8.0f} GB/s (algorithmic)")
+    elif w == "s2_32":
+        x = cl(torch.randn(N, 32, 1024, 1024, device=dev).bfloat16()); w2 = torch.randn(64, 9 * 32, device=dev).bfloat16()
+        y = ops.empty_cl(N, 64, 512, 512, torch.bfloat16, dev); bias = torch.randn(64, device=dev)
+        ms = timeit(lambda: ops.tapconv(x, w2, y, plans.conv(3, 2, 1024, 1024), None, bias, None, slope=0.2, gain=1.4)); tr = x.numel() * 2 + y.numel() * 2
+        print(f"{w:8s} {ms:8.3f} ms  {tr/ms/1e6:8.0f} GB/s (algorithmic)")
     elif w == "res32":
         x = cl(torch.randn(N, 32, 512, 512, device=dev).bfloat16()); w2 = torch.randn(64, 32, device=dev).bfloat16()
         y = ops.empty_cl(N, 64, 512, 512, torch.bfloat16, dev); res = cl(torch.randn(N, 64, 512, 512, device=dev).bfloat16())

@@ -57,6 +57,9 @@ CASES = [  # kind, k, N, Cin, Cout, H, W
     # side of a tile, one tile per image, 16 / 64 output channels, many images, non-square maps
     ("s1", 3, 3, 32, 16, 16, 8), ("s1", 3, 2, 32, 64, 32, 16), ("s1", 3, 33, 64, 64, 16, 32), ("s1", 3, 2, 32, 32, 256, 256),
     ("s1", 3, 2, 64, 48, 64, 128),
+    # haloed stride-2 mode (3x3, 32 input channels, pixel pairs as 128-byte rows): one tile, many tiles, non-square,
+    # 32 / 128 output channels, odd image counts
+    ("s2", 3, 3, 32, 64, 64, 128), ("s2", 3, 2, 32, 32, 32, 16), ("s2", 3, 2, 32, 128, 64, 64), ("s2", 3, 5, 32, 64, 256, 256),
     # widths that are not multiples of the tile width, a single row of tiles, mixed 32 / 64 channel counts
     ("s1", 3, 3, 32, 32, 8, 24), ("s1", 3, 2, 64, 64, 24, 40), ("s1", 3, 1, 64, 32, 40, 72), ("s1", 3, 2, 32, 64, 8, 16),
     ("s1", 3, 5, 32, 32, 64, 1024),
