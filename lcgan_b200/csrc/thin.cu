@@ -539,20 +539,28 @@ skinny_linear_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const TWt*
 #pragma unroll
   for (int m = 0; m < 32; ++m) acc[m] = 0.f;
   const TWt* wr = w + (int64_t)(nlive ? n : 0) * d.w_ld;
+  static_assert(kThreads == kSkinnyKC, "the staging below gives thread t column t of the chunk");
   for (int k0 = 0; k0 < K; k0 += kSkinnyKC) {
     const int kc = min(kSkinnyKC, K - k0);
-    __syncthreads();
-    for (int i = threadIdx.x; i < 32 * kSkinnyKC; i += kThreads) {
-      const int m = i / kSkinnyKC, k = i - m * kSkinnyKC;
-      xs[m][k] = (m < M && k < kc) ? ldf(x + m * d.xs_n + (int64_t)(k0 + k) * d.xs_c) : 0.f;
-    }
-    __syncthreads();
+    // These layers are latency-, not bandwidth-bound (1 MB of weights, 64 KB of x; 24 us per launch in the graph-replay
+    // profile): the staging loop kept ~4 of its 32 loads per thread in flight.  All 32 x loads and the 8 weight loads
+    // are now issued before anything waits on them.
     float wv[kSkinnyKC / 32];
 #pragma unroll
     for (int j = 0; j < kSkinnyKC / 32; ++j) {
       const int k = lane + 32 * j;
       wv[j] = (nlive && k < kc) ? ldf(wr + k0 + k) : 0.f;
     }
+    float stage[32];
+    {
+      const int k = threadIdx.x;
+#pragma unroll
+      for (int m = 0; m < 32; ++m) stage[m] = (m < M && k < kc) ? ldf(x + m * d.xs_n + (int64_t)(k0 + k) * d.xs_c) : 0.f;
+    }
+    __syncthreads();                                          // the previous chunk is consumed
+#pragma unroll
+    for (int m = 0; m < 32; ++m) xs[m][threadIdx.x] = stage[m];
+    __syncthreads();
 #pragma unroll
     for (int j = 0; j < kSkinnyKC / 32; ++j) {
 #pragma unroll
@@ -686,14 +694,19 @@ pw_in32_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const void* __re
   }
   if (threadIdx.x < 32) bs[threadIdx.x] = bias ? bias[threadIdx.x] * d.bias_scale * d.gain : 0.f;
   __syncthreads();
+  // A thread computes the 64 bytes of one pixel, but a warp stores through a 2 KB transpose tile so that every store
+  // instruction writes 512 contiguous bytes: per-thread 16-byte stores at a 64-byte lane stride ran this kernel at
+  // 2.7 TB/s where the load-side mirror image (pw_out32) reaches 3.9 and fully coalesced passes 5+.
+  __shared__ uint4 tr[kThreads / 32][32 * 4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t hw = (uint32_t)d.MH * d.MW, rows = (uint32_t)d.N * hw, MW = d.MW;
-  for (uint32_t r = blockIdx.x * kThreads + threadIdx.x; r < rows; r += gridDim.x * kThreads) {
+  for (uint32_t rb = blockIdx.x * kThreads + warp * 32; rb < rows; rb += gridDim.x * kThreads) {
+    const uint32_t r = min(rb + lane, rows - 1);                                 // (lanes past the end recompute the last pixel)
     const uint32_t b = r / hw, p = r - b * hw, m = p / MW, n = p - m * MW;
     const TX* xp = x + (int64_t)b * d.xs_n + (int64_t)m * d.xs_h + (int64_t)n * d.xs_w;
     float xv[CI];
 #pragma unroll
     for (int c = 0; c < CI; ++c) xv[c] = c < d.Cin ? ldf(xp + c * d.xs_c) : 0.f;
-    uint4* yp = reinterpret_cast<uint4*>(y + (int64_t)r * 32);                  // dense channels-last: pixel r
     const uint4* rp = residual ? reinterpret_cast<const uint4*>(residual + (int64_t)r * 32) : nullptr;
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
@@ -715,8 +728,16 @@ pw_in32_kernel(const lcgan_tapconv d, const TX* __restrict__ x, const void* __re
       }
       Vec16<bf16> o;
       o.pack(f);
-      yp[v] = o.v;
+      tr[warp][lane * 4 + (v ^ ((lane >> 1) & 3))] = o.v;                       // XOR-swizzled slots: conflict-free both ways
     }
+    __syncwarp();
+    uint4* yw = reinterpret_cast<uint4*>(y + (int64_t)rb * 32);                 // dense channels-last: pixels rb .. rb+31
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = i * 32 + lane, px = idx >> 2, c = idx & 3;
+      if (rb + px < rows) yw[idx] = tr[warp][px * 4 + (c ^ ((px >> 1) & 3))];
+    }
+    __syncwarp();
   }
 }
 

@@ -35,6 +35,14 @@ for w in which:
         else:
             ms = timeit(lambda: ops.tapconv_wgrad(x, g, plan, C, C))
         print(f"{w:8s} {ms:8.3f} ms  {flops/ms/1e9:8.1f} TF/s  {nbytes/ms/1e6:8.0f} GB/s (algorithmic)")
+    elif w == "skinny":
+        x = torch.randn(32, 512, device=dev); wt = torch.randn(512, 512, device=dev); y = torch.empty(32, 512, device=dev); bias = torch.randn(512, device=dev)
+        x4, y4 = x.view(32, 512, 1, 1), y.view(32, 512, 1, 1)
+        ms = timeit(lambda: ops.tapconv(x4, wt, y4, plans.conv(1, 1, 1, 1), None, bias, None, slope=0.2, gain=1.4), n=50)
+        print(f"{w:8s} {ms*1e3:8.1f} us per launch (512 -> 512, 32 rows, fp32)")
+        g = torch.randn(32, 512, device=dev).view(32, 512, 1, 1)
+        ms = timeit(lambda: ops.tapconv_wgrad(x4, g, plans.conv(1, 1, 1, 1), 512, 512), n=50)
+        print(f"{w:8s} {ms*1e3:8.1f} us per launch (wgrad, incl. the zero fill)")
     elif w == "s2_32":
         x = cl(torch.randn(N, 32, 1024, 1024, device=dev).bfloat16()); w2 = torch.randn(64, 9 * 32, device=dev).bfloat16()
         y = ops.empty_cl(N, 64, 512, 512, torch.bfloat16, dev); bias = torch.randn(64, device=dev)
