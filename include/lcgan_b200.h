@@ -147,6 +147,15 @@ int lcgan_box3_cs(const void* a, const void* mask, void* out, const float* cs, f
 int lcgan_pool2(const void* x, void* y, int dt, int N, int H, int W, int C, float scale, void* stream);
 /* y[b,2i+a,2j+b,c] = scale * x[b,i,j,c]   (F.interpolate nearest x2, custom_layers.py:146; adjoint of pool2) */
 int lcgan_up2(const void* x, void* y, int dt, int N, int H, int W, int C, float scale, void* stream);
+/* out = a + scale * nearest_up2(s): s [N,H,W,C], a and out [N,2H,2W,C].  The gradient of a tensor that feeds both a layer
+ * (gradient a) and F.avg_pool2d(x, 2) (gradient s, scale .25) - DiscriminatorBlock's input, custom_layers.py:206-216 - in
+ * one pass instead of up2 + add. */
+int lcgan_up2_add(const void* a, const void* s, void* out, int dt, int N, int H, int W, int C, float scale, void* stream);
+
+/* out [N,H/2,W/2,C] = sum-pool2(box3(g)), g [N,H,W,C]: the gradient of the block skip `box_filter(upsample(skip))`
+ * (custom_layers.py:146-147,159) with respect to skip, in one pass. */
+int lcgan_box3_pool2(const void* g, void* out, int dt, int N, int H, int W, int C, void* stream);
+
 /* out = box3(nearest_up2(s)) + t   (custom_layers.py:146-147,159); s [N,H,W,C], t/out [N,2H,2W,C] */
 int lcgan_up2box_add(const void* s, const void* t, void* out, int dt, int N, int H, int W, int C, void* stream);
 

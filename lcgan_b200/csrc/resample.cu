@@ -327,6 +327,68 @@ up2_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int 
   }
 }
 
+// out = a + scale * nearest_up2(s) ; s [N,H,W,C], a / out [N,2H,2W,C]: the gradient of a tensor that feeds both a layer
+// (gradient a) and a 2x2 average pool (gradient s) in one pass - autograd's own route is up2 (write N) + add (read 2N,
+// write N).  IDX = uint32_t when the vector count fits (64-bit div / mod dominate these index-decoding kernels).
+template <typename T, int V, typename IDX>
+__global__ void __launch_bounds__(kThreads)
+up2_add_kernel(const T* __restrict__ a, const T* __restrict__ s, T* __restrict__ out, int N, int H, int W, int C,
+               float scale) {
+  const IDX cv = C / V, OH = H * 2, OW = W * 2;
+  const IDX total = (IDX)N * OH * OW * cv;
+  for (IDX idx = blockIdx.x * (IDX)kThreads + threadIdx.x; idx < total; idx += (IDX)gridDim.x * kThreads) {
+    const IDX c = (idx % cv) * V;
+    IDX p = idx / cv;
+    const IDX ox = p % OW; p /= OW;
+    const IDX oy = p % OH;
+    const IDX b = p / OH;
+    float f[V], g[V];
+    ldv<T, V>(a + (int64_t)idx * V, f);
+    ldv<T, V>(s + (((int64_t)b * H + oy / 2) * W + ox / 2) * C + c, g);
+#pragma unroll
+    for (int i = 0; i < V; ++i) f[i] = fmaf(g[i], scale, f[i]);
+    stv<T, V>(out + (int64_t)idx * V, f);
+  }
+}
+
+// out[y, x] = (1/9) sum_{i,j = -1..2} w_i w_j g[2y+i, 2x+j], w = (1,2,2,1), zeros outside: sum-pool2(box3(g)), the
+// gradient of box3(nearest_up2(.)), in one pass (box3 + pool2 separately: read N, write N, read N, write N/4)
+template <typename T, int V, typename IDX>
+__global__ void __launch_bounds__(kThreads)
+box3_pool2_kernel(const T* __restrict__ g, T* __restrict__ out, int N, int H, int W, int C) {
+  const IDX cv = C / V, OH = H / 2, OW = W / 2;
+  const IDX total = (IDX)N * OH * OW * cv;
+  for (IDX idx = blockIdx.x * (IDX)kThreads + threadIdx.x; idx < total; idx += (IDX)gridDim.x * kThreads) {
+    const IDX c = (idx % cv) * V;
+    IDX p = idx / cv;
+    const int ox = (int)(p % OW); p /= OW;
+    const int oy = (int)(p % OH);
+    const IDX b = p / OH;
+    float acc[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int i = -1; i <= 2; ++i) {
+      const int y = 2 * oy + i;
+      const float wy = (i == 0 || i == 1) ? 2.f : 1.f;
+#pragma unroll
+      for (int j = -1; j <= 2; ++j) {
+        const int x = 2 * ox + j;
+        const float wgt = wy * ((j == 0 || j == 1) ? 2.f : 1.f);
+        if (y >= 0 && y < H && x >= 0 && x < W) {
+          float f[V];
+          ldv<T, V>(g + (((int64_t)b * H + y) * W + x) * C + c, f);
+#pragma unroll
+          for (int k = 0; k < V; ++k) acc[k] = fmaf(f[k], wgt, acc[k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] *= (1.f / 9.f);
+    stv<T, V>(out + (int64_t)idx * V, acc);
+  }
+}
+
 // out = box3(nearest_up2(s)) + t ; s [N,H,W,C] -> out [N,2H,2W,C]
 template <typename T, int V>
 __global__ void __launch_bounds__(kThreads)
@@ -704,6 +766,41 @@ extern "C" int lcgan_up2(const void* x, void* y, int dt, int N, int H, int W, in
 #define CALL(T, V)                                                                              \
   up2_kernel<T, V><<<grid_for((int64_t)N * H * W * 4 * (C / V)), kThreads, 0, s>>>(             \
       (const T*)x, (T*)y, N, H, W, C, scale)
+  DISPATCH_TV(dt, C, CALL);
+#undef CALL
+  LCGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int lcgan_up2_add(const void* a, const void* sm, void* out, int dt, int N, int H, int W, int C, float scale,
+                             void* stream) {
+  LCGAN_CHECK(a && sm && out && N > 0 && H > 0 && W > 0 && C > 0, "up2_add: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+#define CALL(T, V)                                                                                       \
+  do {                                                                                                   \
+    const int64_t total_ = (int64_t)N * H * W * 4 * (C / V);                                             \
+    if (total_ < (1LL << 31) - (1LL << 24))                                                              \
+      up2_add_kernel<T, V, uint32_t><<<grid_for(total_), kThreads, 0, s>>>((const T*)a, (const T*)sm, (T*)out, N, H, W, C, scale); \
+    else                                                                                                 \
+      up2_add_kernel<T, V, int64_t><<<grid_for(total_), kThreads, 0, s>>>((const T*)a, (const T*)sm, (T*)out, N, H, W, C, scale);  \
+  } while (0)
+  DISPATCH_TV(dt, C, CALL);
+#undef CALL
+  LCGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int lcgan_box3_pool2(const void* g, void* out, int dt, int N, int H, int W, int C, void* stream) {
+  LCGAN_CHECK(g && out && N > 0 && H > 0 && W > 0 && C > 0 && H % 2 == 0 && W % 2 == 0, "box3_pool2: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+#define CALL(T, V)                                                                                       \
+  do {                                                                                                   \
+    const int64_t total_ = (int64_t)N * (H / 2) * (W / 2) * (C / V);                                     \
+    if (total_ < (1LL << 31) - (1LL << 24))                                                              \
+      box3_pool2_kernel<T, V, uint32_t><<<grid_for(total_), kThreads, 0, s>>>((const T*)g, (T*)out, N, H, W, C); \
+    else                                                                                                 \
+      box3_pool2_kernel<T, V, int64_t><<<grid_for(total_), kThreads, 0, s>>>((const T*)g, (T*)out, N, H, W, C);  \
+  } while (0)
   DISPATCH_TV(dt, C, CALL);
 #undef CALL
   LCGAN_LAUNCH_CHECK();

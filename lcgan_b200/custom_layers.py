@@ -241,9 +241,9 @@ class DiscriminatorBlock(nn.Module):
     def forward(self, x):
         x = _as_act(x)
         if self.skip:
+            x, pooled = ops.PoolFork.apply(x, 0.25)                            # (x, avg_pool2d(x, 2)): one backward node
             t = self.conv0(x, slope=0.2, gain=float(self.gain), box=True)      # conv -> lrelu * sqrt2 -> box filter
             t = self.conv1(t, slope=0.2)
-            pooled = ops.Pool2.apply(x, 0.25)
             # skip*sqrt(.5) + t, with the add fused into the (activation-free) skip conv epilogue
             return self.skip_layer(pooled, gain=float(self.skip_gain), residual=t)
         t = self.conv0(x, slope=0.2)

@@ -822,6 +822,53 @@ class Pool2(torch.autograd.Function):
         return Up2.apply(dy, ctx.scale), None
 
 
+class AddUp2(torch.autograd.Function):
+    """out = a + scale * nearest_up2(s): the two gradients of a pooled-and-used tensor summed in one pass."""
+
+    @staticmethod
+    def forward(ctx, a, s, scale):
+        _need_cuda(a, s)
+        a, s = _cl(a), _cl(s)
+        n, c, h, w = s.shape
+        ctx.scale = scale
+        out = torch.empty_like(a)
+        _lib.call("lcgan_up2_add", _ptr(a), _ptr(s), _ptr(out), _dt(a), n, h, w, c, C.c_float(scale), _stream(a),
+                  nbytes=2.25 * a.numel() * a.element_size())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, (Pool2.apply(g, ctx.scale) if ctx.needs_input_grad[1] else None), None
+
+
+class PoolFork(torch.autograd.Function):
+    """(x, scale * sumpool2x2(x)): the input of a block that uses x AND its 2x2 average (DiscriminatorBlock,
+    custom_layers.py:206-216).  As ONE node with two outputs its backward receives the two gradients separately and
+    adds them in a single pass (AddUp2) - autograd's own sum of the two branches costs up2 (write N) + add (read 2N,
+    write N); every piece is again a Function, so the R1 double backward goes through our kernels."""
+
+    @staticmethod
+    def forward(ctx, x, scale):
+        _need_cuda(x)
+        xc = _cl(x)
+        n, c, h, w = xc.shape
+        ctx.scale = scale
+        pooled = empty_cl(n, c, h // 2, w // 2, xc.dtype, xc.device)
+        _lib.call("lcgan_pool2", _ptr(xc), _ptr(pooled), _dt(xc), n, h, w, c, C.c_float(scale), _stream(xc),
+                  nbytes=1.25 * xc.numel() * xc.element_size())
+        return xc.view_as(xc), pooled
+
+    @staticmethod
+    def backward(ctx, g_main, g_pool):
+        if g_pool is None:
+            return g_main, None
+        if g_main is None:
+            return Up2.apply(g_pool, ctx.scale), None
+        if g_main.dtype != g_pool.dtype:
+            return g_main + Up2.apply(g_pool, ctx.scale).to(g_main.dtype), None
+        return AddUp2.apply(g_main, g_pool, ctx.scale), None
+
+
 class Up2(torch.autograd.Function):
     """y[2i+a, 2j+b] = scale * x[i, j]; adjoint is Pool2."""
 
@@ -951,12 +998,8 @@ class Up2BoxAdd(torch.autograd.Function):
         n, c, h, w = dy.shape
         ds = None
         if ctx.needs_input_grad[0]:
-            tmp = torch.empty_like(dy)
-            _lib.call("lcgan_box3", _ptr(dy), None, _ptr(tmp), _dt(dy), n, h, w, c,
-                      C.c_float(1.0), C.c_float(1.0), C.c_float(1.0), C.c_float(1.0), _stream(dy),
-                      nbytes=2 * dy.numel() * dy.element_size())
             ds = empty_cl(n, c, h // 2, w // 2, dy.dtype, dy.device)
-            _lib.call("lcgan_pool2", _ptr(tmp), _ptr(ds), _dt(dy), n, h, w, c, C.c_float(1.0), _stream(dy),
+            _lib.call("lcgan_box3_pool2", _ptr(dy), _ptr(ds), _dt(dy), n, h, w, c, _stream(dy),
                       nbytes=1.25 * dy.numel() * dy.element_size())
         return ds, (dy if ctx.needs_input_grad[1] else None)
 

@@ -321,3 +321,37 @@ def test_inference_runner_matches_reference_golden(golden_dir, name, mode):
     with torch.no_grad():
         ref2 = G(z["rand1"], z["rand2"], 0.7)
     assert rel_l2(img2, ref2) < 1e-6 and rel_l2(img2, img) > 1e-3
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("shape", [(2, 32, 16, 32), (3, 64, 8, 8), (1, 16, 4, 6)])
+def test_pool_fork_first_and_second_order(mode, shape):
+    """ops.PoolFork (the discriminator block's input: x and avg_pool2d(x, 2) as one node whose backward adds the two
+    gradients in a single pass, custom_layers.py:206-216) against torch, including the double backward R1 takes."""
+    from lcgan_b200 import ops
+    ops.set_precision(mode)
+    dt = ops.act_dtype()
+    tol = 1e-5 if mode == "fp32" else 1e-2
+    torch.manual_seed(3)
+    x0 = torch.randn(*shape, device="cuda")
+    w1 = torch.randn(*shape, device="cuda")
+    w2 = torch.randn(shape[0], shape[1], shape[2] // 2, shape[3] // 2, device="cuda")
+
+    def run(ours):
+        x = x0.clone().to(dt if ours else torch.float32).requires_grad_()
+        if ours:
+            xm, pooled = ops.PoolFork.apply(x.contiguous(memory_format=torch.channels_last), 0.25)
+        else:
+            xm, pooled = x, F.avg_pool2d(x, 2)
+        y = (xm.float() * w1).tanh().sum() + (pooled.float() * w2).tanh().sum() * 3.0
+        (g,) = torch.autograd.grad(y, x, create_graph=True)
+        pen = g.float().square().sum()
+        (gg,) = torch.autograd.grad(pen, x)
+        return pooled.float().detach(), g.float().detach(), gg.float().detach()
+
+    try:
+        ours, ref = run(True), run(False)
+    finally:
+        ops.set_precision("bf16")
+    for a, b, name in zip(ours, ref, ("pooled", "grad", "grad of the gradient penalty")):
+        assert rel_l2(a, b) < tol, (name, rel_l2(a, b))
