@@ -663,6 +663,34 @@ template <typename T> constexpr int vec_of() { return Vec16<T>::N; }
 
 }  // namespace
 
+// The flow fields (2 fp32 channels, custom_layers.py:150-151: box_filter(flow)): one thread per pixel, float2 taps,
+// 32-bit indices.  The generic scalar kernel spent ~125 us per launch on them (64-bit div / mod per element, one
+// channel per thread): 5 ms per iteration at 1024^2.
+__global__ void __launch_bounds__(kThreads)
+box3_c2_kernel(const float2* __restrict__ a, float2* __restrict__ out, int N, int H, int W) {
+  const uint32_t total = (uint32_t)N * H * W;
+  for (uint32_t idx = blockIdx.x * kThreads + threadIdx.x; idx < total; idx += gridDim.x * kThreads) {
+    const int x = (int)(idx % (uint32_t)W);
+    const uint32_t t = idx / (uint32_t)W;
+    const int y = (int)(t % (uint32_t)H);
+    const float2* img = a + (size_t)(t / (uint32_t)H) * H * W;
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int yy = y + dy;
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int xx = x + dx;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+          const float2 v = img[(size_t)yy * W + xx];
+          acc.x += v.x; acc.y += v.y;
+        }
+      }
+    }
+    out[idx] = make_float2(acc.x * (1.f / 9.f), acc.y * (1.f / 9.f));
+  }
+}
+
 // the tiled kernel for every flavour (mask / style / reduction / post-mask); bf16 windows arrive by TMA
 static void launch_box_tile(const void* a, const void* mask, void* out, int dt, int N, int H, int W, int C, float pre_slope,
                             float pre_gain, float post_slope, float post_gain, const float* cs, float* red,
@@ -692,6 +720,10 @@ extern "C" int lcgan_box3(const void* a, const void* mask, void* out, int dt, in
   LCGAN_CHECK(a && out && N > 0 && H > 0 && W > 0 && C > 0, "box3: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
   const int cc = dt == LCGAN_BF16 ? 32 : 16;
+  if (dt == LCGAN_F32 && C == 2 && !mask && pre_slope == 1.f && pre_gain == 1.f && post_slope == 1.f && post_gain == 1.f &&
+      (int64_t)N * H * W < (1LL << 31) - (1LL << 24) && (uintptr_t)a % 8 == 0 && (uintptr_t)out % 8 == 0) {
+    box3_c2_kernel<<<grid_for((int64_t)N * H * W), kThreads, 0, s>>>((const float2*)a, (float2*)out, N, H, W);
+  } else
   if ((dt == LCGAN_BF16 || dt == LCGAN_F32) && C % cc == 0 && W >= kBoxTW && H >= kBoxTH &&
       getenv("LCGAN_BOX_NO_TILE") == nullptr) {
     launch_box_tile(a, mask, out, dt, N, H, W, C, pre_slope, pre_gain, post_slope, post_gain, nullptr, nullptr, nullptr, s);

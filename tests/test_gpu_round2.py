@@ -355,3 +355,19 @@ def test_pool_fork_first_and_second_order(mode, shape):
         ops.set_precision("bf16")
     for a, b, name in zip(ours, ref, ("pooled", "grad", "grad of the gradient penalty")):
         assert rel_l2(a, b) < tol, (name, rel_l2(a, b))
+
+
+@pytest.mark.parametrize("shape", [(3, 2, 40, 24), (1, 2, 8, 8), (5, 2, 128, 256)])
+def test_box3_flow_field_kernel(shape):
+    """Box filter of the 2-channel fp32 flow field (custom_layers.py:150-151) - its own one-thread-per-pixel kernel -
+    against F.avg_pool2d(3, 1, 1) (which divides by 9 on the border too), forward and backward (self-adjoint)."""
+    from lcgan_b200 import ops, _lib
+    torch.manual_seed(5)
+    x = torch.randn(*shape, device="cuda").contiguous(memory_format=torch.channels_last).requires_grad_()
+    g = torch.randn(*shape, device="cuda")
+    y = ops.Box3.apply(x)
+    y.backward(g)
+    xr = x.detach().clone().requires_grad_()
+    yr = F.avg_pool2d(xr, 3, 1, 1)
+    yr.backward(g)
+    assert rel_l2(y, yr) < 1e-6 and rel_l2(x.grad, xr.grad) < 1e-6
