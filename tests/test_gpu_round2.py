@@ -367,7 +367,10 @@ def test_box3_flow_field_kernel(shape):
     g = torch.randn(*shape, device="cuda")
     y = ops.Box3.apply(x)
     y.backward(g)
-    xr = x.detach().clone().requires_grad_()
+    xr = x.detach().contiguous().clone().requires_grad_()            # (plain NCHW for the torch reference)
     yr = F.avg_pool2d(xr, 3, 1, 1)
     yr.backward(g)
-    assert rel_l2(y, yr) < 1e-6 and rel_l2(x.grad, xr.grad) < 1e-6
+    assert rel_l2(y, yr) < 1e-6, rel_l2(y, yr)
+    # the filter is self-adjoint: the gradient is the filtered upstream gradient
+    assert rel_l2(x.grad, F.avg_pool2d(g, 3, 1, 1)) < 1e-6, rel_l2(x.grad, F.avg_pool2d(g, 3, 1, 1))
+    assert rel_l2(x.grad, xr.grad) < 1e-6, rel_l2(x.grad, xr.grad)
