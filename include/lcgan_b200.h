@@ -269,6 +269,12 @@ int lcgan_epilogue_grads(const float* r0, const float* r1, const float* bias, co
  * Kernels launched in this mode must not run concurrently on two streams. */
 int lcgan_set_deterministic(int on);
 
+/* Debug: raw tcgen05 / TMA issue rates (scratch/rates.py).  mode 0 / 1: `iters` back-to-back M=128 x n x K=16 MMAs with
+ * K-major / MN-major shared-memory operands; mode 2: `iters` TMA loads of a 16 x ht box of act [N,H,W,C] into a 4-slot
+ * ring.  out_cycles[block] = elapsed SM clocks.  Not used by the product path. */
+int lcgan_debug_tc_rate(int mode, int n, int iters, const void* act, int N, int H, int W, int C, int ht,
+                        long long* out_cycles, int blocks, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

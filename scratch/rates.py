@@ -12,7 +12,7 @@ for Cc in (64,32):
     x=torch.randn(32,1024,1024,Cc,device=dev).bfloat16() if Cc==32 else torch.randn(32,512,512,Cc,device=dev).bfloat16()
     H=x.shape[1]
     for mode in (0,1):
-        for n in (16,32,64,128,256):
+        for n in (16,32,64,96,128,192,256):
             if mode==1 and Cc==32: continue
             it=4096
             rc=fn(mode,n,it,x.data_ptr(),32,H,H,Cc,8,out.data_ptr(),148,st); torch.cuda.synchronize()
