@@ -35,6 +35,10 @@ for w in which:
         else:
             ms = timeit(lambda: ops.tapconv_wgrad(x, g, plan, C, C))
         print(f"{w:8s} {ms:8.3f} ms  {flops/ms/1e9:8.1f} TF/s  {nbytes/ms/1e6:8.0f} GB/s (algorithmic)")
+    elif w == "up2box":
+        sk = cl(torch.randn(N, 32, 512, 512, device=dev).bfloat16()); t = cl(torch.randn(N, 32, 1024, 1024, device=dev).bfloat16())
+        ms = timeit(lambda: ops.Up2BoxAdd.apply(sk, t)); tr = (sk.numel() + 2 * t.numel()) * 2
+        print(f"{w:8s} {ms:8.3f} ms  {tr/ms/1e6:8.0f} GB/s (algorithmic)")
     elif w == "skinny":
         x = torch.randn(32, 512, device=dev); wt = torch.randn(512, 512, device=dev); y = torch.empty(32, 512, device=dev); bias = torch.randn(512, device=dev)
         x4, y4 = x.view(32, 512, 1, 1), y.view(32, 512, 1, 1)
