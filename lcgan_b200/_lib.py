@@ -116,6 +116,8 @@ _SIGS = {
                        C.c_float, C.c_float, C.c_float, C.c_float, _VOIDP], C.c_int),
     "lcgan_pool2": ([_VOIDP, _VOIDP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _VOIDP], C.c_int),
     "lcgan_up2": ([_VOIDP, _VOIDP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _VOIDP], C.c_int),
+    "lcgan_debug_tc_rate": ([C.c_int, C.c_int, C.c_int, _VOIDP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _VOIDP, C.c_int,
+                             _VOIDP], C.c_int),
     "lcgan_up2_add": ([_VOIDP, _VOIDP, _VOIDP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _VOIDP], C.c_int),
     "lcgan_box3_pool2": ([_VOIDP, _VOIDP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _VOIDP], C.c_int),
     "lcgan_up2box_add": ([_VOIDP, _VOIDP, _VOIDP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _VOIDP], C.c_int),

@@ -91,9 +91,19 @@ def _ptr(t):
 
 
 def _need_cuda(*ts):
+    """Every op is a launch on the CURRENT device with a stream taken from its tensors: refuse CPU tensors (there is no
+    fallback) and tensors of another device (one process per GPU, as in the reference)."""
+    cur = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("lcgan_b200 ops need CUDA tensors (there is no CPU fallback)")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise RuntimeError(f"lcgan_b200 ops launch on the current device (cuda:{cur}); got a tensor on {t.device} - "
+                               "call torch.cuda.set_device() first (one process per GPU)")
 
 
 def _cl(x: torch.Tensor, dtype=None) -> torch.Tensor:
